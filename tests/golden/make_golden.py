@@ -1,0 +1,82 @@
+"""Regenerates tests/golden/*.npz.  Runs ONLY in the build container (needs /root/reference):
+
+  * extractor vectors come from the reference's own ORBextractor.cpp, compiled unmodified against
+    oracle/cvshim with the canonical flags/allocator (oracle/_ref/libref_canonical.so, see oracle/Makefile);
+  * stereo vectors come from the reference's own Frame class, imported unchanged from /root/reference/Frame.py
+    and constructed exactly like Tracking.grab_image_stereo does (Tracking.py:95-112), on top of those
+    extractors -- so mvuRight / mvDepth are produced by Frame.compute_stereo_matches itself.
+
+Usage: python tests/golden/make_golden.py
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+import cv2  # noqa: E402
+from Frame import Frame  # noqa: E402  (the reference's own class)
+
+from oracle.refext import RefExtractor  # noqa: E402
+from pyorbslam_b200.synthetic import make_stereo_pair, pair_digest  # noqa: E402
+
+
+def sha(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def frame_args(fx, fy, cx, cy, W, H):   # Tracking.py:97-109 with zero distortion (bounds = image rectangle)
+    return [fx, fy, cx, cy, 1.0 / fx, 1.0 / fy, 64.0 / W, 48.0 / H, 0.0, float(W), 0.0, float(H), 48, 64]
+
+
+def stereo_case(name, idx, H, W, params, fx, fy, cx, cy, mbf):
+    L, R = make_stereo_pair(idx, H, W)
+    eL, eR = RefExtractor(*params), RefExtractor(*params)
+    mK = np.eye(3, dtype=np.float32)
+    mK[0, 0], mK[1, 1], mK[0, 2], mK[1, 2] = fx, fy, cx, cy
+    f = Frame(L, R, 0.0, eL, eR, None, mK, np.zeros((4, 1), np.float32), mbf, mbf * 35 / fx, frame_args(fx, fy, cx, cy, W, H))
+    kL = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in f.mvKeys], np.float32)
+    kR = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in f.mvKeysRight], np.float32)
+    uR = np.array([float(v) for v in f.mvuRight], np.float64)
+    dep = np.array([float(v) for v in f.mvDepth], np.float64)
+    np.savez_compressed(os.path.join(HERE, name), idx=idx, H=H, W=W, params=np.array(params, np.float64),
+                        fx=fx, fy=fy, cx=cx, cy=cy, mbf=mbf, image_digest=pair_digest(L, R),
+                        kpsL=kL, descL=f.mDescriptors, kpsR=kR, descR=f.mDescriptorsRight, uRight=uR, depth=dep)
+    print(name, "N", f.N, "matched", int((uR >= 0).sum()))
+
+
+def main():
+    # config 1: the bundled fixture image (8-bit gray 1226x370), test.py parameters
+    src = os.path.join(REF, "pyORBExtractor", "kitti06-436.png")
+    img = cv2.imread(src, cv2.IMREAD_UNCHANGED)
+    assert img.shape == (370, 1226) and img.dtype == np.uint8
+    np.save(os.path.join(HERE, "kitti06-436.gray.npy"), img)   # raw pixels; avoids needing a PNG decoder on the box
+    e = RefExtractor(2000, 1.2, 8, 20, 7)
+    k, d = e.extract_arrays(img)
+    pyr = e.GetImagePyramid()
+    np.savez_compressed(os.path.join(HERE, "kitti06_extract.npz"), kps=k, desc=d,
+                        level_sizes=np.array([p.shape for p in pyr]), pyramid_view_sha=np.array([sha(p) for p in pyr]))
+    print("kitti06", len(k))
+    # config 2: KITTI00-02 camera (configs/KITTI00-02.yaml:7-24)
+    stereo_case("stereo_kitti_shape.npz", 0, 376, 1241, (2000, 1.2, 8, 20, 7), 718.856, 718.856, 607.1928, 185.2157, 386.1448)
+    stereo_case("stereo_small.npz", 7, 240, 640, (1000, 1.2, 6, 20, 7), 500.0, 500.0, 320.0, 120.0, 100.0)
+    # config 4 (digests only: the arrays would be ~0.5 MB); input = left view of synthetic pair 4 at 2560x1440
+    big, _ = make_stereo_pair(4, 1440, 2560)
+    e4 = RefExtractor(8000, 1.2, 12, 20, 7)
+    k4, d4 = e4.extract_arrays(big)
+    np.savez_compressed(os.path.join(HERE, "hires_extract_digest.npz"), image_sha=sha(big), n=len(k4), kps_sha=sha(k4),
+                        desc_sha=sha(d4), per_level=np.bincount(k4[:, 5].astype(int), minlength=12))
+    print("hires", len(k4))
+
+
+if __name__ == "__main__":
+    main()
