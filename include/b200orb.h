@@ -1,0 +1,145 @@
+/* b200orb -- C ABI of the B200-native stereo ORB front-end.
+ *
+ * Drop-in boundary for ONE hot path of M2219/pyOrbSLAM: ORB extraction of the left and right image plus
+ * Frame.compute_stereo_matches.  Every entry point names the reference interface it replaces
+ * (paths relative to the reference root).  Plain pointers and sizes only; no torch / pybind types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B200ORB_E_* code on failure;
+ *     b200orb_last_error() returns the message of the last failure on the calling thread.
+ *   - "kps" arrays are float[n][6] = (x, y, size, angle, response, octave): the tuple layout of the
+ *     reference's cv::KeyPoint caster (pyORBExtractor/opencv_type_casters.h:107).
+ *   - "desc" arrays are uint8[n][32] (256-bit rBRIEF), row i belongs to keypoint i
+ *     (pyORBExtractor/ORBextractor.cpp:1067,1087-1088).
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with B200ORB_E_CUDA.
+ */
+#ifndef B200ORB_H
+#define B200ORB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ORB_OK 0
+#define B200ORB_E_ARG (-1)      /* bad argument / unsupported geometry */
+#define B200ORB_E_CUDA (-2)     /* CUDA runtime error (incl. no device) */
+#define B200ORB_E_STATE (-3)    /* call order violated (e.g. results requested before extract) */
+#define B200ORB_E_RANGE (-4)    /* stereo: a keypoint row / SAD window leaves the pyramid (reference raises) */
+
+#define B200ORB_MAX_LEVELS 16
+
+const char* b200orb_last_error(void);
+int b200orb_version(void);
+/* number of CUDA devices visible; <= 0 means the product cannot run here */
+int b200orb_device_count(void);
+/* kernels launched by this library since load (all contexts); bench.py reports the delta as gpu_launches */
+long long b200orb_kernel_launches(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Single-image extractor object == ORB_SLAM2::ORBextractor
+ * (pyORBExtractor/ORBextractor.h:45-113, bound at pyORBExtractor/orb_extractor.cpp:22-38)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct b200orb_extractor b200orb_extractor;
+
+/* ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)  -- ORBextractor.cpp:410-470 */
+int b200orb_extractor_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
+                             int device, b200orb_extractor** out);
+void b200orb_extractor_destroy(b200orb_extractor* e);
+
+/* GetLevels / GetScaleFactor / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares  -- ORBextractor.h:62-82; each array has GetLevels() entries */
+int b200orb_get_levels(const b200orb_extractor* e);
+float b200orb_get_scale_factor(const b200orb_extractor* e);
+int b200orb_get_scale_factors(const b200orb_extractor* e, float* out);
+int b200orb_get_inverse_scale_factors(const b200orb_extractor* e, float* out);
+int b200orb_get_scale_sigma_squares(const b200orb_extractor* e, float* out);
+int b200orb_get_inverse_scale_sigma_squares(const b200orb_extractor* e, float* out);
+/* per-level feature quota (mnFeaturesPerLevel, ORBextractor.cpp:435-446) -- diagnostic */
+int b200orb_get_features_per_level(const b200orb_extractor* e, int* out);
+
+/* operator_kd(image) -- ORBextractor.cpp:1042-1104 via orb_extractor.cpp:31-38.
+ * image: host uint8[H][W], C-contiguous (CV_8UC1).  Writes the keypoint count to *n_keypoints and keeps
+ * the results (and the pyramid) resident on the device until the next call.  H == 0 or W == 0 -> 0 keypoints. */
+int b200orb_extract(b200orb_extractor* e, const uint8_t* image, int H, int W, int* n_keypoints);
+/* copies of the last results: kps float[n][6], desc uint8[n][32] (either may be NULL) */
+int b200orb_get_results(b200orb_extractor* e, float* kps, uint8_t* desc);
+/* upper bound of keypoints one call can return for the current image size (>= nfeatures) */
+int b200orb_max_keypoints(const b200orb_extractor* e);
+
+/* GetImagePyramid() -- ORBextractor.h:84-86 through the Mat->ndarray caster, which copies rows*cols
+ * CONTIGUOUS bytes from the level's ROI start inside its (w+38)-pitch bordered buffer
+ * (opencv_type_casters.h:230-239): out[r*w + c] = bordered.flat[19*(w+38) + 19 + r*w + c].
+ * That sheared view is what Frame.compute_stereo_matches reads; we return exactly it. */
+int b200orb_level_size(const b200orb_extractor* e, int level, int* w, int* h);
+int b200orb_get_pyramid_level(b200orb_extractor* e, int level, uint8_t* out /* h*w bytes */);
+/* the true level image (dense h*w copy of the ROI) and its 7x7 sigma-2 blur -- diagnostics / parity tests */
+int b200orb_get_level_image(b200orb_extractor* e, int level, int blurred, uint8_t* out /* h*w bytes */);
+/* FAST candidates fed to DistributeOctTree for one level, int[cap][3] = (x, y, response), coordinates
+ * relative to the (16,16) detection origin, in the reference's order (ORBextractor.cpp:788-828); returns count */
+int b200orb_get_level_candidates(b200orb_extractor* e, int level, int cap, int* out, int* n);
+
+/* ---------------------------------------------------------------------------------------------
+ * Frame.compute_stereo_matches -- Frame.py:161-279
+ * ------------------------------------------------------------------------------------------- */
+/* device-resident form: uses the keypoints, descriptors and pyramids left on the device by the last
+ * b200orb_extract of `left` and `right` (Frame.__init__ order: ExtractORB x2, then compute_stereo_matches,
+ * Frame.py:48-65).  mbf = Camera.bf (python float), fx = mK[0][0] (float32).
+ * uRight/depth: float[nLeft], -1 = no match (Frame.py:163-164,277-278).  matchIdx (optional): index of the
+ * Hamming winner in the right image, -1 if bestDist >= (TH_HIGH+TH_LOW)/2 (Frame.py:203-222). */
+int b200orb_stereo(b200orb_extractor* left, b200orb_extractor* right, double mbf, float fx,
+                   float* uRight, float* depth, int* matchIdx);
+
+/* general form on caller-supplied host data (any keypoints, e.g. the stereo-only sweep):
+ * kps*: float[n][3] = (x, y, octave); pyr*: nlevels pointers to the GetImagePyramid() views, level l is
+ * uint8[lh[l]][lw[l]]; sf/isf: GetScaleFactors()/GetInverseScaleFactors(). */
+int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t* descL,
+                        int nRight, const float* kpsR, const uint8_t* descR,
+                        int nlevels, const float* sf, const float* isf,
+                        const uint8_t* const* pyrL, const uint8_t* const* pyrR, const int* lw, const int* lh,
+                        double mbf, float fx, float* uRight, float* depth, int* matchIdx);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched stereo front-end (throughput API): what Tracking.grab_image_stereo -> Frame.__init__ does for
+ * one pair (Tracking.py:95-112, Frame.py:48-65), for n_pairs independent pairs per call.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct b200orb_batch b200orb_batch;
+
+int b200orb_batch_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
+                         int H, int W, int max_pairs, int device, b200orb_batch** out);
+void b200orb_batch_destroy(b200orb_batch* b);
+int b200orb_batch_max_pairs(const b200orb_batch* b);
+/* row capacity of every per-image output array (>= any possible keypoint count) */
+int b200orb_batch_kp_capacity(const b200orb_batch* b);
+/* bytes of device workspace held by the batch object */
+long long b200orb_batch_workspace_bytes(const b200orb_batch* b);
+
+/* Inputs already in device memory: left/right uint8[n_pairs][H][W].  Outputs in device memory, caller-
+ * allocated with C = b200orb_batch_kp_capacity():
+ *   kps   float[2][n_pairs][C][6]   (index 0 = left images, 1 = right images)
+ *   desc  uint8[2][n_pairs][C][32]
+ *   nkp   int32[2][n_pairs]
+ *   uRight, depth  float[n_pairs][C];  matchIdx int32[n_pairs][C]   (entries >= nkp[0][p] are unspecified)
+ * Asynchronous on `stream` (a cudaStream_t, may be NULL for the default stream). */
+int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint8_t* d_right, int n_pairs,
+                             double mbf, float fx, float* d_kps, uint8_t* d_desc, int32_t* d_nkp,
+                             float* d_uRight, float* d_depth, int32_t* d_matchIdx, void* stream);
+
+/* Same work with HOST buffers (pinned recommended): chunks of max_pairs pairs are uploaded, processed and
+ * downloaded with copy/compute overlap.  n_pairs may exceed max_pairs.  Host outputs use the device layout
+ * with n_pairs = the whole job: kps float[2][n_pairs][C][6], desc uint8[2][n_pairs][C][32], nkp int32[2][n_pairs],
+ * uRight/depth float[n_pairs][C], matchIdx int32[n_pairs][C] (matchIdx may be NULL).
+ * Synchronous: returns when all outputs are in host memory. */
+int b200orb_batch_run_host(b200orb_batch* b, const uint8_t* h_left, const uint8_t* h_right, int n_pairs,
+                           double mbf, float fx, float* h_kps, uint8_t* h_desc, int32_t* h_nkp,
+                           float* h_uRight, float* h_depth, int32_t* h_matchIdx);
+
+/* pinned host memory helpers for callers without their own allocator */
+int b200orb_host_alloc(void** p, size_t bytes);
+int b200orb_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ORB_H */

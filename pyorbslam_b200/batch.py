@@ -1,0 +1,78 @@
+"""Batched stereo front-end (throughput API): N independent stereo pairs per call, everything on the device.
+
+PyTorch is used only for device/pinned buffers and the stream handle; the work is libb200orb's kernels."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class StereoFrontend:
+    """What Tracking.grab_image_stereo -> Frame.__init__ computes per pair (Tracking.py:95-112, Frame.py:48-65):
+    ORB extraction of left and right + compute_stereo_matches, for `max_pairs` pairs per launch sequence."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, H, W, max_pairs, device=0):
+        self._h = None
+        self.device = int(device)
+        self.H, self.W = int(H), int(W)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().b200orb_batch_create(int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST),
+                                                   self.H, self.W, int(max_pairs), self.device, C.byref(h)))
+        self._h = h
+        self.max_pairs = int(_lib.lib().b200orb_batch_max_pairs(h))
+        self.capacity = int(_lib.lib().b200orb_batch_kp_capacity(h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            try:
+                _lib.lib().b200orb_batch_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    def workspace_bytes(self):
+        return int(_lib.lib().b200orb_batch_workspace_bytes(self._h))
+
+    def alloc_outputs(self, n_pairs, pinned_host=False):
+        C_ = self.capacity
+        kw = dict(device="cpu", pin_memory=True) if pinned_host else dict(device=f"cuda:{self.device}")
+        return {
+            "kps": torch.empty((2, n_pairs, C_, 6), dtype=torch.float32, **kw),
+            "desc": torch.empty((2, n_pairs, C_, 32), dtype=torch.uint8, **kw),
+            "nkp": torch.empty((2, n_pairs), dtype=torch.int32, **kw),
+            "uRight": torch.empty((n_pairs, C_), dtype=torch.float32, **kw),
+            "depth": torch.empty((n_pairs, C_), dtype=torch.float32, **kw),
+            "matchIdx": torch.empty((n_pairs, C_), dtype=torch.int32, **kw),
+        }
+
+    def run(self, left, right, mbf, fx, out=None):
+        """left/right: uint8 CUDA tensors [n, H, W] (n <= max_pairs).  Asynchronous on the current stream."""
+        assert left.is_cuda and right.is_cuda and left.dtype == torch.uint8 and right.dtype == torch.uint8
+        assert left.is_contiguous() and right.is_contiguous() and left.shape == right.shape
+        n = left.shape[0]
+        assert tuple(left.shape[1:]) == (self.H, self.W)
+        if out is None:
+            out = self.alloc_outputs(n)
+        st = torch.cuda.current_stream(left.device).cuda_stream
+        _lib.check(_lib.lib().b200orb_batch_run_device(self._h, left.data_ptr(), right.data_ptr(), n, float(mbf), float(np.float32(fx)),
+                                                       out["kps"].data_ptr(), out["desc"].data_ptr(), out["nkp"].data_ptr(),
+                                                       out["uRight"].data_ptr(), out["depth"].data_ptr(), out["matchIdx"].data_ptr(),
+                                                       C.c_void_p(st)))
+        return out
+
+    def run_host(self, left, right, mbf, fx, out=None):
+        """left/right: uint8 HOST tensors or arrays [n, H, W] (pinned recommended, n may exceed max_pairs).
+        Uploads, processes and downloads chunk by chunk with copy/compute overlap; returns host tensors."""
+        lt = left if isinstance(left, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(left))
+        rt = right if isinstance(right, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(right))
+        assert not lt.is_cuda and not rt.is_cuda and lt.dtype == torch.uint8 and lt.is_contiguous() and rt.is_contiguous()
+        n = lt.shape[0]
+        assert tuple(lt.shape[1:]) == (self.H, self.W) and lt.shape == rt.shape
+        if out is None:
+            out = self.alloc_outputs(n, pinned_host=True)
+        _lib.check(_lib.lib().b200orb_batch_run_host(self._h, lt.data_ptr(), rt.data_ptr(), n, float(mbf), float(np.float32(fx)),
+                                                     out["kps"].data_ptr(), out["desc"].data_ptr(), out["nkp"].data_ptr(),
+                                                     out["uRight"].data_ptr(), out["depth"].data_ptr(), out["matchIdx"].data_ptr()))
+        return out

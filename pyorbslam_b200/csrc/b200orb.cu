@@ -1,0 +1,734 @@
+// b200orb: host side of the C ABI declared in include/b200orb.h.
+// Builds the geometry plan, owns the device workspace, and enqueues the kernel sequence
+//   K1 border + 7 x resize  ->  K5 blur  ->  K2 FAST cells  ->  K3 octree  ->  K4/K6 orient+describe  ->  K7/K8 stereo
+// for S images at a time (S = 1 for the reference-compatible extractor object, 2 x pairs for the batch API).
+// There is deliberately no CPU implementation behind these entry points.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200orb.h"
+#include "kernels_image.cuh"
+#include "kernels_octree.cuh"
+#include "kernels_features.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return fail(B200ORB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+    } while (0)
+#define TRY(expr) do { int _r = (expr); if (_r != 0) return _r; } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+// ------------------------------------------------------------------------------------------------
+// extractor constants: ORBextractor::ORBextractor, ORBextractor.cpp:410-470
+// ------------------------------------------------------------------------------------------------
+struct Params {
+    int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
+    float scaleFactorF = 0;
+    std::vector<float> sf, isf, sig2, isig2;
+    std::vector<int> quota;
+    int umax[16];
+};
+
+int make_params(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, Params& p) {
+    if (nlevels < 1 || nlevels > ORB_MAX_LEVELS) return fail(B200ORB_E_ARG, "nlevels must be in [1,16]");
+    if (nfeatures < 0) return fail(B200ORB_E_ARG, "nfeatures must be >= 0");
+    if (!(scaleFactor > 1.0f)) return fail(B200ORB_E_ARG, "scaleFactor must be > 1");
+    p.nfeatures = nfeatures; p.nlevels = nlevels; p.iniTh = iniTh; p.minTh = minTh; p.scaleFactorF = scaleFactor;
+    const double scaleD = scaleFactor;                 // member `double scaleFactor`, ORBextractor.h:97
+    p.sf.assign(nlevels, 1.f); p.sig2.assign(nlevels, 1.f); p.isf.resize(nlevels); p.isig2.resize(nlevels);
+    for (int i = 1; i < nlevels; ++i) {
+        p.sf[i] = (float)(p.sf[i - 1] * scaleD);
+        p.sig2[i] = p.sf[i] * p.sf[i];
+    }
+    for (int i = 0; i < nlevels; ++i) { p.isf[i] = 1.0f / p.sf[i]; p.isig2[i] = 1.0f / p.sig2[i]; }
+    p.quota.resize(nlevels);
+    const float factor = (float)(1.0f / scaleD);
+    float per = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; ++l) {
+        p.quota[l] = cv_round_f(per);
+        sum += p.quota[l];
+        per *= factor;
+    }
+    p.quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+    // umax: end of each row of the radius-15 disc, made symmetric (ORBextractor.cpp:454-469)
+    int um[17] = {0};
+    const int vmax = (int)floor(15 * sqrtf(2.f) / 2 + 1), vmin = (int)ceil(15 * sqrtf(2.f) / 2);
+    for (int v = 0; v <= vmax; ++v) um[v] = (int)lrint(sqrt(225.0 - v * v));
+    for (int v = 15, v0 = 0; v >= vmin; --v) {
+        while (um[v0] == um[v0 + 1]) ++v0;
+        um[v] = v0;
+        ++v0;
+    }
+    for (int v = 0; v < 16; ++v) p.umax[v] = um[v];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry plan
+// ------------------------------------------------------------------------------------------------
+struct HostPlan {
+    Plan P;
+    std::vector<XTab> xtab;
+    std::vector<YTab> ytab;
+    int fast_SP = 0, fast_SR = 0, fast_TP = 0, fast_TR = 0;
+    size_t fast_smem = 0;
+    int oct_capN = 0, oct_capK = 0, oct_capC = 0;
+    size_t oct_smem = 0;
+};
+
+inline short sat_short(int v) { return (short)(v < -32768 ? -32768 : v > 32767 ? 32767 : v); }
+
+int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
+    if (H < 1 || W < 1) return fail(B200ORB_E_ARG, "empty image");
+    if (W > 4096 || H > 4096) return fail(B200ORB_E_ARG, "image larger than 4096 px per side is not supported (12-bit coordinates)");
+    Plan& P = hp.P;
+    memset(&P, 0, sizeof(P));
+    P.nlevels = prm.nlevels; P.H = H; P.W = W; P.iniTh = prm.iniTh; P.minTh = prm.minTh;
+    for (int v = 0; v < 16; ++v) P.umax[v] = prm.umax[v];
+    hp.xtab.clear(); hp.ytab.clear();
+    int pyr = 0, blr = 0, cells = 0, cand = 0, kpt = 0, fctas = 0, bctas = 0, maxw = 0, maxh = 0, maxcap = 0, maxcells = 0;
+    for (int l = 0; l < prm.nlevels; ++l) {
+        LevelGeom& G = P.lv[l];
+        G.w = cv_round_f((float)W * prm.isf[l]);       // ORBextractor.cpp:1110-1111
+        G.h = cv_round_f((float)H * prm.isf[l]);
+        if (G.w < 1 || G.h < 1) return fail(B200ORB_E_ARG, "pyramid level collapses to zero size");
+        G.pitch = round_up(G.w + 2 * ORB_EDGE, 64);
+        G.rows = G.h + 2 * ORB_EDGE;
+        G.pyr_ofs = pyr; pyr += round_up(G.pitch * G.rows, 256);
+        G.blur_pitch = round_up(G.w, 64);
+        G.blur_ofs = blr; blr += round_up(G.blur_pitch * G.h, 256);
+        G.maxBX = G.w - ORB_EDGE + 3; G.maxBY = G.h - ORB_EDGE + 3;
+        const float width = (float)(G.maxBX - ORB_DET_ORIGIN), height = (float)(G.maxBY - ORB_DET_ORIGIN);
+        int nCols = (int)(width / 30.f), nRows = (int)(height / 30.f);    // ORBextractor.cpp:783-784
+        if (nCols <= 0 || nRows <= 0) { nCols = 0; nRows = 0; }          // the reference's cell loops do not run
+        G.nCols = nCols; G.nRows = nRows;
+        if (nRows) { G.wCell = (int)ceilf(width / nCols); G.hCell = (int)ceilf(height / nRows); }
+        G.cell_ofs = cells; cells += nRows * nCols;
+        G.cell_cap = nRows ? ((G.wCell + 1) / 2) * ((G.hCell + 1) / 2) : 0;   // strict 8-neighbour maxima: <= 1 per 2x2 block
+        G.cand_ofs = cand; cand += round_up(nRows * nCols * G.cell_cap, 4);
+        G.fast_groups = (nCols + FAST_WARPS - 1) / FAST_WARPS;
+        G.fast_cta_ofs = fctas; fctas += nRows * G.fast_groups;
+        G.blur_tiles_x = (G.w + BLUR_TW - 1) / BLUR_TW;
+        G.blur_cta_ofs = bctas; bctas += G.blur_tiles_x * ((G.h + BLUR_TH - 1) / BLUR_TH);
+        G.quota = prm.quota[l];
+        G.nIni = 0; G.hX = 1.f;
+        if (nRows) {
+            G.nIni = (int)roundf((float)(G.maxBX - ORB_DET_ORIGIN) / (G.maxBY - ORB_DET_ORIGIN));   // ORBextractor.cpp:543
+            if (G.nIni < 1) return fail(B200ORB_E_ARG, "image taller than 2x its width: the reference divides by zero here");
+            G.hX = (float)(G.maxBX - ORB_DET_ORIGIN) / G.nIni;
+        }
+        G.kp_cap = nRows ? std::max(4 * G.nIni, G.quota + 3) : 0;
+        G.kp_ofs = kpt; kpt += G.kp_cap;
+        G.sf = prm.sf[l]; G.isf = prm.isf[l];
+        G.psize = (int)(31 * prm.sf[l]);
+        maxw = std::max(maxw, G.wCell); maxh = std::max(maxh, G.hCell);
+        maxcap = std::max(maxcap, G.kp_cap); maxcells = std::max(maxcells, nRows * nCols);
+        if (l > 0) {   // cv::resize INTER_LINEAR tables, SURVEY.md App. A2
+            const LevelGeom& S = P.lv[l - 1];
+            G.xtab_ofs = (int)hp.xtab.size(); G.ytab_ofs = (int)hp.ytab.size();
+            const double sx_ = 1. / ((double)G.w / S.w), sy_ = 1. / ((double)G.h / S.h);
+            for (int dx = 0; dx < G.w; ++dx) {
+                float fx = (float)((dx + 0.5) * sx_ - 0.5);
+                int sx = (int)floorf(fx);
+                fx -= sx;
+                if (sx < 0) { fx = 0; sx = 0; }
+                if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
+                hp.xtab.push_back(XTab{sx, sat_short(cv_round_f((1.f - fx) * 2048.f)), sat_short(cv_round_f(fx * 2048.f))});
+            }
+            for (int dy = 0; dy < G.h; ++dy) {
+                float fy = (float)((dy + 0.5) * sy_ - 0.5);
+                int sy = (int)floorf(fy);
+                fy -= sy;
+                hp.ytab.push_back(YTab{(short)std::min(std::max(sy, 0), S.h - 1), (short)std::min(std::max(sy + 1, 0), S.h - 1),
+                                       sat_short(cv_round_f((1.f - fy) * 2048.f)), sat_short(cv_round_f(fy * 2048.f))});
+            }
+        }
+    }
+    P.pyr_bytes = pyr; P.blur_bytes = blr; P.ncells = std::max(cells, 1); P.cand_entries = std::max(cand, 4);
+    P.kp_total = std::max(kpt, 1); P.fast_ctas = fctas; P.blur_ctas = bctas; P.max_cells_level = maxcells;
+    hp.fast_SP = round_up(3 + FAST_WARPS * maxw + 6 + 4, 4);
+    hp.fast_SR = maxh + 6;
+    hp.fast_TP = round_up(maxw + 2, 4);
+    hp.fast_TR = maxh + 2;
+    hp.fast_smem = (size_t)hp.fast_SP * hp.fast_SR + (size_t)FAST_WARPS * hp.fast_TP * hp.fast_TR;
+    hp.fast_smem = (hp.fast_smem + 15) & ~(size_t)15;
+    if (hp.fast_smem > 200 * 1024) return fail(B200ORB_E_ARG, "cell size too large for the FAST kernel's shared memory");
+    hp.oct_capN = round_up(maxcap + 8, 4);
+    hp.oct_capC = round_up(std::max(maxcells, 1), 4);
+    const size_t fixed = oct_smem_bytes(hp.oct_capN, 0, hp.oct_capC);
+    long long room = 100 * 1024 - (long long)fixed;
+    if (room < 4096 * 8) room = 200 * 1024 - (long long)fixed;
+    if (room < 1024 * 8) return fail(B200ORB_E_ARG, "nfeatures too large for the octree kernel's shared memory");
+    hp.oct_capK = (int)(room / 8) & ~3;
+    hp.oct_smem = oct_smem_bytes(hp.oct_capN, hp.oct_capK, hp.oct_capC);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Engine: workspace for S image slots + the kernel sequence
+// ------------------------------------------------------------------------------------------------
+struct Engine {
+    Params prm;
+    HostPlan hp;
+    int device = 0, S = 0;
+    bool planned = false;
+    u8 *d_pyr = nullptr, *d_blur = nullptr;
+    u32 *d_cand = nullptr, *d_scratch = nullptr, *d_lvlkp = nullptr;
+    int *d_cellcnt = nullptr, *d_lvlcnt = nullptr, *d_status = nullptr;
+    XTab* d_xtab = nullptr;
+    YTab* d_ytab = nullptr;
+    long long bytes = 0;
+
+    void release() {
+        cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_cand); cudaFree(d_scratch); cudaFree(d_lvlkp);
+        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_ytab);
+        d_pyr = d_blur = nullptr; d_cand = d_scratch = d_lvlkp = nullptr; d_cellcnt = d_lvlcnt = d_status = nullptr;
+        d_xtab = nullptr; d_ytab = nullptr; planned = false; bytes = 0;
+    }
+    template <typename T> int alloc(T** p, size_t n) {
+        CU_TRY(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+        bytes += (long long)(n * sizeof(T));
+        return 0;
+    }
+    int plan(int H, int W, int slots) {
+        if (planned && hp.P.H == H && hp.P.W == W && S == slots) return 0;
+        CU_TRY(cudaSetDevice(device));
+        release();
+        TRY(build_plan(prm, H, W, hp));
+        S = slots;
+        const Plan& P = hp.P;
+        TRY(alloc(&d_pyr, (size_t)S * P.pyr_bytes));
+        TRY(alloc(&d_blur, (size_t)S * P.blur_bytes));
+        TRY(alloc(&d_cand, (size_t)S * P.cand_entries));
+        TRY(alloc(&d_scratch, (size_t)S * P.cand_entries * 2));
+        TRY(alloc(&d_lvlkp, (size_t)S * P.kp_total));
+        TRY(alloc(&d_cellcnt, (size_t)S * P.ncells));
+        TRY(alloc(&d_lvlcnt, (size_t)S * P.nlevels));
+        TRY(alloc(&d_status, 1));
+        TRY(alloc(&d_xtab, hp.xtab.size()));
+        TRY(alloc(&d_ytab, hp.ytab.size()));
+        CU_TRY(cudaMemset(d_pyr, 0, (size_t)S * P.pyr_bytes));
+        CU_TRY(cudaMemset(d_blur, 0, (size_t)S * P.blur_bytes));
+        CU_TRY(cudaMemset(d_status, 0, sizeof(int)));
+        if (!hp.xtab.empty()) CU_TRY(cudaMemcpy(d_xtab, hp.xtab.data(), hp.xtab.size() * sizeof(XTab), cudaMemcpyHostToDevice));
+        if (!hp.ytab.empty()) CU_TRY(cudaMemcpy(d_ytab, hp.ytab.data(), hp.ytab.size() * sizeof(YTab), cudaMemcpyHostToDevice));
+        CU_TRY(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.fast_smem));
+        CU_TRY(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.oct_smem));
+        planned = true;
+        return 0;
+    }
+    // images: slots [0, splitA) from imgA, [splitA, n) from imgB; outputs: kps [n][kp_total][6], desc [n][kp_total][32], nkp [n]
+    int extract(const u8* imgA, const u8* imgB, int splitA, int n, float* d_kps, u8* d_desc, int* d_nkp, cudaStream_t st) {
+        if (n < 1 || n > S) return fail(B200ORB_E_ARG, "slot count out of range");
+        const Plan& P = hp.P;
+        {
+            const LevelGeom& G = P.lv[0];
+            dim3 grid(((G.pitch >> 2) * G.rows + 255) / 256, n);
+            k_border0<<<grid, 256, 0, st>>>(P, imgA, imgB, splitA, d_pyr);
+            ++g_launches;
+        }
+        for (int l = 1; l < P.nlevels; ++l) {
+            const LevelGeom& G = P.lv[l];
+            dim3 grid(((G.pitch >> 2) * G.rows + 255) / 256, n);
+            k_resize<<<grid, 256, 0, st>>>(P, l, d_pyr, d_xtab, d_ytab);
+            ++g_launches;
+        }
+        k_blur<<<dim3(P.blur_ctas, n), 256, 0, st>>>(P, d_pyr, d_blur);
+        ++g_launches;
+        if (P.fast_ctas > 0) {
+            k_fast_cells<<<dim3(P.fast_ctas, n), FAST_WARPS * 32, hp.fast_smem, st>>>(P, d_pyr, d_cand, d_cellcnt, hp.fast_SP, hp.fast_SR,
+                                                                                   hp.fast_TP, hp.fast_TR);
+            ++g_launches;
+        }
+        k_octree<<<dim3(P.nlevels, n), OCT_THREADS, hp.oct_smem, st>>>(P, d_cand, d_cellcnt, d_scratch, d_lvlkp, d_lvlcnt, hp.oct_capN,
+                                                                      hp.oct_capK, hp.oct_capC);
+        ++g_launches;
+        k_describe<<<dim3((P.kp_total + DESC_WARPS - 1) / DESC_WARPS, n), DESC_WARPS * 32, 0, st>>>(P, d_pyr, d_blur, d_lvlkp, d_lvlcnt, d_kps,
+                                                                                                    d_desc, d_nkp);
+        ++g_launches;
+        CU_TRY(cudaGetLastError());
+        return 0;
+    }
+    void stereo_geom(StereoGeom& SG) const {
+        const Plan& P = hp.P;
+        memset(&SG, 0, sizeof(SG));
+        SG.nlevels = P.nlevels;
+        SG.nRows = P.lv[0].h;
+        for (int l = 0; l < P.nlevels; ++l) {
+            const LevelGeom& G = P.lv[l];
+            SG.sf[l] = G.sf; SG.isf[l] = G.isf; SG.w[l] = G.w; SG.h[l] = G.h;
+            SG.plog[l] = G.w + 2 * ORB_EDGE;                 // the reference's Mat step
+            SG.pitch[l] = G.pitch;
+            SG.off0[l] = ORB_EDGE * SG.plog[l] + ORB_EDGE;
+            SG.base[l] = G.pyr_ofs;
+        }
+    }
+};
+
+void fill_stereo_consts(StereoArgs& A, double mbf, float fx) {
+    A.mbf = mbf;
+    A.mbf32 = (float)mbf;            // python float / np.float32 -> float32 (NumPy >= 2), Frame.py:43
+    A.mb = A.mbf32 / fx;
+    A.maxD = A.mbf32 / A.mb;         // Frame.py:183
+}
+
+int launch_stereo(const StereoGeom& SG, const StereoArgs& A, int max_left, int pairs, cudaStream_t st) {
+    if (pairs < 1 || max_left < 1) return 0;
+    dim3 grid((max_left + ST_LEFT_PER_CTA - 1) / ST_LEFT_PER_CTA, pairs);
+    k_stereo<<<grid, ST_WARPS * 32, 0, st>>>(SG, A);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+struct b200orb_extractor {
+    Engine eng;
+    cudaStream_t st = nullptr;
+    u8* d_img = nullptr; size_t img_cap = 0;
+    float* d_kps = nullptr; u8* d_desc = nullptr; int* d_nkp = nullptr;
+    float *d_uR = nullptr, *d_depth = nullptr; int* d_match = nullptr;
+    int out_cap = 0;
+    int n = -1;          // keypoints of the last call, -1 = none yet
+    bool empty_last = false;
+};
+
+struct b200orb_batch {
+    Engine eng;
+    int P = 0, H = 0, W = 0;
+    // run_host pipeline state
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    u8* d_in[2] = {nullptr, nullptr};
+    float* d_kps[2] = {nullptr, nullptr}; u8* d_desc[2] = {nullptr, nullptr}; int* d_nkp[2] = {nullptr, nullptr};
+    float* d_uR[2] = {nullptr, nullptr}; float* d_dep[2] = {nullptr, nullptr}; int* d_mi[2] = {nullptr, nullptr};
+    bool host_ready = false;
+    long long host_bytes = 0;
+};
+
+extern "C" {
+
+const char* b200orb_last_error(void) { return g_err.c_str(); }
+int b200orb_version(void) { return 100; }
+int b200orb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+long long b200orb_kernel_launches(void) { return g_launches.load(); }
+
+int b200orb_extractor_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int device,
+                             b200orb_extractor** out) {
+    if (!out) return fail(B200ORB_E_ARG, "out is NULL");
+    *out = nullptr;
+    b200orb_extractor* e = new b200orb_extractor;
+    int r = make_params(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, e->eng.prm);
+    if (r) { delete e; return r; }
+    e->eng.device = device;
+    *out = e;
+    return 0;
+}
+
+void b200orb_extractor_destroy(b200orb_extractor* e) {
+    if (!e) return;
+    if (e->st || e->d_img || e->eng.planned) {
+        cudaSetDevice(e->eng.device);
+        e->eng.release();
+        cudaFree(e->d_img); cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_nkp);
+        cudaFree(e->d_uR); cudaFree(e->d_depth); cudaFree(e->d_match);
+        if (e->st) cudaStreamDestroy(e->st);
+    }
+    delete e;
+}
+
+int b200orb_get_levels(const b200orb_extractor* e) { return e->eng.prm.nlevels; }
+float b200orb_get_scale_factor(const b200orb_extractor* e) { return e->eng.prm.scaleFactorF; }
+static int copy_tab(const std::vector<float>& v, float* out) { if (!out) return fail(B200ORB_E_ARG, "out is NULL"); memcpy(out, v.data(), v.size() * 4); return 0; }
+int b200orb_get_scale_factors(const b200orb_extractor* e, float* out) { return copy_tab(e->eng.prm.sf, out); }
+int b200orb_get_inverse_scale_factors(const b200orb_extractor* e, float* out) { return copy_tab(e->eng.prm.isf, out); }
+int b200orb_get_scale_sigma_squares(const b200orb_extractor* e, float* out) { return copy_tab(e->eng.prm.sig2, out); }
+int b200orb_get_inverse_scale_sigma_squares(const b200orb_extractor* e, float* out) { return copy_tab(e->eng.prm.isig2, out); }
+int b200orb_get_features_per_level(const b200orb_extractor* e, int* out) {
+    if (!out) return fail(B200ORB_E_ARG, "out is NULL");
+    memcpy(out, e->eng.prm.quota.data(), e->eng.prm.quota.size() * 4);
+    return 0;
+}
+
+int b200orb_extract(b200orb_extractor* e, const uint8_t* image, int H, int W, int* n_keypoints) {
+    if (!e || !n_keypoints) return fail(B200ORB_E_ARG, "NULL argument");
+    if (H == 0 || W == 0 || !image) {       // ORBextractor.cpp:1045-1046: empty image -> nothing happens
+        *n_keypoints = 0; e->n = 0; e->empty_last = true;
+        return 0;
+    }
+    if (H < 0 || W < 0) return fail(B200ORB_E_ARG, "negative image size");
+    CU_TRY(cudaSetDevice(e->eng.device));
+    if (!e->st) CU_TRY(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    TRY(e->eng.plan(H, W, 1));
+    const Plan& P = e->eng.hp.P;
+    if ((size_t)H * W > e->img_cap) {
+        cudaFree(e->d_img);
+        e->d_img = nullptr;
+        CU_TRY(cudaMalloc((void**)&e->d_img, (size_t)H * W));
+        e->img_cap = (size_t)H * W;
+    }
+    if (e->out_cap != P.kp_total) {
+        cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_nkp); cudaFree(e->d_uR); cudaFree(e->d_depth); cudaFree(e->d_match);
+        e->d_kps = nullptr; e->d_desc = nullptr; e->d_nkp = nullptr; e->d_uR = e->d_depth = nullptr; e->d_match = nullptr;
+        CU_TRY(cudaMalloc((void**)&e->d_kps, (size_t)P.kp_total * 6 * 4));
+        CU_TRY(cudaMalloc((void**)&e->d_desc, (size_t)P.kp_total * 32));
+        CU_TRY(cudaMalloc((void**)&e->d_nkp, 4));
+        CU_TRY(cudaMalloc((void**)&e->d_uR, (size_t)P.kp_total * 4));
+        CU_TRY(cudaMalloc((void**)&e->d_depth, (size_t)P.kp_total * 4));
+        CU_TRY(cudaMalloc((void**)&e->d_match, (size_t)P.kp_total * 4));
+        e->out_cap = P.kp_total;
+    }
+    CU_TRY(cudaMemcpyAsync(e->d_img, image, (size_t)H * W, cudaMemcpyHostToDevice, e->st));
+    TRY(e->eng.extract(e->d_img, e->d_img, 1, 1, e->d_kps, e->d_desc, e->d_nkp, e->st));
+    int n = 0;
+    CU_TRY(cudaMemcpyAsync(&n, e->d_nkp, 4, cudaMemcpyDeviceToHost, e->st));
+    CU_TRY(cudaStreamSynchronize(e->st));
+    e->n = n; e->empty_last = false;
+    *n_keypoints = n;
+    return 0;
+}
+
+int b200orb_get_results(b200orb_extractor* e, float* kps, uint8_t* desc) {
+    if (!e || e->n < 0) return fail(B200ORB_E_STATE, "no extract() call yet");
+    if (e->n == 0) return 0;
+    CU_TRY(cudaSetDevice(e->eng.device));
+    if (kps) CU_TRY(cudaMemcpyAsync(kps, e->d_kps, (size_t)e->n * 24, cudaMemcpyDeviceToHost, e->st));
+    if (desc) CU_TRY(cudaMemcpyAsync(desc, e->d_desc, (size_t)e->n * 32, cudaMemcpyDeviceToHost, e->st));
+    CU_TRY(cudaStreamSynchronize(e->st));
+    return 0;
+}
+
+int b200orb_max_keypoints(const b200orb_extractor* e) { return e && e->eng.planned ? e->eng.hp.P.kp_total : 0; }
+
+static int need_pyramid(const b200orb_extractor* e, int level) {
+    if (!e || e->n < 0 || e->empty_last || !e->eng.planned) return fail(B200ORB_E_STATE, "no pyramid: extract() has not processed an image yet");
+    if (level < 0 || level >= e->eng.prm.nlevels) return fail(B200ORB_E_ARG, "level out of range");
+    return 0;
+}
+
+int b200orb_level_size(const b200orb_extractor* e, int level, int* w, int* h) {
+    TRY(need_pyramid(e, level));
+    *w = e->eng.hp.P.lv[level].w; *h = e->eng.hp.P.lv[level].h;
+    return 0;
+}
+
+int b200orb_get_pyramid_level(b200orb_extractor* e, int level, uint8_t* out) {
+    TRY(need_pyramid(e, level));
+    if (!out) return fail(B200ORB_E_ARG, "out is NULL");
+    CU_TRY(cudaSetDevice(e->eng.device));
+    const LevelGeom& G = e->eng.hp.P.lv[level];
+    const int plog = G.w + 2 * ORB_EDGE;
+    std::vector<u8> tmp((size_t)plog * G.rows);
+    CU_TRY(cudaMemcpy2DAsync(tmp.data(), plog, e->eng.d_pyr + G.pyr_ofs, G.pitch, plog, G.rows, cudaMemcpyDeviceToHost, e->st));
+    CU_TRY(cudaStreamSynchronize(e->st));
+    // the caster's step-ignoring copy: rows*cols contiguous bytes from the ROI start (opencv_type_casters.h:230-239)
+    memcpy(out, tmp.data() + (size_t)ORB_EDGE * plog + ORB_EDGE, (size_t)G.w * G.h);
+    return 0;
+}
+
+int b200orb_get_level_image(b200orb_extractor* e, int level, int blurred, uint8_t* out) {
+    TRY(need_pyramid(e, level));
+    if (!out) return fail(B200ORB_E_ARG, "out is NULL");
+    CU_TRY(cudaSetDevice(e->eng.device));
+    const LevelGeom& G = e->eng.hp.P.lv[level];
+    if (blurred)
+        CU_TRY(cudaMemcpy2DAsync(out, G.w, e->eng.d_blur + G.blur_ofs, G.blur_pitch, G.w, G.h, cudaMemcpyDeviceToHost, e->st));
+    else
+        CU_TRY(cudaMemcpy2DAsync(out, G.w, e->eng.d_pyr + G.pyr_ofs + (size_t)ORB_EDGE * G.pitch + ORB_EDGE, G.pitch, G.w, G.h,
+                                 cudaMemcpyDeviceToHost, e->st));
+    CU_TRY(cudaStreamSynchronize(e->st));
+    return 0;
+}
+
+int b200orb_get_level_candidates(b200orb_extractor* e, int level, int cap, int* out, int* n) {
+    TRY(need_pyramid(e, level));
+    if (!n) return fail(B200ORB_E_ARG, "n is NULL");
+    CU_TRY(cudaSetDevice(e->eng.device));
+    const Plan& P = e->eng.hp.P;
+    const LevelGeom& G = P.lv[level];
+    const int nc = G.nRows * G.nCols;
+    std::vector<int> cnt(std::max(nc, 1));
+    std::vector<u32> c((size_t)std::max(nc * G.cell_cap, 1));
+    if (nc) {
+        CU_TRY(cudaMemcpy(cnt.data(), e->eng.d_cellcnt + G.cell_ofs, (size_t)nc * 4, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(c.data(), e->eng.d_cand + G.cand_ofs, (size_t)nc * G.cell_cap * 4, cudaMemcpyDeviceToHost));
+    }
+    int k = 0;
+    for (int i = 0; i < nc; ++i)
+        for (int j = 0; j < cnt[i]; ++j, ++k)
+            if (out && k < cap) {
+                const u32 v = c[(size_t)i * G.cell_cap + j];
+                out[3 * k] = v & 0xfff; out[3 * k + 1] = (v >> 12) & 0xfff; out[3 * k + 2] = v >> 24;
+            }
+    *n = k;
+    return 0;
+}
+
+int b200orb_stereo(b200orb_extractor* L, b200orb_extractor* R, double mbf, float fx, float* uRight, float* depth, int* matchIdx) {
+    if (!L || !R || !uRight || !depth) return fail(B200ORB_E_ARG, "NULL argument");
+    if (L->n < 0 || R->n < 0) return fail(B200ORB_E_STATE, "both extractors need an extract() call first");
+    if (L->n == 0) return 0;
+    if (L->empty_last || R->empty_last) {
+        if (R->empty_last && !L->empty_last) { for (int i = 0; i < L->n; ++i) { uRight[i] = -1.f; depth[i] = -1.f; if (matchIdx) matchIdx[i] = -1; } return 0; }
+        return fail(B200ORB_E_STATE, "left extractor holds no image");
+    }
+    if (L->eng.device != R->eng.device) return fail(B200ORB_E_ARG, "extractors live on different devices");
+    const Plan &PL = L->eng.hp.P, &PR = R->eng.hp.P;
+    if (PL.H != PR.H || PL.W != PR.W || PL.nlevels != PR.nlevels || L->eng.prm.scaleFactorF != R->eng.prm.scaleFactorF)
+        return fail(B200ORB_E_ARG, "left and right extractors have different geometry");
+    CU_TRY(cudaSetDevice(L->eng.device));
+    StereoGeom SG;
+    L->eng.stereo_geom(SG);
+    StereoArgs A;
+    memset(&A, 0, sizeof(A));
+    A.kpsL = L->d_kps; A.descL = L->d_desc; A.nL = L->d_nkp;
+    A.kpsR = R->d_kps; A.descR = R->d_desc; A.nR = R->d_nkp;
+    A.pyrL = L->eng.d_pyr; A.pyrR = R->eng.d_pyr;
+    A.kp_row = 6; A.oct_idx = 5; A.out_stride = PL.kp_total;
+    A.uRight = L->d_uR; A.depth = L->d_depth; A.matchIdx = L->d_match; A.status = L->eng.d_status;
+    fill_stereo_consts(A, mbf, fx);
+    CU_TRY(cudaMemsetAsync(L->eng.d_status, 0, 4, L->st));
+    TRY(launch_stereo(SG, A, L->n, 1, L->st));
+    int status = 0;
+    CU_TRY(cudaMemcpyAsync(uRight, L->d_uR, (size_t)L->n * 4, cudaMemcpyDeviceToHost, L->st));
+    CU_TRY(cudaMemcpyAsync(depth, L->d_depth, (size_t)L->n * 4, cudaMemcpyDeviceToHost, L->st));
+    if (matchIdx) CU_TRY(cudaMemcpyAsync(matchIdx, L->d_match, (size_t)L->n * 4, cudaMemcpyDeviceToHost, L->st));
+    CU_TRY(cudaMemcpyAsync(&status, L->eng.d_status, 4, cudaMemcpyDeviceToHost, L->st));
+    CU_TRY(cudaStreamSynchronize(L->st));
+    if (status) return fail(B200ORB_E_RANGE, "a SAD window leaves the pyramid view (the reference raises IndexError/ValueError here)");
+    return 0;
+}
+
+int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t* descL, int nRight, const float* kpsR,
+                        const uint8_t* descR, int nlevels, const float* sf, const float* isf, const uint8_t* const* pyrL,
+                        const uint8_t* const* pyrR, const int* lw, const int* lh, double mbf, float fx, float* uRight, float* depth,
+                        int* matchIdx) {
+    if (nLeft < 0 || nRight < 0 || nlevels < 1 || nlevels > ORB_MAX_LEVELS) return fail(B200ORB_E_ARG, "bad sizes");
+    if (nLeft == 0) return 0;
+    if (nRight >= (1 << 20)) return fail(B200ORB_E_ARG, "more than 2^20 right keypoints");
+    CU_TRY(cudaSetDevice(device));
+    StereoGeom SG;
+    memset(&SG, 0, sizeof(SG));
+    SG.nlevels = nlevels; SG.nRows = lh[0];
+    long long total = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        SG.sf[l] = sf[l]; SG.isf[l] = isf[l]; SG.w[l] = lw[l]; SG.h[l] = lh[l];
+        SG.plog[l] = lw[l]; SG.pitch[l] = lw[l]; SG.off0[l] = 0; SG.base[l] = total;
+        total += ((long long)lw[l] * lh[l] + 255) & ~255LL;
+    }
+    // host-side validation of what the reference would index (rows of vRowIndices, octaves)
+    for (int i = 0; i < nRight; ++i) {
+        const int o = (int)kpsR[3 * i + 2];
+        if (o < 0 || o >= nlevels) return fail(B200ORB_E_RANGE, "right keypoint octave out of range");
+        const double y = kpsR[3 * i + 1], r = 2.0 * (double)sf[o];
+        if (floor(y - r) < 0 || ceil(y + r) >= lh[0]) return fail(B200ORB_E_RANGE, "right keypoint row band leaves the image (the reference raises IndexError)");
+    }
+    for (int i = 0; i < nLeft; ++i) {
+        const int o = (int)kpsL[3 * i + 2];
+        if (o < 0 || o >= nlevels) return fail(B200ORB_E_RANGE, "left keypoint octave out of range");
+        if ((int)kpsL[3 * i + 1] < 0 || (int)kpsL[3 * i + 1] >= lh[0]) return fail(B200ORB_E_RANGE, "left keypoint row outside the image");
+    }
+    u8 *d_blob = nullptr, *d_dL = nullptr, *d_dR = nullptr;
+    float *d_kL = nullptr, *d_kR = nullptr, *d_u = nullptr, *d_d = nullptr;
+    int *d_m = nullptr, *d_n = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() { cudaFree(d_blob); cudaFree(d_dL); cudaFree(d_dR); cudaFree(d_kL); cudaFree(d_kR); cudaFree(d_u); cudaFree(d_d); cudaFree(d_m); cudaFree(d_n); };
+#define CU_TRY2(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(B200ORB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+    CU_TRY2(cudaMalloc((void**)&d_blob, (size_t)total * 2));
+    CU_TRY2(cudaMalloc((void**)&d_kL, (size_t)nLeft * 12));
+    CU_TRY2(cudaMalloc((void**)&d_dL, (size_t)nLeft * 32));
+    CU_TRY2(cudaMalloc((void**)&d_kR, (size_t)std::max(nRight, 1) * 12));
+    CU_TRY2(cudaMalloc((void**)&d_dR, (size_t)std::max(nRight, 1) * 32));
+    CU_TRY2(cudaMalloc((void**)&d_u, (size_t)nLeft * 4));
+    CU_TRY2(cudaMalloc((void**)&d_d, (size_t)nLeft * 4));
+    CU_TRY2(cudaMalloc((void**)&d_m, (size_t)nLeft * 4));
+    CU_TRY2(cudaMalloc((void**)&d_n, 12));
+    for (int l = 0; l < nlevels; ++l) {
+        CU_TRY2(cudaMemcpy(d_blob + SG.base[l], pyrL[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice));
+        CU_TRY2(cudaMemcpy(d_blob + total + SG.base[l], pyrR[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice));
+    }
+    CU_TRY2(cudaMemcpy(d_kL, kpsL, (size_t)nLeft * 12, cudaMemcpyHostToDevice));
+    CU_TRY2(cudaMemcpy(d_dL, descL, (size_t)nLeft * 32, cudaMemcpyHostToDevice));
+    if (nRight) {
+        CU_TRY2(cudaMemcpy(d_kR, kpsR, (size_t)nRight * 12, cudaMemcpyHostToDevice));
+        CU_TRY2(cudaMemcpy(d_dR, descR, (size_t)nRight * 32, cudaMemcpyHostToDevice));
+    }
+    const int hn[3] = {nLeft, nRight, 0};
+    CU_TRY2(cudaMemcpy(d_n, hn, 12, cudaMemcpyHostToDevice));
+    StereoArgs A;
+    memset(&A, 0, sizeof(A));
+    A.kpsL = d_kL; A.descL = d_dL; A.nL = d_n; A.kpsR = d_kR; A.descR = d_dR; A.nR = d_n + 1;
+    A.pyrL = d_blob; A.pyrR = d_blob + total;
+    A.kp_row = 3; A.oct_idx = 2; A.out_stride = nLeft;
+    A.uRight = d_u; A.depth = d_d; A.matchIdx = d_m; A.status = d_n + 2;
+    fill_stereo_consts(A, mbf, fx);
+    rc = launch_stereo(SG, A, nLeft, 1, nullptr);
+    if (rc) { cleanup(); return rc; }
+    int status = 0;
+    CU_TRY2(cudaMemcpy(uRight, d_u, (size_t)nLeft * 4, cudaMemcpyDeviceToHost));
+    CU_TRY2(cudaMemcpy(depth, d_d, (size_t)nLeft * 4, cudaMemcpyDeviceToHost));
+    if (matchIdx) CU_TRY2(cudaMemcpy(matchIdx, d_m, (size_t)nLeft * 4, cudaMemcpyDeviceToHost));
+    CU_TRY2(cudaMemcpy(&status, d_n + 2, 4, cudaMemcpyDeviceToHost));
+    cleanup();
+    if (status) return fail(B200ORB_E_RANGE, "a SAD window leaves the pyramid view (the reference raises IndexError/ValueError here)");
+    return 0;
+}
+
+// ---------------------------------------------------------------- batch
+int b200orb_batch_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int H, int W, int max_pairs,
+                         int device, b200orb_batch** out) {
+    if (!out) return fail(B200ORB_E_ARG, "out is NULL");
+    *out = nullptr;
+    if (max_pairs < 1) return fail(B200ORB_E_ARG, "max_pairs must be >= 1");
+    b200orb_batch* b = new b200orb_batch;
+    int r = make_params(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, b->eng.prm);
+    if (!r) { b->eng.device = device; b->P = max_pairs; b->H = H; b->W = W; r = b->eng.plan(H, W, 2 * max_pairs); }
+    if (r) { b200orb_batch_destroy(b); return r; }
+    *out = b;
+    return 0;
+}
+
+void b200orb_batch_destroy(b200orb_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->eng.device);
+    b->eng.release();
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(b->d_in[i]); cudaFree(b->d_kps[i]); cudaFree(b->d_desc[i]); cudaFree(b->d_nkp[i]);
+        cudaFree(b->d_uR[i]); cudaFree(b->d_dep[i]); cudaFree(b->d_mi[i]);
+        if (b->ev_in[i]) cudaEventDestroy(b->ev_in[i]);
+        if (b->ev_comp[i]) cudaEventDestroy(b->ev_comp[i]);
+        if (b->ev_out[i]) cudaEventDestroy(b->ev_out[i]);
+    }
+    if (b->s_in) cudaStreamDestroy(b->s_in);
+    if (b->s_comp) cudaStreamDestroy(b->s_comp);
+    if (b->s_out) cudaStreamDestroy(b->s_out);
+    delete b;
+}
+
+int b200orb_batch_max_pairs(const b200orb_batch* b) { return b ? b->P : 0; }
+int b200orb_batch_kp_capacity(const b200orb_batch* b) { return b ? b->eng.hp.P.kp_total : 0; }
+long long b200orb_batch_workspace_bytes(const b200orb_batch* b) { return b ? b->eng.bytes + b->host_bytes : 0; }
+
+int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint8_t* d_right, int n_pairs, double mbf, float fx,
+                             float* d_kps, uint8_t* d_desc, int32_t* d_nkp, float* d_uRight, float* d_depth, int32_t* d_matchIdx,
+                             void* stream) {
+    if (!b || !d_left || !d_right || !d_kps || !d_desc || !d_nkp || !d_uRight || !d_depth) return fail(B200ORB_E_ARG, "NULL argument");
+    if (n_pairs < 1 || n_pairs > b->P) return fail(B200ORB_E_ARG, "n_pairs must be in [1, max_pairs]");
+    CU_TRY(cudaSetDevice(b->eng.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Plan& P = b->eng.hp.P;
+    const size_t C = P.kp_total;
+    TRY(b->eng.extract(d_left, d_right, n_pairs, 2 * n_pairs, d_kps, d_desc, d_nkp, st));
+    StereoGeom SG;
+    b->eng.stereo_geom(SG);
+    StereoArgs A;
+    memset(&A, 0, sizeof(A));
+    A.kpsL = d_kps; A.kpsR = d_kps + (size_t)n_pairs * C * 6;
+    A.descL = d_desc; A.descR = d_desc + (size_t)n_pairs * C * 32;
+    A.nL = d_nkp; A.nR = d_nkp + n_pairs; A.n_stride = 1;
+    A.pyrL = b->eng.d_pyr; A.pyrR = b->eng.d_pyr + (size_t)n_pairs * P.pyr_bytes;
+    A.kp_stride = (long long)C * 6; A.desc_stride = (long long)C * 32; A.pyr_stride = P.pyr_bytes;
+    A.kp_row = 6; A.oct_idx = 5; A.out_stride = (int)C;
+    A.uRight = d_uRight; A.depth = d_depth; A.matchIdx = d_matchIdx; A.status = b->eng.d_status;
+    fill_stereo_consts(A, mbf, fx);
+    return launch_stereo(SG, A, (int)C, n_pairs, st);
+}
+
+static int batch_host_setup(b200orb_batch* b) {
+    if (b->host_ready) return 0;
+    const Plan& P = b->eng.hp.P;
+    const size_t C = P.kp_total, PP = b->P, HW = (size_t)b->H * b->W;
+    CU_TRY(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&b->s_comp, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU_TRY(cudaEventCreateWithFlags(&b->ev_in[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&b->ev_comp[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&b->ev_out[i], cudaEventDisableTiming));
+        CU_TRY(cudaMalloc((void**)&b->d_in[i], 2 * PP * HW));
+        CU_TRY(cudaMalloc((void**)&b->d_kps[i], 2 * PP * C * 24));
+        CU_TRY(cudaMalloc((void**)&b->d_desc[i], 2 * PP * C * 32));
+        CU_TRY(cudaMalloc((void**)&b->d_nkp[i], 2 * PP * 4));
+        CU_TRY(cudaMalloc((void**)&b->d_uR[i], PP * C * 4));
+        CU_TRY(cudaMalloc((void**)&b->d_dep[i], PP * C * 4));
+        CU_TRY(cudaMalloc((void**)&b->d_mi[i], PP * C * 4));
+        b->host_bytes += (long long)(2 * PP * HW + 2 * PP * C * 56 + 2 * PP * 4 + 3 * PP * C * 4);
+    }
+    b->host_ready = true;
+    return 0;
+}
+
+int b200orb_batch_run_host(b200orb_batch* b, const uint8_t* h_left, const uint8_t* h_right, int n_pairs, double mbf, float fx,
+                           float* h_kps, uint8_t* h_desc, int32_t* h_nkp, float* h_uRight, float* h_depth, int32_t* h_matchIdx) {
+    if (!b || !h_left || !h_right || !h_kps || !h_desc || !h_nkp || !h_uRight || !h_depth) return fail(B200ORB_E_ARG, "NULL argument");
+    if (n_pairs < 1) return fail(B200ORB_E_ARG, "n_pairs must be >= 1");
+    CU_TRY(cudaSetDevice(b->eng.device));
+    TRY(batch_host_setup(b));
+    const Plan& P = b->eng.hp.P;
+    const size_t C = P.kp_total, HW = (size_t)b->H * b->W, NT = n_pairs;
+    int k = 0;
+    for (int p0 = 0; p0 < n_pairs; p0 += b->P, ++k) {
+        const int s = k & 1;
+        const size_t np = std::min(b->P, n_pairs - p0);
+        if (k >= 2) CU_TRY(cudaStreamWaitEvent(b->s_in, b->ev_comp[s], 0));     // inputs of chunk k-2 consumed
+        CU_TRY(cudaMemcpyAsync(b->d_in[s], h_left + (size_t)p0 * HW, np * HW, cudaMemcpyHostToDevice, b->s_in));
+        CU_TRY(cudaMemcpyAsync(b->d_in[s] + np * HW, h_right + (size_t)p0 * HW, np * HW, cudaMemcpyHostToDevice, b->s_in));
+        CU_TRY(cudaEventRecord(b->ev_in[s], b->s_in));
+        CU_TRY(cudaStreamWaitEvent(b->s_comp, b->ev_in[s], 0));
+        if (k >= 2) CU_TRY(cudaStreamWaitEvent(b->s_comp, b->ev_out[s], 0));   // outputs of chunk k-2 downloaded
+        TRY(b200orb_batch_run_device(b, b->d_in[s], b->d_in[s] + np * HW, (int)np, mbf, fx, b->d_kps[s], b->d_desc[s], b->d_nkp[s],
+                                     b->d_uR[s], b->d_dep[s], b->d_mi[s], b->s_comp));
+        CU_TRY(cudaEventRecord(b->ev_comp[s], b->s_comp));
+        CU_TRY(cudaStreamWaitEvent(b->s_out, b->ev_comp[s], 0));
+        for (int side = 0; side < 2; ++side) {
+            CU_TRY(cudaMemcpyAsync(h_kps + (side * NT + p0) * C * 6, b->d_kps[s] + side * np * C * 6, np * C * 24, cudaMemcpyDeviceToHost, b->s_out));
+            CU_TRY(cudaMemcpyAsync(h_desc + (side * NT + p0) * C * 32, b->d_desc[s] + side * np * C * 32, np * C * 32, cudaMemcpyDeviceToHost, b->s_out));
+            CU_TRY(cudaMemcpyAsync(h_nkp + side * NT + p0, b->d_nkp[s] + side * np, np * 4, cudaMemcpyDeviceToHost, b->s_out));
+        }
+        CU_TRY(cudaMemcpyAsync(h_uRight + (size_t)p0 * C, b->d_uR[s], np * C * 4, cudaMemcpyDeviceToHost, b->s_out));
+        CU_TRY(cudaMemcpyAsync(h_depth + (size_t)p0 * C, b->d_dep[s], np * C * 4, cudaMemcpyDeviceToHost, b->s_out));
+        if (h_matchIdx) CU_TRY(cudaMemcpyAsync(h_matchIdx + (size_t)p0 * C, b->d_mi[s], np * C * 4, cudaMemcpyDeviceToHost, b->s_out));
+        CU_TRY(cudaEventRecord(b->ev_out[s], b->s_out));
+    }
+    CU_TRY(cudaStreamSynchronize(b->s_out));
+    CU_TRY(cudaStreamSynchronize(b->s_comp));
+    return 0;
+}
+
+int b200orb_host_alloc(void** p, size_t bytes) {
+    if (!p) return fail(B200ORB_E_ARG, "p is NULL");
+    CU_TRY(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return 0;
+}
+int b200orb_host_free(void* p) {
+    CU_TRY(cudaFreeHost(p));
+    return 0;
+}
+
+}  // extern "C"

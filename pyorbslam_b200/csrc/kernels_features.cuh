@@ -1,0 +1,323 @@
+// K4+K6: orientation (IC_Angle) + rBRIEF descriptor + output assembly; K7+K8: stereo matching.
+// Float arithmetic here must reproduce the host bit-for-bit: the translation unit is compiled with
+// --fmad=false (no contraction) and divisions use the IEEE-rounded intrinsics.
+#pragma once
+#include "plan.h"
+#include "../../include/b200orb_pattern31.h"
+
+__device__ __constant__ signed char c_pattern[1024] = {B200ORB_PATTERN_VALUES};
+
+// cv::fastAtan2 (degrees), scalar polynomial path
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale,
+                p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, ax + eps);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = __fdiv_rn(ax, ay + eps);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+// glibc 2.39 sinf/cosf (ARM optimized-routines sincosf) on [0, 2*pi]: fp64 polynomial, one rounding to fp32
+// (the CPU twin in oracle/cvprims.hpp is checked against the host libm on every float).
+__device__ __forceinline__ double sc_sin_poly(double x, double x2) {
+    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    const double x3 = x * x2, s1p = s2 + x2 * s3, x7 = x3 * x2, s = x + x3 * s1;
+    return s + x7 * s1p;
+}
+__device__ __forceinline__ double sc_cos_poly(double x2, bool neg) {
+    double c0 = 0x1p0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5, c3 = -0x1.6c087e89a359dp-10,
+           c4 = 0x1.99343027bf8c3p-16;
+    if (neg) { c0 = -c0; c1 = -c1; c2 = -c2; c3 = -c3; c4 = -c4; }
+    const double x4 = x2 * x2, c2p = c3 + x2 * c4, c1p = c1 + x2 * c2, x6 = x4 * x2, c = c0 + x2 * c1p;
+    return c + x6 * c2p;
+}
+__device__ __forceinline__ void glibc_sincosf(float y, float* sp, float* cp) {
+    double x = (double)y;
+    const unsigned top = (__float_as_uint(y) >> 20) & 0x7ff;
+    if (top < ((__float_as_uint(0x1.921FB6p-1f) >> 20) & 0x7ff)) {
+        if (top < ((__float_as_uint(0x1p-12f) >> 20) & 0x7ff)) { *sp = y; *cp = 1.0f; return; }
+        const double x2 = x * x;
+        *sp = (float)sc_sin_poly(x, x2);
+        *cp = (float)sc_cos_poly(x2, false);
+        return;
+    }
+    const double r = x * 0x1.45F306DC9C883p+23;
+    const int n = ((int)r + 0x800000) >> 24;
+    x = x - (double)n * 0x1.921FB54442D18p0;
+    const double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    const bool tab = (n & 2) != 0;
+    const double xs = x * s, x2 = x * x;
+    *sp = (float)((n & 1) ? sc_cos_poly(x2, tab) : sc_sin_poly(xs, x2));
+    *cp = (float)(((n ^ 1) & 1) ? sc_cos_poly(x2, tab) : sc_sin_poly(xs, x2));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 + K6 + a10: one warp per output keypoint.  Level keypoints come from K3 in list order; the warp finds
+// its level by the per-level counts (levels ascending, ORBextractor.cpp:1075-1103), computes
+//   * IC_Angle (:77-104): m10/m01 over the radius-15 disc on the UN-blurred level, lanes = columns,
+//     31 coalesced row reads, warp-shuffle reduction, fastAtan2;
+//   * computeOrbDescriptor (:108-147): lane i produces descriptor byte i from 16 rotated samples of the
+//     BLURRED level, coordinates rounded half-to-even, a = cosf, b = sinf of angle * (float)(pi/180);
+//   * the output row: (x, y) * mvScaleFactor[level] for level > 0 (:1094-1100), size, angle, response, octave.
+// ------------------------------------------------------------------------------------------------
+#define DESC_WARPS 8
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
+                                                              const u8* __restrict__ blur, const u32* __restrict__ lvl_kp,
+                                                              const int* __restrict__ lvl_cnt, float* __restrict__ kps,
+                                                              u8* __restrict__ desc, int* __restrict__ nkp) {
+    __shared__ signed char pat[1024];
+    for (int i = threadIdx.x; i < 1024; i += DESC_WARPS * 32) pat[i] = c_pattern[i];
+    __syncthreads();
+    const int slot = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
+    const int* cnt = lvl_cnt + (size_t)slot * P.nlevels;
+    int l = 0, off = 0, total = 0;
+    bool found = false;
+    for (int k = 0; k < P.nlevels; ++k) {
+        const int c = cnt[k];
+        if (!found && i < total + c) { l = k; off = total; found = true; }
+        total += c;
+    }
+    if (i == 0 && lane == 0) nkp[slot] = total;
+    if (!found) return;
+    const LevelGeom& G = P.lv[l];
+    const u32 packed = lvl_kp[(size_t)slot * P.kp_total + G.kp_ofs + (i - off)];
+    const int x = packed & 0xfff, y = (packed >> 12) & 0xfff, resp = packed >> 24;
+
+    // ---- orientation ----
+    const u8* c = pyr + (size_t)slot * P.pyr_bytes + G.pyr_ofs + (size_t)(y + ORB_EDGE) * G.pitch + (x + ORB_EDGE);
+    const int u = lane - 15;
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int au = u < 0 ? -u : u;
+#pragma unroll 1
+        for (int v = -15; v <= 15; ++v) {
+            if (au <= P.umax[v < 0 ? -v : v]) {
+                const int val = c[v * G.pitch + u];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- descriptor ----
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    float a, b;
+    glibc_sincosf(angle * factorPI, &b, &a);
+    const u8* bc = blur + (size_t)slot * P.blur_bytes + G.blur_ofs + (size_t)y * G.blur_pitch + x;
+    const signed char* pp = pat + lane * 32;
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float x0 = pp[4 * k], y0 = pp[4 * k + 1], x1 = pp[4 * k + 2], y1 = pp[4 * k + 3];
+        const int t0 = bc[__float2int_rn(x0 * b + y0 * a) * G.blur_pitch + __float2int_rn(x0 * a - y0 * b)];
+        const int t1 = bc[__float2int_rn(x1 * b + y1 * a) * G.blur_pitch + __float2int_rn(x1 * a - y1 * b)];
+        val |= (t0 < t1) << k;
+    }
+    desc[((size_t)slot * P.kp_total + i) * 32 + lane] = (u8)val;
+    if (lane < 6) {
+        float o;
+        const float fx = (float)x, fy = (float)y;
+        switch (lane) {
+            case 0: o = l ? fx * G.sf : fx; break;
+            case 1: o = l ? fy * G.sf : fy; break;
+            case 2: o = (float)G.psize; break;
+            case 3: o = angle; break;
+            case 4: o = (float)resp; break;
+            default: o = (float)l; break;
+        }
+        kps[((size_t)slot * P.kp_total + i) * 6 + lane] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7 + K8: Frame.compute_stereo_matches (Frame.py:161-279), one warp per left keypoint.
+//   K7  the row-band candidate test (right keypoint rows floor(y-2s) .. ceil(y+2s) in double, Frame.py:173-179;
+//       octave within +-1, uR in [uL - maxD, uL], :209-215) runs over right-keypoint metadata staged in shared
+//       memory; Hamming distance = __popc over 2 x 16-byte loads; the reference's "first strict minimum in
+//       ascending right index" is the minimum of (dist << 20 | index).
+//   K8  11x11 SAD slide (L = 5) on the keypoint's pyramid level through the reference's step-ignoring pyramid
+//       view, parabola fit, |delta| > 1 rejection, disparity / depth in float32 exactly as
+//       NumPy >= 2 evaluates them.
+// kps rows are float[stride_kp] with (x, y) first and the octave at index `oct_idx`.
+// ------------------------------------------------------------------------------------------------
+#define ST_WARPS 8
+#define ST_LEFT_PER_CTA 64
+#define ST_CHUNK 2048
+
+struct StereoArgs {
+    const float* kpsL; const u8* descL; const int* nL;      // per pair: + pair * stride
+    const float* kpsR; const u8* descR; const int* nR;
+    const u8* pyrL; const u8* pyrR;                         // per pair: + pair * pyr_stride
+    long long kp_stride, desc_stride, pyr_stride;           // element / byte strides between pairs
+    int n_stride;                                           // stride of nL / nR between pairs (ints)
+    int kp_row, oct_idx;                                    // floats per keypoint row, index of the octave
+    int out_stride;                                         // rows per pair in the outputs
+    float mbf32, mb, maxD;
+    double mbf;
+    float* uRight; float* depth; int* matchIdx; int* status;
+};
+
+__device__ __forceinline__ const u8* view_ptr(const u8* base, const StereoGeom& SG, int o, int row, int col) {
+    const int lin = SG.off0[o] + row * SG.w[o] + col;
+    const int pr = lin / SG.plog[o];
+    return base + SG.base[o] + (size_t)pr * SG.pitch[o] + (lin - pr * SG.plog[o]);
+}
+
+__global__ void __launch_bounds__(ST_WARPS * 32) k_stereo(const __grid_constant__ StereoGeom SG, const StereoArgs A) {
+    __shared__ float s_u[ST_CHUNK];
+    __shared__ short2 s_rows[ST_CHUNK];
+    __shared__ unsigned char s_oct[ST_CHUNK];
+    __shared__ unsigned char s_win[ST_WARPS][11 * 11 + 11 * 21 + 4];
+    const int pair = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nL = A.nL[(size_t)pair * A.n_stride], nR = A.nR[(size_t)pair * A.n_stride];
+    const int left0 = blockIdx.x * ST_LEFT_PER_CTA;
+    if (left0 >= nL) return;
+    const float* kL = A.kpsL + (size_t)pair * A.kp_stride;
+    const float* kR = A.kpsR + (size_t)pair * A.kp_stride;
+    const u8* dL = A.descL + (size_t)pair * A.desc_stride;
+    const u8* dR = A.descR + (size_t)pair * A.desc_stride;
+    constexpr int PER_WARP = ST_LEFT_PER_CTA / ST_WARPS;
+
+    unsigned best[PER_WARP];
+#pragma unroll
+    for (int k = 0; k < PER_WARP; ++k) best[k] = (100u << 20);   // bestDist = TH_HIGH, bestIdxR = 0 (Frame.py:203-204)
+
+    for (int c0 = 0; c0 < nR; c0 += ST_CHUNK) {
+        const int cn = min(ST_CHUNK, nR - c0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < cn; j += ST_WARPS * 32) {
+            const float* r = kR + (size_t)(c0 + j) * A.kp_row;
+            const int o = (int)r[A.oct_idx];
+            const double y = (double)r[1], reach = 2.0 * (double)SG.sf[o];
+            s_u[j] = r[0];
+            s_rows[j] = make_short2((short)(int)floor(y - reach), (short)(int)ceil(y + reach));
+            s_oct[j] = (unsigned char)o;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PER_WARP; ++k) {
+            const int iL = left0 + warp + k * ST_WARPS;
+            if (iL >= nL) continue;
+            const float* p = kL + (size_t)iL * A.kp_row;
+            const float uL = p[0], vL = p[1];
+            const int oL = (int)p[A.oct_idx];
+            const int row = (int)vL;
+            const float minU = uL - A.maxD;
+            if (uL < 0) continue;
+            const uint4* dl = reinterpret_cast<const uint4*>(dL + (size_t)iL * 32);
+            const uint4 l0 = dl[0], l1 = dl[1];
+            unsigned b = best[k];
+            for (int j = lane; j < cn; j += 32) {
+                const short2 rr = s_rows[j];
+                const int oR = s_oct[j];
+                const float uR = s_u[j];
+                if (row < rr.x || row > rr.y || oR < oL - 1 || oR > oL + 1 || !(minU <= uR) || !(uR <= uL)) continue;
+                const uint4* dr = reinterpret_cast<const uint4*>(dR + (size_t)(c0 + j) * 32);
+                const uint4 r0 = __ldg(dr), r1 = __ldg(dr + 1);
+                const unsigned d = __popc(l0.x ^ r0.x) + __popc(l0.y ^ r0.y) + __popc(l0.z ^ r0.z) + __popc(l0.w ^ r0.w) +
+                                   __popc(l1.x ^ r1.x) + __popc(l1.y ^ r1.y) + __popc(l1.z ^ r1.z) + __popc(l1.w ^ r1.w);
+                b = min(b, (d << 20) | (unsigned)(c0 + j));
+            }
+            best[k] = b;
+        }
+    }
+
+#pragma unroll
+    for (int k = 0; k < PER_WARP; ++k) {
+        const int iL = left0 + warp + k * ST_WARPS;
+        if (iL >= nL) continue;
+        unsigned b = best[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b = min(b, __shfl_xor_sync(0xffffffffu, b, o));
+        const int bestDist = b >> 20, bestR = b & 0xfffff;
+        const size_t oi = (size_t)pair * A.out_stride + iL;
+        float outU = -1.f, outD = -1.f;
+        int outM = -1;
+        if (bestDist < 75) {    // thOrbDist = (TH_HIGH + TH_LOW) / 2, Frame.py:166,222
+            outM = bestR;
+            const float* p = kL + (size_t)iL * A.kp_row;
+            const float uL = p[0], vL = p[1];
+            const int oL = (int)p[A.oct_idx];
+            const float uR0 = kR[(size_t)bestR * A.kp_row];
+            const double inv = (double)SG.isf[oL];
+            const int su = __double2int_rn((double)uL * inv), sv = __double2int_rn((double)vL * inv);   // python round()
+            const int sr = __double2int_rn((double)uR0 * inv);
+            const int w = SG.w[oL], h = SG.h[oL];
+            bool ok = !(sr < 0 || sr + 11 >= w);                                        // Frame.py:240-243
+            if (ok && (sv - 5 < 0 || sv + 5 >= h || su - 5 < 0 || su + 5 >= w || sr - 10 < 0 || sr + 10 >= w)) {
+                ok = false;                                                             // the reference would raise
+                if (lane == 0) atomicOr(A.status, 1);
+            }
+            if (ok) {
+                unsigned char* wl = s_win[warp];
+                unsigned char* wr = wl + 121;
+                const u8* bl = A.pyrL + (size_t)pair * A.pyr_stride;
+                const u8* br = A.pyrR + (size_t)pair * A.pyr_stride;
+                for (int t = lane; t < 121; t += 32) { const int r = t / 11, cc = t - r * 11; wl[t] = *view_ptr(bl, SG, oL, sv - 5 + r, su - 5 + cc); }
+                for (int t = lane; t < 231; t += 32) { const int r = t / 21, cc = t - r * 21; wr[t] = *view_ptr(br, SG, oL, sv - 5 + r, sr - 10 + cc); }
+                __syncwarp();
+                const int lc = wl[5 * 11 + 5];
+                int dist[11];
+#pragma unroll
+                for (int inc = 0; inc < 11; ++inc) {
+                    const int rc = wr[5 * 21 + inc + 5];
+                    int s = 0;
+                    for (int t = lane; t < 121; t += 32) {
+                        const int r = t / 11, cc = t - r * 11;
+                        s += abs((wl[t] - lc) - (wr[r * 21 + cc + inc] - rc));
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    dist[inc] = s;
+                }
+                __syncwarp();
+                int bestInc = 0, bestSad = dist[0];
+#pragma unroll
+                for (int inc = 1; inc < 11; ++inc) if (dist[inc] < bestSad) { bestSad = dist[inc]; bestInc = inc; }
+                if (bestInc != 0 && bestInc != 10) {                                    // Frame.py:257
+                    float d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll
+                    for (int inc = 1; inc < 10; ++inc) if (inc == bestInc) { d1 = (float)dist[inc - 1]; d2 = (float)dist[inc]; d3 = (float)dist[inc + 1]; }
+                    const float deltaR = __fdiv_rn(d1 - d3, 2.0f * (d1 + d3 - 2.0f * d2));   // Frame.py:264
+                    if (!(deltaR < -1.f || deltaR > 1.f)) {
+                        const float bestuR = SG.sf[oL] * ((float)(sr + bestInc - 5) + deltaR);   // Frame.py:269
+                        const float disparity = uL - bestuR;
+                        if (0.f <= disparity && disparity < A.maxD) {                    // Frame.py:272
+                            if (disparity <= 0.f) {                                      // python-float branch, :273-275
+                                outD = (float)(A.mbf / 0.01);
+                                outU = (float)((double)uL - 0.01);
+                            } else {
+                                outD = __fdiv_rn(A.mbf32, disparity);
+                                outU = bestuR;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            A.uRight[oi] = outU;
+            A.depth[oi] = outD;
+            if (A.matchIdx) A.matchIdx[oi] = outM;
+        }
+    }
+}

@@ -1,0 +1,117 @@
+"""`ORBextractor`: the reference's pybind class (pyORBExtractor/orb_extractor.cpp:22-38) on the B200.
+
+Same constructor keywords, same nine methods, same return types: `operator_kd(image)` returns
+(list of (x, y, size, angle, response, octave) tuples, np.uint8[N,32]) -- owning copies, like the reference's
+casters (opencv_type_casters.h:106-108, 205-240).  The results and the image pyramid also stay resident on the
+device, so the patched `Frame.compute_stereo_matches` (stereo.py) can match without re-uploading anything."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class ORBextractor:
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0):
+        self._h = None
+        h = C.c_void_p()
+        _lib.check(_lib.lib().b200orb_extractor_create(int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST),
+                                                       int(minThFAST), int(device), C.byref(h)))
+        self._h = h
+        self._nlevels = int(nlevels)
+        self._last_desc = None      # identity token: the descriptor array handed out by the last operator_kd
+        self._last_n = -1
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            try:
+                _lib.lib().b200orb_extractor_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ---- getters, ORBextractor.h:62-86 ----
+    def GetLevels(self):
+        return int(_lib.lib().b200orb_get_levels(self._h))
+
+    def GetScaleFactor(self):
+        return float(_lib.lib().b200orb_get_scale_factor(self._h))
+
+    def _tab(self, fn, dtype=np.float32):
+        out = np.empty(self._nlevels, dtype)
+        _lib.check(getattr(_lib.lib(), fn)(self._h, out.ctypes.data))
+        return out
+
+    def GetScaleFactors(self):
+        return self._tab("b200orb_get_scale_factors").tolist()
+
+    def GetInverseScaleFactors(self):
+        return self._tab("b200orb_get_inverse_scale_factors").tolist()
+
+    def GetScaleSigmaSquares(self):
+        return self._tab("b200orb_get_scale_sigma_squares").tolist()
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._tab("b200orb_get_inverse_scale_sigma_squares").tolist()
+
+    def features_per_level(self):
+        return self._tab("b200orb_get_features_per_level", np.int32).tolist()
+
+    # ---- operator_kd, orb_extractor.cpp:31-38 ----
+    def extract_arrays(self, image):
+        """(kps float32[N,6], desc uint8[N,32]) -- the array form of operator_kd."""
+        image = np.asarray(image)
+        if image.ndim not in (2, 3):
+            raise RuntimeError(f"Unsupported dim {image.ndim}, only support 2d, or 3-d")   # opencv_type_casters.h:181-184
+        if image.dtype not in (np.uint8, np.int32, np.float32):
+            raise RuntimeError("Unsupported type, only support uchar, int32, float")        # opencv_type_casters.h:195-197
+        if image.ndim != 2 or image.dtype != np.uint8:
+            # the reference asserts CV_8UC1 (ORBextractor.cpp:1049) but compiles the assert out (-DNDEBUG) and then
+            # reads the buffer as if it were 8-bit gray; we refuse instead of reproducing undefined behaviour
+            raise RuntimeError("image must be 8-bit single channel (CV_8UC1)")
+        image = np.ascontiguousarray(image)
+        n = C.c_int(0)
+        H, W = image.shape
+        _lib.check(_lib.lib().b200orb_extract(self._h, image.ctypes.data, H, W, C.byref(n)))
+        n = n.value
+        kps = np.empty((n, 6), np.float32)
+        desc = np.empty((n, 32), np.uint8) if n else np.zeros((0, 0), np.uint8)
+        if n:
+            _lib.check(_lib.lib().b200orb_get_results(self._h, kps.ctypes.data, desc.ctypes.data))
+        self._last_desc = desc
+        self._last_n = n
+        return kps, desc
+
+    def operator_kd(self, image):
+        kps, desc = self.extract_arrays(image)
+        rows = kps.tolist()
+        return [(r[0], r[1], r[2], r[3], r[4], int(r[5])) for r in rows], desc
+
+    # ---- GetImagePyramid, ORBextractor.h:84-86 through the Mat caster ----
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        _lib.check(_lib.lib().b200orb_level_size(self._h, int(level), C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def GetImagePyramid(self):
+        out = []
+        for l in range(self._nlevels):
+            w, h = self.level_size(l)
+            v = np.empty((h, w), np.uint8)
+            _lib.check(_lib.lib().b200orb_get_pyramid_level(self._h, l, v.ctypes.data))
+            out.append(v)
+        return out
+
+    # ---- diagnostics used by the parity tests ----
+    def level_image(self, level, blurred=False):
+        w, h = self.level_size(level)
+        v = np.empty((h, w), np.uint8)
+        _lib.check(_lib.lib().b200orb_get_level_image(self._h, int(level), int(bool(blurred)), v.ctypes.data))
+        return v
+
+    def level_candidates(self, level):
+        n = C.c_int(0)
+        _lib.check(_lib.lib().b200orb_get_level_candidates(self._h, int(level), 0, None, C.byref(n)))
+        out = np.empty((max(n.value, 1), 3), np.int32)
+        _lib.check(_lib.lib().b200orb_get_level_candidates(self._h, int(level), n.value, out.ctypes.data, C.byref(n)))
+        return out[:n.value]
