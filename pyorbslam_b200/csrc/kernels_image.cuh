@@ -162,22 +162,27 @@ __device__ __forceinline__ int fast_score(const u8* p, int SP, int t) {
     u32 rb = mb & (mb >> 1); rb &= rb >> 2; rb &= rb >> 4; rb &= mb >> 8;
     u32 rd = md & (md >> 1); rd &= rd >> 2; rd &= rd >> 4; rd &= md >> 8;
     if (!((rb | rd) & 0xffffu)) return 0;
-    // sliding min / max over windows of 9 on the circle (doubling: 2, 4, 8, then +1)
+    // sliding min / max over windows of 9 on the circle (doubling: 2, 4, 8, then +1).
+    // Works on the biased differences D = 255 + v - p_k in [0, 510]: the bright side min(p_k - v) equals
+    // 255 - max(D), so no negated operand ever feeds a max -- ptxas 12.9 (sm_100a, -O1 and above) drops the
+    // negation when it fuses max(x, -y) chains into VIMNMX3 (caught by tests/cuda_unit/fast_unit.cu).
     int d[16], a[16], b[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = v - q[k];
+    for (int k = 0; k < 16; ++k) d[k] = 255 + v - q[k];
 #pragma unroll
     for (int k = 0; k < 16; ++k) { a[k] = min(d[k], d[(k + 1) & 15]); b[k] = max(d[k], d[(k + 1) & 15]); }
     int a4[16], b4[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) { a4[k] = min(a[k], a[(k + 2) & 15]); b4[k] = max(b[k], b[(k + 2) & 15]); }
-    int best = 0;
+    int bestDark = 0, worstBright = 510;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const int mn = min(min(a4[k], a4[(k + 4) & 15]), d[(k + 8) & 15]);
         const int mx = max(max(b4[k], b4[(k + 4) & 15]), d[(k + 8) & 15]);
-        best = max(best, max(mn, -mx));
+        bestDark = max(bestDark, mn);          // 255 + max_arcs min(v - p)
+        worstBright = min(worstBright, mx);    // 255 - max_arcs min(p - v)
     }
+    const int best = max(bestDark - 255, 255 - worstBright);
     return best - 1;
 }
 
