@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- stereo frames/s of the B200 stereo ORB front-end (extract L + extract R + stereo match).
+
+  python bench.py [--gpus N --steps K --warmup W]            our arm (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference [--steps K --warmup W]    the reference's CPU implementation on the host cores
+
+Workload = BASELINE.json configs[2]: a batch of synthetic KITTI-shape stereo pairs (1241x376, 2000 features,
+8 levels, 1.2, FAST 20/7), `--pairs` pairs per GPU per step (weak scaling: frames are independent, every rank
+owns its own batch, no data-path collective).  One step = one pass of the hot path over that batch.
+  value : frames/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e   : frames/s through the host-buffer C-ABI call (pinned H2D of the images + D2H of every result inside the timing)
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ORB = dict(nfeatures=2000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7)   # configs/KITTI00-02.yaml:36-50
+H, W = 376, 1241
+MBF, FX = 386.1448, 718.856                                                       # configs/KITTI00-02.yaml:7,24
+METRIC, UNIT = "stereo_frames_per_sec", "frames/s"
+
+
+# ------------------------------------------------------------------------------------------------ geometry / bytes
+def level_sizes(Hh=H, Ww=W, nlevels=8, scale=1.2):
+    s, out = np.float32(1.0), []
+    for l in range(nlevels):
+        if l:
+            s = np.float32(np.float64(s) * np.float64(np.float32(scale)))
+        inv = np.float32(1.0) / s
+        out.append((int(np.rint(np.float32(Ww) * inv)), int(np.rint(np.float32(Hh) * inv))))
+    return out
+
+
+def algorithmic_bytes(K=2000):
+    """bytes each kernel must move per IMAGE (per PAIR for stereo), and B_frame."""
+    lv = level_sizes()
+    S0 = lv[0][0] * lv[0][1]
+    s = [w * h for w, h in lv]
+    b = [(w + 38) * (h + 38) for w, h in lv]
+    S, Sb = sum(s), sum(b)
+    per_image = {
+        "border0": S0 + b[0],
+        "resize_chain": (S - s[-1]) + (Sb - b[0]),
+        "blur": 2 * S,
+        "fast_cells": S,
+        "octree": None,                      # data dependent: 4 B per FAST candidate in, 4 B per keypoint out (filled at run time)
+        "orient_describe": S + 56 * K,
+    }
+    stereo_per_pair = 2 * 56 * K + 352 * K + 8 * K
+    B_img = S0 + Sb + (S - s[-1]) + S + 2 * S + S + 56 * K
+    return per_image, stereo_per_pair, 2 * B_img + stereo_per_pair
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_worker(args):
+    """One stereo frame the way the reference computes it: ORBextractor.operator_kd x2 (+ tuple -> cv2.KeyPoint lists,
+    Frame.py:114-121) + GetImagePyramid x2 (Frame.py:59-60) + compute_stereo_matches (Frame.py:161-279)."""
+    L, R, use_ref = args
+    import oracle as O
+    from oracle import refext, stereo_py
+    global _W_EXT
+    if "_W_EXT" not in globals():
+        p = (ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"])
+        mk = (lambda: refext.RefExtractor(*p, kind="shipped")) if use_ref else (lambda: O.OracleExtractor(*p))
+        _W_EXT = (mk(), mk())
+    eL, eR = _W_EXT
+    t0 = time.perf_counter()
+    tl, dl = eL.operator_kd(L)
+    tr, dr = eR.operator_kd(R)
+    try:
+        import cv2
+        kl = [cv2.KeyPoint(*k) for k in tl]
+        kr = [cv2.KeyPoint(*k) for k in tr]
+        keysL = [(k.pt[0], k.pt[1], k.octave) for k in kl]
+        keysR = [(k.pt[0], k.pt[1], k.octave) for k in kr]
+    except ImportError:
+        keysL = [(k[0], k[1], k[5]) for k in tl]
+        keysR = [(k[0], k[1], k[5]) for k in tr]
+    pl, pr = eL.GetImagePyramid(), eR.GetImagePyramid()
+    t1 = time.perf_counter()
+    u, d = stereo_py.stereo_matches(keysL, dl, keysR, dr, eL.GetScaleFactors(), eL.GetInverseScaleFactors(), pl, pr, MBF, np.float32(FX))
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, sum(1 for v in u if v != -1)
+
+
+class CpuReference:
+    """The reference CPU path on the host cores.  Extractor = the reference's own ORBextractor.cpp compiled unmodified
+    (oracle/_ref/libref_shipped.so, -O3) when present, else the oracle port; stereo = Python restatement of
+    Frame.compute_stereo_matches with the reference's per-keypoint Python structure (oracle/stereo_py.py)."""
+
+    def __init__(self, workers=None):
+        from oracle import refext
+        import oracle as O
+        O.build()
+        self.use_ref = refext.available("shipped")
+        self.workers = workers or max(1, min(os.cpu_count() or 1, 32))
+        self.pool = mp.get_context("fork").Pool(self.workers)
+        from pyorbslam_b200.synthetic import make_stereo_pair
+        self.pairs = [make_stereo_pair(i) for i in range(min(self.workers, 8))]   # a few distinct frames, reused round-robin
+
+    def step(self, n_pairs):
+        work = [(self.pairs[i % len(self.pairs)][0], self.pairs[i % len(self.pairs)][1], self.use_ref) for i in range(n_pairs)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, work, chunksize=1)
+        dt = time.perf_counter() - t0
+        return dt, res
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def describe(self, n_pairs, res):
+        te = float(np.mean([r[0] for r in res]))
+        ts = float(np.mean([r[1] for r in res]))
+        return (f"{n_pairs} synthetic 1241x376 pairs per step over {self.workers} worker processes; per frame on one core: "
+                f"extract L+R + KeyPoint lists + pyramids {te*1e3:.0f} ms "
+                f"({'reference ORBextractor.cpp compiled -O3 against oracle/cvshim scalar primitives' if self.use_ref else 'oracle port'}), "
+                f"compute_stereo_matches {ts*1e3:.0f} ms (Python restatement, reference structure)")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ref = CpuReference()
+    n = 2 * ref.workers
+    for _ in range(args.warmup):
+        ref.step(min(n, ref.workers))
+    total_t, res = 0.0, []
+    for _ in range(args.steps):
+        dt, r = ref.step(n)
+        total_t += dt
+        res = r
+    ref.close()
+    fps = n * args.steps / total_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": workload_config(n, None),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ref.workers, "kind": "reference" if ref.use_ref else "port",
+                         "sample": ref.describe(n, res)},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(pairs, chunk):
+    return {"workload": "BASELINE.json configs[2]: batch of synthetic KITTI00-02-shape stereo pairs, extract L+R + compute_stereo_matches",
+            "image": [H, W], **ORB, "bf": MBF, "fx": FX, "pairs_per_gpu_per_step": pairs, "chunk_pairs": chunk,
+            "l2": "inputs of one step exceed the 126 MB L2 (0.93 MB per pair)", "parallelism": "frames sharded per GPU, no collective"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_b200_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # CPU baseline first (rank 0 of a 1-GPU run only), before this process creates a CUDA context
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = CpuReference()
+        n = 2 * ref.workers
+        ref.step(ref.workers)                      # warm the pool / page in the libraries
+        dt, res = ref.step(n)
+        ref.close()
+        cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": ref.workers, "kind": "reference" if ref.use_ref else "port",
+                        "sample": ref.describe(n, res),
+                        "one_core_frames_per_sec": 1.0 / float(np.mean([r[0] + r[1] for r in res]))}
+
+    import torch
+    import torch.distributed as dist
+    from pyorbslam_b200 import StereoFrontend, _lib
+    from pyorbslam_b200.synthetic import make_stereo_pair
+
+    if _lib.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: pyorbslam_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, P = args.pairs, args.chunk
+    nb = args.base_pairs
+    # synthetic batch: `nb` distinct scenes per rank, frame i = scene (i % nb) rolled horizontally by 9 * (i // nb) px
+    # in BOTH views (disparities unchanged; every frame lands differently on the FAST cell grid)
+    base = [make_stereo_pair(1000 * rank + i) for i in range(nb)]
+    bl = torch.from_numpy(np.stack([p[0] for p in base])).to(dev)
+    br = torch.from_numpy(np.stack([p[1] for p in base])).to(dev)
+    left = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    right = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    for g in range(0, B, nb):
+        m = min(nb, B - g)
+        left[g:g + m] = torch.roll(bl[:m], shifts=9 * (g // nb), dims=2)
+        right[g:g + m] = torch.roll(br[:m], shifts=9 * (g // nb), dims=2)
+    del bl, br
+
+    fe = StereoFrontend(ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"], H, W, P, device=local)
+    chunks = [(c, min(P, B - c)) for c in range(0, B, P)]
+    outs = [fe.alloc_outputs(n) for _, n in chunks]
+
+    def step():
+        for (c, n), o in zip(chunks, outs):
+            fe.run(left[c:c + n], right[c:c + n], MBF, FX, out=o)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    fe.profile(True, max_calls=args.steps * len(chunks))
+    clocks = ClockSampler(local)
+    l0 = _lib.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.kernel_launches() - l0
+    clk = clocks.stop()
+    stage_ms, prof_calls, prof_pairs = fe.profile_read()
+    fe.profile(False)
+    ncand = fe.candidate_count(2 * chunks[-1][1]) / (2 * chunks[-1][1])
+    nkp = float(torch.cat([o["nkp"].float().flatten() for o in outs]).mean())
+    matched = float(sum(int(((o["uRight"] >= 0) & (torch.arange(fe.capacity, device=dev)[None, :] < o["nkp"][0][:, None])).sum()) for o in outs)) / B
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t)
+    value = world * B * args.steps / (ms_max / 1e3)
+
+    # ---- end to end through the host-buffer C-ABI call ----
+    Be = min(B, args.e2e_pairs)
+    lh = left[:Be].cpu().pin_memory()
+    rh = right[:Be].cpu().pin_memory()
+    oh = fe.alloc_outputs(Be, pinned_host=True)
+    for _ in range(2):
+        fe.run_host(lh, rh, MBF, FX, out=oh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fe.run_host(lh, rh, MBF, FX, out=oh)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * Be * args.steps / float(te)
+    d2h = sum(v.numel() * v.element_size() for v in oh.values())
+    # the e2e result must equal the device-resident one (same frames)
+    same = bool((oh["nkp"][:, :chunks[0][1]] == outs[0]["nkp"].cpu()).all())
+
+    if rank == 0:
+        per_image, stereo_pp, B_frame = algorithmic_bytes(ORB["nfeatures"])
+        per_image["octree"] = 4 * ncand + 4 * nkp
+        peak, peak_src = measured_peak()
+        kernels = {}
+        launches_per_call = {"border0": 1, "resize_chain": ORB["nlevels"] - 1, "blur": 1, "fast_cells": 1, "octree": 1, "orient_describe": 1, "stereo": 1}
+        for k, tot in stage_ms.items():
+            bytes_total = (stereo_pp * prof_pairs) if k == "stereo" else (per_image[k] * 2 * prof_pairs)
+            gbs = bytes_total / (tot / 1e3) / 1e9 if tot > 0 else 0.0
+            kernels[k] = {"ms_total": tot, "share": tot / max(sum(stage_ms.values()), 1e-9), "avg_launch_ms": tot / max(prof_calls * launches_per_call[k], 1),
+                          "algorithmic_bytes_per_launch": bytes_total / max(prof_calls * launches_per_call[k], 1), "achieved_gbs": gbs, "frac": gbs / peak}
+        dom = max(stage_ms, key=stage_ms.get)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(dom)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": workload_config(B, P), "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * Be * H * W, "d2h_bytes_per_step": d2h, "pairs_per_step": Be,
+                    "matches_device_resident_result": same},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                         "avg_launch_ms": kernels[dom]["avg_launch_ms"], "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes_per_launch"]},
+            "roofline_whole_path": {"B_frame_bytes": B_frame, "achieved": B_frame * (value / world) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": B_frame * (value / world) / 1e9 / peak},
+            "kernels": kernels,
+            "workload_stats": {"keypoints_per_image": nkp, "fast_candidates_per_image": ncand, "stereo_matches_per_pair": matched,
+                               "workspace_bytes": fe.workspace_bytes()},
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=4096, help="stereo pairs per GPU per step (BASELINE.json configs[2]: 4096)")
+    ap.add_argument("--chunk", type=int, default=128, help="pairs per kernel-sequence launch")
+    ap.add_argument("--base-pairs", type=int, default=16, help="distinct synthetic scenes per rank")
+    ap.add_argument("--e2e-pairs", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

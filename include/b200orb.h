@@ -135,6 +135,19 @@ int b200orb_batch_run_host(b200orb_batch* b, const uint8_t* h_left, const uint8_
                            double mbf, float fx, float* h_kps, uint8_t* h_desc, int32_t* h_nkp,
                            float* h_uRight, float* h_depth, int32_t* h_matchIdx);
 
+/* diagnostic: total number of FAST candidates (the octree kernel's input) in the first n_images slots of the last
+ * run -- bench.py uses it for the octree kernel's algorithmic byte count */
+int b200orb_batch_candidate_count(b200orb_batch* b, int n_images, long long* total);
+
+/* Per-kernel timing of the batched path, measured with CUDA events recorded on the launching stream between
+ * the kernels of every b200orb_batch_run_device call (up to max_calls calls are kept).  Stages:
+ * 0 level-0 border, 1 resize chain (nlevels-1 launches), 2 blur, 3 FAST cells, 4 octree, 5 orient+describe, 6 stereo.
+ * _read sums the elapsed milliseconds per stage over the recorded calls, reports how many calls / pairs they
+ * covered, and clears the record. */
+#define B200ORB_NSTAGE 7
+int b200orb_batch_profile(b200orb_batch* b, int enable, int max_calls);
+int b200orb_batch_profile_read(b200orb_batch* b, float* ms_per_stage, int* n_calls, long long* n_pairs);
+
 /* pinned host memory helpers for callers without their own allocator */
 int b200orb_host_alloc(void** p, size_t bytes);
 int b200orb_host_free(void* p);

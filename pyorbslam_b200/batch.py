@@ -35,6 +35,25 @@ class StereoFrontend:
     def workspace_bytes(self):
         return int(_lib.lib().b200orb_batch_workspace_bytes(self._h))
 
+    STAGES = ("border0", "resize_chain", "blur", "fast_cells", "octree", "orient_describe", "stereo")
+
+    def profile(self, enable=True, max_calls=1024):
+        """Record CUDA events between the kernels of the next run() calls (on the launching stream)."""
+        _lib.check(_lib.lib().b200orb_batch_profile(self._h, int(bool(enable)), int(max_calls)))
+
+    def profile_read(self):
+        """-> ({stage: total ms}, calls, pairs) over the calls recorded since profile(); clears the record."""
+        ms = (C.c_float * 7)()
+        n = C.c_int(0)
+        pairs = C.c_longlong(0)
+        _lib.check(_lib.lib().b200orb_batch_profile_read(self._h, ms, C.byref(n), C.byref(pairs)))
+        return {s: float(ms[i]) for i, s in enumerate(self.STAGES)}, n.value, pairs.value
+
+    def candidate_count(self, n_images):
+        t = C.c_longlong(0)
+        _lib.check(_lib.lib().b200orb_batch_candidate_count(self._h, int(n_images), C.byref(t)))
+        return int(t.value)
+
     def alloc_outputs(self, n_pairs, pinned_host=False):
         C_ = self.capacity
         kw = dict(device="cpu", pin_memory=True) if pinned_host else dict(device=f"cuda:{self.device}")

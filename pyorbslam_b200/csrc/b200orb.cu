@@ -236,7 +236,10 @@ struct Engine {
         return 0;
     }
     // images: slots [0, splitA) from imgA, [splitA, n) from imgB; outputs: kps [n][kp_total][6], desc [n][kp_total][32], nkp [n]
-    int extract(const u8* imgA, const u8* imgB, int splitA, int n, float* d_kps, u8* d_desc, int* d_nkp, cudaStream_t st) {
+    // evs (optional): B200ORB_NSTAGE + 1 events; evs[0] must already be recorded by the caller, evs[k + 1] is
+    // recorded after stage k (0 border, 1 resize chain, 2 blur, 3 FAST, 4 octree, 5 describe; 6 = stereo, by the caller)
+    int extract(const u8* imgA, const u8* imgB, int splitA, int n, float* d_kps, u8* d_desc, int* d_nkp, cudaStream_t st,
+                cudaEvent_t* evs = nullptr) {
         if (n < 1 || n > S) return fail(B200ORB_E_ARG, "slot count out of range");
         const Plan& P = hp.P;
         {
@@ -244,6 +247,7 @@ struct Engine {
             dim3 grid(((G.pitch >> 2) * G.rows + 255) / 256, n);
             k_border0<<<grid, 256, 0, st>>>(P, imgA, imgB, splitA, d_pyr);
             ++g_launches;
+            if (evs) cudaEventRecord(evs[1], st);
         }
         for (int l = 1; l < P.nlevels; ++l) {
             const LevelGeom& G = P.lv[l];
@@ -251,19 +255,24 @@ struct Engine {
             k_resize<<<grid, 256, 0, st>>>(P, l, d_pyr, d_xtab, d_ytab);
             ++g_launches;
         }
+        if (evs) cudaEventRecord(evs[2], st);
         k_blur<<<dim3(P.blur_ctas, n), 256, 0, st>>>(P, d_pyr, d_blur);
         ++g_launches;
+        if (evs) cudaEventRecord(evs[3], st);
         if (P.fast_ctas > 0) {
             k_fast_cells<<<dim3(P.fast_ctas, n), FAST_WARPS * 32, hp.fast_smem, st>>>(P, d_pyr, d_cand, d_cellcnt, hp.fast_SP, hp.fast_SR,
                                                                                    hp.fast_TP, hp.fast_TR);
             ++g_launches;
         }
+        if (evs) cudaEventRecord(evs[4], st);
         k_octree<<<dim3(P.nlevels, n), OCT_THREADS, hp.oct_smem, st>>>(P, d_cand, d_cellcnt, d_scratch, d_lvlkp, d_lvlcnt, hp.oct_capN,
                                                                       hp.oct_capK, hp.oct_capC);
         ++g_launches;
+        if (evs) cudaEventRecord(evs[5], st);
         k_describe<<<dim3((P.kp_total + DESC_WARPS - 1) / DESC_WARPS, n), DESC_WARPS * 32, 0, st>>>(P, d_pyr, d_blur, d_lvlkp, d_lvlcnt, d_kps,
                                                                                                     d_desc, d_nkp);
         ++g_launches;
+        if (evs) cudaEventRecord(evs[6], st);
         CU_TRY(cudaGetLastError());
         return 0;
     }
@@ -326,6 +335,11 @@ struct b200orb_batch {
     float* d_uR[2] = {nullptr, nullptr}; float* d_dep[2] = {nullptr, nullptr}; int* d_mi[2] = {nullptr, nullptr};
     bool host_ready = false;
     long long host_bytes = 0;
+    // per-kernel timing (b200orb_batch_profile): a pool of event sets, one set per run_device call
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_pairs;
+    int prof_cap = 0, prof_used = 0;
+    bool prof_on = false;
 };
 
 extern "C" {
@@ -618,6 +632,7 @@ void b200orb_batch_destroy(b200orb_batch* b) {
     if (!b) return;
     cudaSetDevice(b->eng.device);
     b->eng.release();
+    for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         cudaFree(b->d_in[i]); cudaFree(b->d_kps[i]); cudaFree(b->d_desc[i]); cudaFree(b->d_nkp[i]);
         cudaFree(b->d_uR[i]); cudaFree(b->d_dep[i]); cudaFree(b->d_mi[i]);
@@ -644,7 +659,14 @@ int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint
     cudaStream_t st = (cudaStream_t)stream;
     const Plan& P = b->eng.hp.P;
     const size_t C = P.kp_total;
-    TRY(b->eng.extract(d_left, d_right, n_pairs, 2 * n_pairs, d_kps, d_desc, d_nkp, st));
+    cudaEvent_t* evs = nullptr;
+    if (b->prof_on && b->prof_used < b->prof_cap) {
+        evs = b->prof_ev.data() + (size_t)b->prof_used * (B200ORB_NSTAGE + 1);
+        b->prof_pairs[b->prof_used] = n_pairs;
+        ++b->prof_used;
+        CU_TRY(cudaEventRecord(evs[0], st));
+    }
+    TRY(b->eng.extract(d_left, d_right, n_pairs, 2 * n_pairs, d_kps, d_desc, d_nkp, st, evs));
     StereoGeom SG;
     b->eng.stereo_geom(SG);
     StereoArgs A;
@@ -657,7 +679,64 @@ int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint
     A.kp_row = 6; A.oct_idx = 5; A.out_stride = (int)C;
     A.uRight = d_uRight; A.depth = d_depth; A.matchIdx = d_matchIdx; A.status = b->eng.d_status;
     fill_stereo_consts(A, mbf, fx);
-    return launch_stereo(SG, A, (int)C, n_pairs, st);
+    TRY(launch_stereo(SG, A, (int)C, n_pairs, st));
+    if (evs) CU_TRY(cudaEventRecord(evs[B200ORB_NSTAGE], st));
+    return 0;
+}
+
+int b200orb_batch_candidate_count(b200orb_batch* b, int n_images, long long* total) {
+    if (!b || !total) return fail(B200ORB_E_ARG, "NULL argument");
+    if (n_images < 1 || n_images > b->eng.S) return fail(B200ORB_E_ARG, "n_images out of range");
+    CU_TRY(cudaSetDevice(b->eng.device));
+    const Plan& P = b->eng.hp.P;
+    std::vector<int> cnt((size_t)n_images * P.ncells);
+    CU_TRY(cudaMemcpy(cnt.data(), b->eng.d_cellcnt, cnt.size() * 4, cudaMemcpyDeviceToHost));
+    long long t = 0;
+    int real_cells = 0;
+    for (int l = 0; l < P.nlevels; ++l) real_cells += P.lv[l].nRows * P.lv[l].nCols;
+    for (int i = 0; i < n_images; ++i)
+        for (int c = 0; c < real_cells; ++c) t += cnt[(size_t)i * P.ncells + c];
+    *total = t;
+    return 0;
+}
+
+int b200orb_batch_profile(b200orb_batch* b, int enable, int max_calls) {
+    if (!b) return fail(B200ORB_E_ARG, "NULL batch");
+    CU_TRY(cudaSetDevice(b->eng.device));
+    if (enable && max_calls > b->prof_cap) {
+        const size_t want = (size_t)max_calls * (B200ORB_NSTAGE + 1);
+        while (b->prof_ev.size() < want) {
+            cudaEvent_t e;
+            CU_TRY(cudaEventCreate(&e));
+            b->prof_ev.push_back(e);
+        }
+        b->prof_pairs.resize(max_calls);
+        b->prof_cap = max_calls;
+    }
+    b->prof_on = enable != 0;
+    b->prof_used = 0;
+    return 0;
+}
+
+int b200orb_batch_profile_read(b200orb_batch* b, float* ms_per_stage, int* n_calls, long long* n_pairs) {
+    if (!b || !ms_per_stage || !n_calls) return fail(B200ORB_E_ARG, "NULL argument");
+    CU_TRY(cudaSetDevice(b->eng.device));
+    for (int k = 0; k < B200ORB_NSTAGE; ++k) ms_per_stage[k] = 0.f;
+    long long pairs = 0;
+    for (int c = 0; c < b->prof_used; ++c) {
+        cudaEvent_t* evs = b->prof_ev.data() + (size_t)c * (B200ORB_NSTAGE + 1);
+        CU_TRY(cudaEventSynchronize(evs[B200ORB_NSTAGE]));
+        for (int k = 0; k < B200ORB_NSTAGE; ++k) {
+            float ms = 0.f;
+            CU_TRY(cudaEventElapsedTime(&ms, evs[k], evs[k + 1]));
+            ms_per_stage[k] += ms;
+        }
+        pairs += b->prof_pairs[c];
+    }
+    *n_calls = b->prof_used;
+    if (n_pairs) *n_pairs = pairs;
+    b->prof_used = 0;
+    return 0;
 }
 
 static int batch_host_setup(b200orb_batch* b) {

@@ -1,0 +1,84 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/b200orb.h
+declares, its host-side tables equal the oracle's, and compute calls fail loudly without a CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle as O
+from pyorbslam_b200 import ORBextractor, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200orb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(b200orb_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_constructor_tables_match_oracle_and_reference_known_answers():
+    e = ORBextractor(nfeatures=2000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7)   # keyword names of orb_extractor.cpp:23
+    o = O.OracleExtractor(2000, 1.2, 8, 20, 7)
+    assert e.GetLevels() == 8
+    assert e.GetScaleFactor() == float(np.float32(1.2))
+    assert e.GetScaleFactors() == o.GetScaleFactors()
+    assert e.GetInverseScaleFactors() == o.GetInverseScaleFactors()
+    assert e.GetScaleSigmaSquares() == o.GetScaleSigmaSquares()
+    assert e.GetInverseScaleSigmaSquares() == o.GetInverseScaleSigmaSquares()
+    assert e.features_per_level() == [434, 362, 302, 251, 209, 175, 145, 122]
+    assert all(isinstance(v, float) for v in e.GetScaleFactors())
+
+
+def test_bad_parameters_raise():
+    with pytest.raises(ValueError):
+        ORBextractor(100, 1.2, 0, 20, 7)
+    with pytest.raises(ValueError):
+        ORBextractor(100, 1.0, 8, 20, 7)
+    with pytest.raises(ValueError):
+        ORBextractor(100, 1.2, 17, 20, 7)
+
+
+def test_input_contract_errors_match_the_caster():
+    e = ORBextractor(100, 1.2, 4, 20, 7)
+    with pytest.raises(RuntimeError):      # opencv_type_casters.h:181-184
+        e.operator_kd(np.zeros(10, np.uint8))
+    with pytest.raises(RuntimeError):      # opencv_type_casters.h:195-197
+        e.operator_kd(np.zeros((10, 10), np.float64))
+    with pytest.raises(RuntimeError):      # CV_8UC1 only (ORBextractor.cpp:1049)
+        e.operator_kd(np.zeros((10, 10, 3), np.uint8))
+    with pytest.raises(_lib.B200OrbError):  # GetImagePyramid before any image
+        e.GetImagePyramid()
+
+
+def test_empty_image_returns_nothing_like_the_reference():
+    e = ORBextractor(100, 1.2, 4, 20, 7)
+    kps, desc = e.operator_kd(np.zeros((0, 0), np.uint8))   # ORBextractor.cpp:1045-1046
+    assert kps == [] and desc.size == 0
+
+
+@pytest.mark.skipif(_lib.device_count() > 0, reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    e = ORBextractor(100, 1.2, 4, 20, 7)
+    with pytest.raises(_lib.B200OrbError):
+        e.operator_kd(np.zeros((100, 200), np.uint8))
+    from pyorbslam_b200.stereo import stereo_host
+    with pytest.raises(_lib.B200OrbError):
+        stereo_host(np.zeros((1, 3), np.float32), np.zeros((1, 32), np.uint8), np.zeros((1, 3), np.float32), np.zeros((1, 32), np.uint8),
+                    [1.0], [1.0], [np.zeros((50, 50), np.uint8)], [np.zeros((50, 50), np.uint8)], 100.0, 300.0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pyorbslam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "liborb_oracle" not in txt and "oracle/_ref" not in txt, f

@@ -1,0 +1,321 @@
+"""Parity tests proper (B200 box): the CUDA path, called through the C ABI (ctypes -> libb200orb.so), against
+  * the committed golden vectors produced by the reference itself (tests/golden/make_golden.py),
+  * the CPU oracle on the same seeded inputs,
+  * size-independent properties at BASELINE.json's full sizes.
+Bars: keypoints / octaves / angles / responses / descriptors / stereo match indices bit-exact;
+uRight / depth within 1e-3 px of the reference (they are in fact bit-exact and asserted so where the
+reference's own output is available)."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as O
+from pyorbslam_b200 import ORBextractor, _lib, install
+from pyorbslam_b200.stereo import compute_stereo_matches, stereo_host, stereo_resident
+from pyorbslam_b200.synthetic import make_stereo_pair, pair_digest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KITTI = (2000, 1.2, 8, 20, 7)
+TOL_PX = 1e-3     # north_star tolerance for uRight / depth
+
+
+def _sha(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def _same(kg, dg, ko, do):
+    assert kg.shape == ko.shape, (kg.shape, ko.shape)
+    assert np.array_equal(kg.view(np.uint32), ko.view(np.uint32))
+    assert dg.shape == do.shape and np.array_equal(dg, do)
+
+
+def test_native_library_is_the_path_and_device_is_b200():
+    assert _lib.device_count() >= 1
+    assert os.path.exists(_lib.LIB_PATH)
+
+
+def test_config1_fixture_image_vs_reference_golden(golden_dir):
+    img = np.load(os.path.join(golden_dir, "kitti06-436.gray.npy"))
+    g = np.load(os.path.join(golden_dir, "kitti06_extract.npz"))
+    e = ORBextractor(*KITTI)
+    before = _lib.kernel_launches()
+    tuples, desc = e.operator_kd(img)
+    assert _lib.kernel_launches() - before >= 8 + 4       # our kernels ran (8 pyramid launches + blur/FAST/octree/describe)
+    assert len(tuples) == 2006 and desc.shape == (2006, 32) and desc.dtype == np.uint8
+    kps = np.array(tuples, np.float32)
+    _same(kps, desc, g["kps"], g["desc"])
+    assert isinstance(tuples[0][0], float) and isinstance(tuples[0][5], int)       # caster tuple types
+    pyr = e.GetImagePyramid()
+    assert [p.shape for p in pyr] == [tuple(s) for s in g["level_sizes"]]
+    assert [_sha(p) for p in pyr] == list(g["pyramid_view_sha"])                    # the sheared caster view (F6)
+    # 20 iterations like pyORBExtractor/test.py:28-38: deterministic
+    for _ in range(3):
+        t2, d2 = e.operator_kd(img)
+        assert t2 == tuples and np.array_equal(d2, desc)
+
+
+@pytest.mark.parametrize("name", ["stereo_kitti_shape.npz", "stereo_small.npz"])
+def test_config2_stereo_pair_vs_reference_frame_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name))
+    L, R = make_stereo_pair(int(g["idx"]), int(g["H"]), int(g["W"]))
+    assert pair_digest(L, R) == str(g["image_digest"])
+    p = g["params"]
+    params = (int(p[0]), float(p[1]), int(p[2]), int(p[3]), int(p[4]))
+    eL, eR = ORBextractor(*params), ORBextractor(*params)
+    kL, dL = eL.extract_arrays(L)
+    kR, dR = eR.extract_arrays(R)
+    _same(kL, dL, g["kpsL"], g["descL"])
+    _same(kR, dR, g["kpsR"], g["descR"])
+    uR, dep, mi = stereo_resident(eL, eR, float(g["mbf"]), float(g["fx"]))
+    gu, gd = g["uRight"], g["depth"]
+    assert np.array_equal(uR >= 0, gu >= 0)                                   # match decisions exact
+    assert np.abs(uR.astype(np.float64) - gu).max() <= TOL_PX
+    m = gu >= 0
+    assert np.abs(dep[m].astype(np.float64) - gd[m]).max() <= TOL_PX * np.abs(gd[m]).max()
+    assert np.array_equal(uR.astype(np.float64), gu) and np.array_equal(dep.astype(np.float64), gd)   # in fact bit-exact
+    assert m.sum() > 100
+
+
+class _FakeFrame:
+    """The attributes Frame.compute_stereo_matches reads (Frame.py:161-279), filled like Frame.__init__ does."""
+
+    def __init__(self, L, R, eL, eR, mbf, fx):
+        import types
+        self.mpORBextractorLeft, self.mpORBextractorRight = eL, eR
+        self.mbf = mbf
+        self.mK = np.eye(3, dtype=np.float32)
+        self.mK[0, 0] = fx
+        self.mb = self.mbf / self.mK[0][0]
+        tl, self.mDescriptors = eL.operator_kd(L)
+        tr, self.mDescriptorsRight = eR.operator_kd(R)
+        kp = lambda t: types.SimpleNamespace(pt=(t[0], t[1]), octave=t[5])
+        self.mvKeys = [kp(t) for t in tl]
+        self.mvKeysRight = [kp(t) for t in tr]
+        self.mvScaleFactors = eL.GetScaleFactors()
+        self.mvInvScaleFactors = eL.GetInverseScaleFactors()
+        self.mvImagePyramidLeft = eL.GetImagePyramid()
+        self.mvImagePyramidRight = eR.GetImagePyramid()
+        self.N = len(self.mvKeys)
+
+
+def test_drop_in_compute_stereo_matches_resident_and_host_paths(golden_dir):
+    g = np.load(os.path.join(golden_dir, "stereo_small.npz"))
+    L, R = make_stereo_pair(int(g["idx"]), int(g["H"]), int(g["W"]))
+    params = (1000, 1.2, 6, 20, 7)
+    f = _FakeFrame(L, R, ORBextractor(*params), ORBextractor(*params), float(g["mbf"]), float(g["fx"]))
+    compute_stereo_matches(f)                                   # device-resident path
+    assert len(f.mvuRight) == f.N and len(f.mvDepth) == f.N
+    assert np.array_equal(np.array(f.mvuRight, np.float64), g["uRight"])
+    assert np.array_equal(np.array(f.mvDepth, np.float64), g["depth"])
+    assert f.mvuRight[int(np.argmin(g["uRight"]))] == -1 and isinstance(f.mvuRight[int(np.argmin(g["uRight"]))], int)
+    # host path: descriptors are copies, so the identity token does not match and the frame's own arrays are uploaded
+    f.mDescriptors = f.mDescriptors.copy()
+    compute_stereo_matches(f)
+    assert np.array_equal(np.array(f.mvuRight, np.float64), g["uRight"])
+    assert np.array_equal(np.array(f.mvDepth, np.float64), g["depth"])
+
+    class Cls:          # install() patches the class attribute, as README.md:13 suggests
+        def compute_stereo_matches(self):
+            raise AssertionError("unpatched")
+    orig = install(Cls)
+    assert Cls.compute_stereo_matches is compute_stereo_matches and orig is not None
+
+
+@pytest.mark.parametrize("case", ["noise", "smooth", "odd_params", "right_view", "three_levels", "scale_1.5"])
+def test_extractor_vs_oracle_seeded(case):
+    rng = np.random.default_rng(11)
+    params = KITTI
+    if case == "noise":
+        img = rng.integers(0, 256, (376, 1241), dtype=np.uint8)        # ~40k FAST candidates per level 0: global-scratch octree path
+    elif case == "smooth":
+        img = O.blur7(O.blur7(rng.integers(0, 256, (300, 500), dtype=np.uint8)))
+        params = (700, 1.2, 6, 20, 7)
+    elif case == "odd_params":
+        img = make_stereo_pair(5, 240, 320)[0]
+        params = (500, 1.3, 5, 15, 5)
+    elif case == "right_view":
+        img = make_stereo_pair(3)[1]
+    elif case == "three_levels":
+        img = make_stereo_pair(8, 200, 333)[0]
+        params = (60, 1.2, 3, 20, 7)       # tiny quota: the octree stops after its first passes
+    else:
+        img = make_stereo_pair(6, 480, 640)[0]
+        params = (1500, 1.5, 5, 25, 10)
+    kg, dg = ORBextractor(*params).extract_arrays(img)
+    ko, do = O.OracleExtractor(*params).extract_arrays(img)
+    _same(kg, dg, ko, do)
+
+
+def test_stage_by_stage_vs_oracle():
+    img = make_stereo_pair(2)[0]
+    g, o = ORBextractor(*KITTI), O.OracleExtractor(*KITTI)
+    g.extract_arrays(img)
+    o.extract_arrays(img)
+    for l in range(8):
+        w, h = o.level_size(l)
+        assert g.level_size(l) == (w, h)
+        assert np.array_equal(g.level_image(l), o.level_bordered(l)[19:19 + h, 19:19 + w])      # K1
+        assert np.array_equal(g.level_image(l, blurred=True), o.level_blurred(l))               # K5
+        assert np.array_equal(g.level_candidates(l), o.level_candidates(l))                     # K2 (set AND order)
+        assert np.array_equal(g.GetImagePyramid()[l], o.GetImagePyramid()[l])                   # caster view
+
+
+def test_edge_inputs_flat_tiny_and_changing_sizes():
+    e = ORBextractor(500, 1.2, 4, 20, 7)
+    k, d = e.extract_arrays(np.full((120, 160), 77, np.uint8))          # no corners anywhere
+    assert k.shape == (0, 6) and d.size == 0
+    tuples, desc = e.operator_kd(np.full((120, 160), 77, np.uint8))
+    assert tuples == [] and desc.shape == (0, 0)
+    o = O.OracleExtractor(500, 1.2, 4, 20, 7)
+    img = np.random.default_rng(3).integers(0, 256, (64, 80), dtype=np.uint8)     # upper levels lose their cell grid
+    _same(*e.extract_arrays(img), *o.extract_arrays(img))
+    img2 = make_stereo_pair(1, 100, 700)[0]                                         # same object, new size, wide aspect (nIni = 10)
+    _same(*e.extract_arrays(img2), *o.extract_arrays(img2))
+    with pytest.raises(ValueError):
+        e.extract_arrays(np.zeros((400, 100), np.uint8))                            # taller than 2x width: reference divides by zero
+
+
+def test_config4_hires_vs_reference_digest(golden_dir):
+    g = np.load(os.path.join(golden_dir, "hires_extract_digest.npz"))
+    img, _ = make_stereo_pair(4, 1440, 2560)
+    assert _sha(img) == str(g["image_sha"])
+    k, d = ORBextractor(8000, 1.2, 12, 20, 7).extract_arrays(img)
+    assert len(k) == int(g["n"]) and _sha(k) == str(g["kps_sha"]) and _sha(d) == str(g["desc_sha"])
+    assert np.array_equal(np.bincount(k[:, 5].astype(int), minlength=12), g["per_level"])
+
+
+@pytest.mark.parametrize("n", [1000, 4000, 16000])
+def test_config5_stereo_only_sweep_vs_oracle(n):
+    """Synthetic keypoints (uniform in the valid area, octave ~ quota, random descriptors, right = left with ~10 % of
+    the bits flipped at a known disparity) on real pyramids; GPU K7+K8 vs the C restatement of Frame.py:161-279."""
+    rng = np.random.default_rng(n)
+    L, R = make_stereo_pair(12)
+    o = O.OracleExtractor(*KITTI)
+    o.extract_arrays(L)
+    pyrL = o.GetImagePyramid()
+    o.extract_arrays(R)
+    pyrR = o.GetImagePyramid()
+    octv = rng.choice(8, size=n, p=o.quota / o.quota.sum())
+    sf = o.sf[octv]
+    H, W = L.shape
+    lx = rng.integers(19, (W / sf - 20).astype(int)).astype(np.float32)
+    ly = rng.integers(19, (H / sf - 20).astype(int)).astype(np.float32)
+    disp = rng.integers(1, 80, n).astype(np.float32)
+    kL = np.stack([np.where(octv > 0, lx * sf, lx), np.where(octv > 0, ly * sf, ly), octv.astype(np.float32)], 1).astype(np.float32)
+    rx = np.maximum(lx - np.floor(disp / sf), 19).astype(np.float32)
+    kR = np.stack([np.where(octv > 0, rx * sf, rx), kL[:, 1], octv.astype(np.float32)], 1).astype(np.float32)
+    dL = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    flips = (rng.random((n, 256)) < 0.1)
+    dR = dL ^ np.packbits(flips, axis=1, bitorder="little")
+    perm = rng.permutation(n)                    # right keypoints in a different order than left
+    kR, dR = kR[perm], dR[perm]
+    ou, od, oi, _ = O.stereo(kL, dL, kR, dR, o.sf, o.isf, pyrL, pyrR, 386.1448, 718.856)
+    gu, gd, gi = stereo_host(kL, dL, kR, dR, o.sf, o.isf, pyrL, pyrR, 386.1448, 718.856)
+    assert np.array_equal(gi, oi)
+    assert np.array_equal(gu.view(np.uint32), ou.view(np.uint32)) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    assert (oi >= 0).sum() > 0.5 * n
+
+
+def test_stereo_edges_no_right_keypoints_and_range_error():
+    o = O.OracleExtractor(300, 1.2, 4, 20, 7)
+    L, _ = make_stereo_pair(9, 160, 320)
+    k, d = o.extract_arrays(L)
+    pyr = o.GetImagePyramid()
+    u, dep, mi = stereo_host(k[:, [0, 1, 5]], d, np.zeros((0, 3), np.float32), np.zeros((0, 32), np.uint8), o.sf, o.isf, pyr, pyr, 100.0, 300.0)
+    assert (u == -1).all() and (dep == -1).all() and (mi == -1).all()
+    u, dep, mi = stereo_host(np.zeros((0, 3), np.float32), np.zeros((0, 32), np.uint8), k[:, [0, 1, 5]], d, o.sf, o.isf, pyr, pyr, 100.0, 300.0)
+    assert len(u) == 0
+    bad = k[:, [0, 1, 5]].copy()
+    bad[0, 1] = 159.0          # row band leaves the image: the reference's vRowIndices[yi] raises IndexError
+    with pytest.raises(IndexError):
+        stereo_host(k[:, [0, 1, 5]], d, bad, d, o.sf, o.isf, pyr, pyr, 100.0, 300.0)
+    # identical views: every keypoint's Hamming winner is itself
+    u, dep, mi = stereo_host(k[:, [0, 1, 5]], d, k[:, [0, 1, 5]], d, o.sf, o.isf, pyr, pyr, 100.0, 300.0)
+    ou, od, oi, _ = O.stereo(k[:, [0, 1, 5]], d, k[:, [0, 1, 5]], d, o.sf, o.isf, pyr, pyr, 100.0, 300.0)
+    assert np.array_equal(mi, np.arange(len(k))) and np.array_equal(u.view(np.uint32), ou.view(np.uint32))
+
+
+def test_batch_api_equals_single_image_api_and_chunks():
+    import torch
+    from pyorbslam_b200 import StereoFrontend
+    n, P = 5, 2                      # 5 pairs through a 2-pair engine: run_host must chunk 2 + 2 + 1
+    pairs = [make_stereo_pair(20 + i) for i in range(n)]
+    left = torch.from_numpy(np.stack([p[0] for p in pairs])).pin_memory()
+    right = torch.from_numpy(np.stack([p[1] for p in pairs])).pin_memory()
+    fe = StereoFrontend(*KITTI, 376, 1241, P)
+    C = fe.capacity
+    assert C >= 2000 + 2 * 8
+    host = fe.run_host(left, right, 386.1448, 718.856)
+    dev = fe.run(left[:P].cuda(), right[:P].cuda(), 386.1448, 718.856)
+    torch.cuda.synchronize()
+    eL, eR = ORBextractor(*KITTI), ORBextractor(*KITTI)
+    for i in range(n):
+        kL, dL = eL.extract_arrays(pairs[i][0])
+        kR, dR = eR.extract_arrays(pairs[i][1])
+        uR, dep, mi = stereo_resident(eL, eR, 386.1448, 718.856)
+        nl, nr = int(host["nkp"][0, i]), int(host["nkp"][1, i])
+        assert (nl, nr) == (len(kL), len(kR))
+        assert np.array_equal(host["kps"][0, i, :nl].numpy().view(np.uint32), kL.view(np.uint32))
+        assert np.array_equal(host["desc"][0, i, :nl].numpy(), dL)
+        assert np.array_equal(host["kps"][1, i, :nr].numpy().view(np.uint32), kR.view(np.uint32))
+        assert np.array_equal(host["desc"][1, i, :nr].numpy(), dR)
+        assert np.array_equal(host["uRight"][i, :nl].numpy().view(np.uint32), uR.view(np.uint32))
+        assert np.array_equal(host["depth"][i, :nl].numpy().view(np.uint32), dep.view(np.uint32))
+        assert np.array_equal(host["matchIdx"][i, :nl].numpy(), mi)
+        if i < P:
+            assert np.array_equal(dev["kps"][0, i, :nl].cpu().numpy().view(np.uint32), kL.view(np.uint32))
+            assert np.array_equal(dev["uRight"][i, :nl].cpu().numpy().view(np.uint32), uR.view(np.uint32))
+
+
+def test_full_size_properties_batch_of_identical_and_swapped_pairs():
+    """Size-independent properties at the bench's shape: (1) the same pair in every slot of a batch gives identical
+    results in every slot (no cross-slot interference); (2) feeding left as both views makes every keypoint its own
+    Hamming winner at distance 0; (3) results do not depend on which slot a pair sits in."""
+    import torch
+    from pyorbslam_b200 import StereoFrontend
+    P = 16
+    fe = StereoFrontend(*KITTI, 376, 1241, P)
+    L, R = make_stereo_pair(31)
+    L2, R2 = make_stereo_pair(32)
+    left = torch.from_numpy(np.stack([L] * (P - 1) + [L2])).cuda()
+    right = torch.from_numpy(np.stack([R] * (P - 1) + [R2])).cuda()
+    out = fe.run(left, right, 386.1448, 718.856)
+    torch.cuda.synchronize()
+    nkp = out["nkp"].cpu().numpy()
+    assert (nkp[:, :P - 1] == nkp[:, :1]).all()
+    n0 = int(nkp[0, 0])
+    for key in ("kps", "desc"):
+        a = out[key][0, :P - 1, :n0]
+        assert bool((a == a[:1]).all())
+    u = out["uRight"][:P - 1, :n0]
+    assert bool((u == u[:1]).all())
+    # slot independence: the odd pair in the last slot equals the same pair processed alone in slot 0
+    alone = fe.run(left[P - 1:].contiguous(), right[P - 1:].contiguous(), 386.1448, 718.856)
+    torch.cuda.synchronize()
+    n1 = int(nkp[0, P - 1])
+    assert int(alone["nkp"][0, 0]) == n1
+    assert bool((alone["kps"][0, 0, :n1] == out["kps"][0, P - 1, :n1]).all())
+    assert bool((alone["uRight"][0, :n1] == out["uRight"][P - 1, :n1]).all())
+    # self-matching
+    same = fe.run(left, left, 386.1448, 718.856)
+    torch.cuda.synchronize()
+    mi = same["matchIdx"][0, :n0].cpu().numpy()
+    assert np.array_equal(mi, np.arange(n0))
+
+
+def test_device_fast_score_unit_harness():
+    """tests/cuda_unit/fast_unit.cu: device corner score vs the oracle on 2^18 random patches (guards the ptxas
+    VIMNMX3 negation miscompile worked around in kernels_image.cuh)."""
+    exe = os.path.join(ROOT, "build", "fast_unit")
+    if not os.path.exists(exe):
+        pytest.skip("build/fast_unit not built")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+    lines = [l for l in out.splitlines() if "bad" in l]
+    assert len(lines) == 3 and all(" bad 0 " in l for l in lines), out
