@@ -68,10 +68,13 @@ class StereoFrontend:
 
     def run(self, left, right, mbf, fx, out=None):
         """left/right: uint8 CUDA tensors [n, H, W] (n <= max_pairs).  Asynchronous on the current stream."""
-        assert left.is_cuda and right.is_cuda and left.dtype == torch.uint8 and right.dtype == torch.uint8
-        assert left.is_contiguous() and right.is_contiguous() and left.shape == right.shape
+        if not (left.is_cuda and right.is_cuda) or left.dtype != torch.uint8 or right.dtype != torch.uint8:
+            raise ValueError("run takes uint8 CUDA tensors")
+        if not (left.is_contiguous() and right.is_contiguous()) or left.shape != right.shape:
+            raise ValueError("left/right must be contiguous and of equal shape")
         n = left.shape[0]
-        assert tuple(left.shape[1:]) == (self.H, self.W)
+        if tuple(left.shape[1:]) != (self.H, self.W) or n < 1 or n > self.max_pairs:
+            raise ValueError(f"expected [n <= {self.max_pairs}, {self.H}, {self.W}], got {tuple(left.shape)}")
         if out is None:
             out = self.alloc_outputs(n)
         st = torch.cuda.current_stream(left.device).cuda_stream
@@ -86,9 +89,13 @@ class StereoFrontend:
         Uploads, processes and downloads chunk by chunk with copy/compute overlap; returns host tensors."""
         lt = left if isinstance(left, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(left))
         rt = right if isinstance(right, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(right))
-        assert not lt.is_cuda and not rt.is_cuda and lt.dtype == torch.uint8 and lt.is_contiguous() and rt.is_contiguous()
+        if lt.is_cuda or rt.is_cuda:
+            raise ValueError("run_host takes host tensors; use run() for device tensors")
+        if lt.dtype != torch.uint8 or rt.dtype != torch.uint8 or not lt.is_contiguous() or not rt.is_contiguous():
+            raise ValueError(f"run_host needs contiguous uint8 tensors, got {lt.dtype}/{rt.dtype} contiguous={lt.is_contiguous()}/{rt.is_contiguous()}")
         n = lt.shape[0]
-        assert tuple(lt.shape[1:]) == (self.H, self.W) and lt.shape == rt.shape
+        if tuple(lt.shape[1:]) != (self.H, self.W) or lt.shape != rt.shape:
+            raise ValueError(f"expected [n, {self.H}, {self.W}] for both views, got {tuple(lt.shape)} / {tuple(rt.shape)}")
         if out is None:
             out = self.alloc_outputs(n, pinned_host=True)
         _lib.check(_lib.lib().b200orb_batch_run_host(self._h, lt.data_ptr(), rt.data_ptr(), n, float(mbf), float(np.float32(fx)),

@@ -91,7 +91,7 @@ def make_stereo_pair(idx, H=376, W=1241, n_rect=60, max_disp=96.0):
         dst[...] = dst * (1 - alpha[:, sub]) + layer[:, sub]
     left = left[:, :W]
     right = right[:, :W]
-    to8 = lambda a: np.clip(np.rint(a * 255.0), 0, 255).astype(np.uint8)
+    to8 = lambda a: np.ascontiguousarray(np.clip(np.rint(a * 255.0), 0, 255).astype(np.uint8))
     return to8(left), to8(right)
 
 
