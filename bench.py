@@ -330,7 +330,7 @@ def run_b200_arm(args):
         per_image["octree"] = 4 * ncand + 4 * nkp
         peak, peak_src = measured_peak()
         kernels = {}
-        launches_per_call = {"border0": 1, "resize_chain": ORB["nlevels"] - 1, "blur": 1, "fast_cells": 1, "octree": 1, "orient_describe": 1, "stereo": 1}
+        launches_per_call = {"border0": 1, "resize_chain": ORB["nlevels"] - 1, "blur": 1, "fast_cells": 1, "octree": 1, "orient_describe": 1, "stereo": 2}
         for k, tot in stage_ms.items():
             bytes_total = (stereo_pp * prof_pairs) if k == "stereo" else (per_image[k] * 2 * prof_pairs)
             gbs = bytes_total / (tot / 1e3) / 1e9 if tot > 0 else 0.0

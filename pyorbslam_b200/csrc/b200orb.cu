@@ -88,7 +88,7 @@ struct HostPlan {
     Plan P;
     std::vector<XTab> xtab;
     std::vector<YTab> ytab;
-    int fast_SP = 0, fast_SR = 0, fast_TP = 0, fast_TR = 0;
+    int fast_SP = 0, fast_SR = 0, fast_TP = 0, fast_TR = 0, fast_LC = 0;
     size_t fast_smem = 0;
     int oct_capN = 0, oct_capK = 0, oct_capC = 0;
     size_t oct_smem = 0;
@@ -168,7 +168,9 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
     hp.fast_SR = maxh + 6;
     hp.fast_TP = round_up(maxw + 2, 4);
     hp.fast_TR = maxh + 2;
-    hp.fast_smem = (size_t)hp.fast_SP * hp.fast_SR + (size_t)FAST_WARPS * hp.fast_TP * hp.fast_TR;
+    if (maxw > 63 || maxh > 63) return fail(B200ORB_E_ARG, "FAST cell larger than 63 px (level narrower than 62 px after the border?)");
+    hp.fast_LC = round_up(std::max(maxw * maxh, 2), 2);
+    hp.fast_smem = (size_t)hp.fast_SP * hp.fast_SR + (size_t)FAST_WARPS * hp.fast_TP * hp.fast_TR + (size_t)FAST_WARPS * hp.fast_LC * 2;
     hp.fast_smem = (hp.fast_smem + 15) & ~(size_t)15;
     if (hp.fast_smem > 200 * 1024) return fail(B200ORB_E_ARG, "cell size too large for the FAST kernel's shared memory");
     hp.oct_capN = round_up(maxcap + 8, 4);
@@ -192,15 +194,15 @@ struct Engine {
     bool planned = false;
     u8 *d_pyr = nullptr, *d_blur = nullptr;
     u32 *d_cand = nullptr, *d_scratch = nullptr, *d_lvlkp = nullptr;
-    int *d_cellcnt = nullptr, *d_lvlcnt = nullptr, *d_status = nullptr;
+    int *d_cellcnt = nullptr, *d_lvlcnt = nullptr, *d_status = nullptr, *d_rowstart = nullptr, *d_sorted = nullptr;
     XTab* d_xtab = nullptr;
     YTab* d_ytab = nullptr;
     long long bytes = 0;
 
     void release() {
         cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_cand); cudaFree(d_scratch); cudaFree(d_lvlkp);
-        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_ytab);
-        d_pyr = d_blur = nullptr; d_cand = d_scratch = d_lvlkp = nullptr; d_cellcnt = d_lvlcnt = d_status = nullptr;
+        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_sorted);
+        d_pyr = d_blur = nullptr; d_cand = d_scratch = d_lvlkp = nullptr; d_cellcnt = d_lvlcnt = d_status = d_rowstart = d_sorted = nullptr;
         d_xtab = nullptr; d_ytab = nullptr; planned = false; bytes = 0;
     }
     template <typename T> int alloc(T** p, size_t n) {
@@ -223,6 +225,8 @@ struct Engine {
         TRY(alloc(&d_cellcnt, (size_t)S * P.ncells));
         TRY(alloc(&d_lvlcnt, (size_t)S * P.nlevels));
         TRY(alloc(&d_status, 1));
+        TRY(alloc(&d_rowstart, (size_t)S * (P.lv[0].h + 1)));
+        TRY(alloc(&d_sorted, (size_t)S * P.kp_total));
         TRY(alloc(&d_xtab, hp.xtab.size()));
         TRY(alloc(&d_ytab, hp.ytab.size()));
         CU_TRY(cudaMemset(d_pyr, 0, (size_t)S * P.pyr_bytes));
@@ -256,12 +260,12 @@ struct Engine {
             ++g_launches;
         }
         if (evs) cudaEventRecord(evs[2], st);
-        k_blur<<<dim3(P.blur_ctas, n), 256, 0, st>>>(P, d_pyr, d_blur);
+        k_blur<<<dim3(P.blur_ctas, n), BLUR_WARPS * 32, 0, st>>>(P, d_pyr, d_blur);
         ++g_launches;
         if (evs) cudaEventRecord(evs[3], st);
         if (P.fast_ctas > 0) {
             k_fast_cells<<<dim3(P.fast_ctas, n), FAST_WARPS * 32, hp.fast_smem, st>>>(P, d_pyr, d_cand, d_cellcnt, hp.fast_SP, hp.fast_SR,
-                                                                                   hp.fast_TP, hp.fast_TR);
+                                                                                   hp.fast_TP, hp.fast_TR, hp.fast_LC);
             ++g_launches;
         }
         if (evs) cudaEventRecord(evs[4], st);
@@ -299,9 +303,18 @@ void fill_stereo_consts(StereoArgs& A, double mbf, float fx) {
     A.maxD = A.mbf32 / A.mb;         // Frame.py:183
 }
 
-int launch_stereo(const StereoGeom& SG, const StereoArgs& A, int max_left, int pairs, cudaStream_t st) {
+// row index of the right keypoints, then the matcher.  A.rowStart / A.sorted / A.idx_stride must point at
+// (nRows + 1) and idx_stride ints per pair of scratch.
+int launch_stereo(const StereoGeom& SG, StereoArgs A, int max_left, int pairs, cudaStream_t st) {
     if (pairs < 1 || max_left < 1) return 0;
-    dim3 grid((max_left + ST_LEFT_PER_CTA - 1) / ST_LEFT_PER_CTA, pairs);
+    float smax = 1.f;
+    for (int l = 0; l < SG.nlevels; ++l) smax = std::max(smax, SG.sf[l]);
+    A.reach = (int)ceil(2.0 * smax) + 2;
+    const size_t smem = (size_t)(2 * SG.nRows + 1) * sizeof(int);
+    k_rowindex<<<pairs, RI_THREADS, smem, st>>>(A.kpsR, A.nR, A.kp_stride, A.n_stride, A.kp_row, SG.nRows, (int*)A.rowStart, (int*)A.sorted,
+                                                A.idx_stride, A.status);
+    ++g_launches;
+    dim3 grid((max_left + ST_WARPS - 1) / ST_WARPS, pairs);
     k_stereo<<<grid, ST_WARPS * 32, 0, st>>>(SG, A);
     ++g_launches;
     CU_TRY(cudaGetLastError());
@@ -526,6 +539,7 @@ int b200orb_stereo(b200orb_extractor* L, b200orb_extractor* R, double mbf, float
     A.pyrL = L->eng.d_pyr; A.pyrR = R->eng.d_pyr;
     A.kp_row = 6; A.oct_idx = 5; A.out_stride = PL.kp_total;
     A.uRight = L->d_uR; A.depth = L->d_depth; A.matchIdx = L->d_match; A.status = L->eng.d_status;
+    A.rowStart = L->eng.d_rowstart; A.sorted = L->eng.d_sorted; A.idx_stride = PL.kp_total;
     fill_stereo_consts(A, mbf, fx);
     CU_TRY(cudaMemsetAsync(L->eng.d_status, 0, 4, L->st));
     TRY(launch_stereo(SG, A, L->n, 1, L->st));
@@ -546,6 +560,7 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     if (nLeft < 0 || nRight < 0 || nlevels < 1 || nlevels > ORB_MAX_LEVELS) return fail(B200ORB_E_ARG, "bad sizes");
     if (nLeft == 0) return 0;
     if (nRight >= (1 << 20)) return fail(B200ORB_E_ARG, "more than 2^20 right keypoints");
+    if (lh[0] < 1 || lh[0] > 4096) return fail(B200ORB_E_ARG, "level-0 height must be in [1, 4096]");
     CU_TRY(cudaSetDevice(device));
     StereoGeom SG;
     memset(&SG, 0, sizeof(SG));
@@ -570,9 +585,9 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     }
     u8 *d_blob = nullptr, *d_dL = nullptr, *d_dR = nullptr;
     float *d_kL = nullptr, *d_kR = nullptr, *d_u = nullptr, *d_d = nullptr;
-    int *d_m = nullptr, *d_n = nullptr;
+    int *d_m = nullptr, *d_n = nullptr, *d_rs = nullptr, *d_so = nullptr;
     int rc = 0;
-    auto cleanup = [&]() { cudaFree(d_blob); cudaFree(d_dL); cudaFree(d_dR); cudaFree(d_kL); cudaFree(d_kR); cudaFree(d_u); cudaFree(d_d); cudaFree(d_m); cudaFree(d_n); };
+    auto cleanup = [&]() { cudaFree(d_blob); cudaFree(d_dL); cudaFree(d_dR); cudaFree(d_kL); cudaFree(d_kR); cudaFree(d_u); cudaFree(d_d); cudaFree(d_m); cudaFree(d_n); cudaFree(d_rs); cudaFree(d_so); };
 #define CU_TRY2(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(B200ORB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
     CU_TRY2(cudaMalloc((void**)&d_blob, (size_t)total * 2));
     CU_TRY2(cudaMalloc((void**)&d_kL, (size_t)nLeft * 12));
@@ -583,6 +598,8 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     CU_TRY2(cudaMalloc((void**)&d_d, (size_t)nLeft * 4));
     CU_TRY2(cudaMalloc((void**)&d_m, (size_t)nLeft * 4));
     CU_TRY2(cudaMalloc((void**)&d_n, 12));
+    CU_TRY2(cudaMalloc((void**)&d_rs, (size_t)(lh[0] + 1) * 4));
+    CU_TRY2(cudaMalloc((void**)&d_so, (size_t)std::max(nRight, 1) * 4));
     for (int l = 0; l < nlevels; ++l) {
         CU_TRY2(cudaMemcpy(d_blob + SG.base[l], pyrL[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice));
         CU_TRY2(cudaMemcpy(d_blob + total + SG.base[l], pyrR[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice));
@@ -601,6 +618,7 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     A.pyrL = d_blob; A.pyrR = d_blob + total;
     A.kp_row = 3; A.oct_idx = 2; A.out_stride = nLeft;
     A.uRight = d_u; A.depth = d_d; A.matchIdx = d_m; A.status = d_n + 2;
+    A.rowStart = d_rs; A.sorted = d_so; A.idx_stride = std::max(nRight, 1);
     fill_stereo_consts(A, mbf, fx);
     rc = launch_stereo(SG, A, nLeft, 1, nullptr);
     if (rc) { cleanup(); return rc; }
@@ -678,6 +696,7 @@ int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint
     A.kp_stride = (long long)C * 6; A.desc_stride = (long long)C * 32; A.pyr_stride = P.pyr_bytes;
     A.kp_row = 6; A.oct_idx = 5; A.out_stride = (int)C;
     A.uRight = d_uRight; A.depth = d_depth; A.matchIdx = d_matchIdx; A.status = b->eng.d_status;
+    A.rowStart = b->eng.d_rowstart; A.sorted = b->eng.d_sorted; A.idx_stride = (int)C;
     fill_stereo_consts(A, mbf, fx);
     TRY(launch_stereo(SG, A, (int)C, n_pairs, st));
     if (evs) CU_TRY(cudaEventRecord(evs[B200ORB_NSTAGE], st));

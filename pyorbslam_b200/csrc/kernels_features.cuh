@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int au = u < 0 ? -u : u;
-#pragma unroll 1
-        for (int v = -15; v <= 15; ++v) {
+#pragma unroll
+        for (int v = -15; v <= 15; ++v) {   // fully unrolled: 31 independent loads in flight per lane
             if (au <= P.umax[v < 0 ? -v : v]) {
                 const int val = c[v * G.pitch + u];
                 m10 += u * val;
@@ -149,19 +149,71 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
+// K7a: row index of the RIGHT keypoints (the GPU form of vRowIndices, Frame.py:170-179): counting sort of the
+// right keypoints by integer row into rowStart[nRows + 1] / sorted[nR].  A left keypoint at row v then only
+// visits the bins v - R .. v + R (R = ceil(2 * max scale) + 2 covers every band) and applies the exact
+// floor(y - 2s) <= v <= ceil(y + 2s) test per candidate.  Order inside a bin is irrelevant: the winner is the
+// minimum of (dist << 20 | right index), which equals the reference's first strict minimum in ascending index.
+// One CTA per right image.
+// ------------------------------------------------------------------------------------------------
+#define RI_THREADS 256
+__global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict__ kpsR, const int* __restrict__ nR, long long kp_stride,
+                                                         int n_stride, int kp_row, int nRows, int* __restrict__ rowStart,
+                                                         int* __restrict__ sorted, int idx_stride, int* __restrict__ status) {
+    extern __shared__ int ri_hist[];     // nRows + 1 counters, then nRows cursors
+    __shared__ int ri_tmp[RI_THREADS / 32 + 1];
+    const int pair = blockIdx.x;
+    const int n = nR[(size_t)pair * n_stride];
+    const float* k = kpsR + (size_t)pair * kp_stride;
+    int* rs = rowStart + (size_t)pair * (nRows + 1);
+    int* so = sorted + (size_t)pair * idx_stride;
+    int* cursor = ri_hist + nRows + 1;
+    for (int i = threadIdx.x; i <= nRows; i += RI_THREADS) ri_hist[i] = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += RI_THREADS) {
+        const int row = (int)k[(size_t)j * kp_row + 1];
+        if (row < 0 || row >= nRows) { atomicOr(status, 2); continue; }
+        atomicAdd(&ri_hist[row], 1);
+    }
+    __syncthreads();
+    // exclusive scan over nRows + 1 entries (the last one becomes the total)
+    const int len = nRows + 1;
+    const int per = (len + RI_THREADS - 1) / RI_THREADS;
+    const int b = min((int)threadIdx.x * per, len), e = min(b + per, len);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += ri_hist[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) ri_tmp[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += ri_tmp[w];
+    base += incl - sum;
+    for (int i = b; i < e; ++i) { const int t = ri_hist[i]; ri_hist[i] = base; base += t; }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= nRows; i += RI_THREADS) { rs[i] = ri_hist[i]; if (i < nRows) cursor[i] = ri_hist[i]; }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += RI_THREADS) {
+        const int row = (int)k[(size_t)j * kp_row + 1];
+        if (row < 0 || row >= nRows) continue;
+        so[atomicAdd(&cursor[row], 1)] = j;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K7 + K8: Frame.compute_stereo_matches (Frame.py:161-279), one warp per left keypoint.
-//   K7  the row-band candidate test (right keypoint rows floor(y-2s) .. ceil(y+2s) in double, Frame.py:173-179;
-//       octave within +-1, uR in [uL - maxD, uL], :209-215) runs over right-keypoint metadata staged in shared
-//       memory; Hamming distance = __popc over 2 x 16-byte loads; the reference's "first strict minimum in
+//   K7  candidates come from the row index (k_rowindex); per candidate the exact row-band test (right keypoint
+//       rows floor(y-2s) .. ceil(y+2s) in double, Frame.py:173-179), octave within +-1, uR in [uL - maxD, uL]
+//       (:209-215); Hamming distance = __popc over 2 x 16-byte loads; the reference's "first strict minimum in
 //       ascending right index" is the minimum of (dist << 20 | index).
 //   K8  11x11 SAD slide (L = 5) on the keypoint's pyramid level through the reference's step-ignoring pyramid
 //       view, parabola fit, |delta| > 1 rejection, disparity / depth in float32 exactly as
 //       NumPy >= 2 evaluates them.
-// kps rows are float[stride_kp] with (x, y) first and the octave at index `oct_idx`.
+// kps rows are float[kp_row] with (x, y) first and the octave at index `oct_idx`.
 // ------------------------------------------------------------------------------------------------
 #define ST_WARPS 8
-#define ST_LEFT_PER_CTA 64
-#define ST_CHUNK 2048
 
 struct StereoArgs {
     const float* kpsL; const u8* descL; const int* nL;      // per pair: + pair * stride
@@ -171,6 +223,8 @@ struct StereoArgs {
     int n_stride;                                           // stride of nL / nR between pairs (ints)
     int kp_row, oct_idx;                                    // floats per keypoint row, index of the octave
     int out_stride;                                         // rows per pair in the outputs
+    const int* rowStart; const int* sorted; int idx_stride; // row index of the right keypoints (k_rowindex)
+    int reach;                                              // bins to visit on each side of the left keypoint's row
     float mbf32, mb, maxD;
     double mbf;
     float* uRight; float* depth; int* matchIdx; int* status;
@@ -183,80 +237,53 @@ __device__ __forceinline__ const u8* view_ptr(const u8* base, const StereoGeom& 
 }
 
 __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo(const __grid_constant__ StereoGeom SG, const StereoArgs A) {
-    __shared__ float s_u[ST_CHUNK];
-    __shared__ short2 s_rows[ST_CHUNK];
-    __shared__ unsigned char s_oct[ST_CHUNK];
     __shared__ unsigned char s_win[ST_WARPS][11 * 11 + 11 * 21 + 4];
     const int pair = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nL = A.nL[(size_t)pair * A.n_stride], nR = A.nR[(size_t)pair * A.n_stride];
-    const int left0 = blockIdx.x * ST_LEFT_PER_CTA;
-    if (left0 >= nL) return;
+    const int nL = A.nL[(size_t)pair * A.n_stride];
+    const int iL = blockIdx.x * ST_WARPS + warp;
+    if (iL >= nL) return;                                   // warp-uniform; no block-level barrier below
     const float* kL = A.kpsL + (size_t)pair * A.kp_stride;
     const float* kR = A.kpsR + (size_t)pair * A.kp_stride;
     const u8* dL = A.descL + (size_t)pair * A.desc_stride;
     const u8* dR = A.descR + (size_t)pair * A.desc_stride;
-    constexpr int PER_WARP = ST_LEFT_PER_CTA / ST_WARPS;
+    const int* rs = A.rowStart + (size_t)pair * (SG.nRows + 1);
+    const int* so = A.sorted + (size_t)pair * A.idx_stride;
 
-    unsigned best[PER_WARP];
-#pragma unroll
-    for (int k = 0; k < PER_WARP; ++k) best[k] = (100u << 20);   // bestDist = TH_HIGH, bestIdxR = 0 (Frame.py:203-204)
-
-    for (int c0 = 0; c0 < nR; c0 += ST_CHUNK) {
-        const int cn = min(ST_CHUNK, nR - c0);
-        __syncthreads();
-        for (int j = threadIdx.x; j < cn; j += ST_WARPS * 32) {
-            const float* r = kR + (size_t)(c0 + j) * A.kp_row;
-            const int o = (int)r[A.oct_idx];
-            const double y = (double)r[1], reach = 2.0 * (double)SG.sf[o];
-            s_u[j] = r[0];
-            s_rows[j] = make_short2((short)(int)floor(y - reach), (short)(int)ceil(y + reach));
-            s_oct[j] = (unsigned char)o;
+    const float* p = kL + (size_t)iL * A.kp_row;
+    const float uL = p[0], vL = p[1];
+    const int oL = (int)p[A.oct_idx];
+    const int row = (int)vL;                                // int(vL), Frame.py:192
+    unsigned best = (100u << 20);                           // bestDist = TH_HIGH, bestIdxR = 0 (Frame.py:203-204)
+    if (row < 0 || row >= SG.nRows) {
+        if (lane == 0) atomicOr(A.status, 1);               // the reference indexes vRowIndices[int(vL)] here
+    } else if (!(uL < 0)) {                                 // maxU < 0 -> continue (Frame.py:200-201)
+        const float minU = uL - A.maxD;
+        const uint4* dl = reinterpret_cast<const uint4*>(dL + (size_t)iL * 32);
+        const uint4 l0 = dl[0], l1 = dl[1];
+        const int c0 = rs[max(row - A.reach, 0)], c1 = rs[min(row + A.reach + 1, SG.nRows)];
+        for (int c = c0 + lane; c < c1; c += 32) {
+            const int j = so[c];
+            const float* r = kR + (size_t)j * A.kp_row;
+            const float uR = r[0];
+            const int oR = (int)r[A.oct_idx];
+            const double y = (double)r[1], reach = 2.0 * (double)SG.sf[oR];
+            if (row < (int)floor(y - reach) || row > (int)ceil(y + reach) || oR < oL - 1 || oR > oL + 1 || !(minU <= uR) || !(uR <= uL)) continue;
+            const uint4* dr = reinterpret_cast<const uint4*>(dR + (size_t)j * 32);
+            const uint4 r0 = __ldg(dr), r1 = __ldg(dr + 1);
+            const unsigned d = __popc(l0.x ^ r0.x) + __popc(l0.y ^ r0.y) + __popc(l0.z ^ r0.z) + __popc(l0.w ^ r0.w) +
+                               __popc(l1.x ^ r1.x) + __popc(l1.y ^ r1.y) + __popc(l1.z ^ r1.z) + __popc(l1.w ^ r1.w);
+            best = min(best, (d << 20) | (unsigned)j);
         }
-        __syncthreads();
 #pragma unroll
-        for (int k = 0; k < PER_WARP; ++k) {
-            const int iL = left0 + warp + k * ST_WARPS;
-            if (iL >= nL) continue;
-            const float* p = kL + (size_t)iL * A.kp_row;
-            const float uL = p[0], vL = p[1];
-            const int oL = (int)p[A.oct_idx];
-            const int row = (int)vL;
-            const float minU = uL - A.maxD;
-            if (uL < 0) continue;
-            const uint4* dl = reinterpret_cast<const uint4*>(dL + (size_t)iL * 32);
-            const uint4 l0 = dl[0], l1 = dl[1];
-            unsigned b = best[k];
-            for (int j = lane; j < cn; j += 32) {
-                const short2 rr = s_rows[j];
-                const int oR = s_oct[j];
-                const float uR = s_u[j];
-                if (row < rr.x || row > rr.y || oR < oL - 1 || oR > oL + 1 || !(minU <= uR) || !(uR <= uL)) continue;
-                const uint4* dr = reinterpret_cast<const uint4*>(dR + (size_t)(c0 + j) * 32);
-                const uint4 r0 = __ldg(dr), r1 = __ldg(dr + 1);
-                const unsigned d = __popc(l0.x ^ r0.x) + __popc(l0.y ^ r0.y) + __popc(l0.z ^ r0.z) + __popc(l0.w ^ r0.w) +
-                                   __popc(l1.x ^ r1.x) + __popc(l1.y ^ r1.y) + __popc(l1.z ^ r1.z) + __popc(l1.w ^ r1.w);
-                b = min(b, (d << 20) | (unsigned)(c0 + j));
-            }
-            best[k] = b;
-        }
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
     }
-
-#pragma unroll
-    for (int k = 0; k < PER_WARP; ++k) {
-        const int iL = left0 + warp + k * ST_WARPS;
-        if (iL >= nL) continue;
-        unsigned b = best[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) b = min(b, __shfl_xor_sync(0xffffffffu, b, o));
-        const int bestDist = b >> 20, bestR = b & 0xfffff;
+    {
+        const int bestDist = best >> 20, bestR = best & 0xfffff;
         const size_t oi = (size_t)pair * A.out_stride + iL;
         float outU = -1.f, outD = -1.f;
         int outM = -1;
         if (bestDist < 75) {    // thOrbDist = (TH_HIGH + TH_LOW) / 2, Frame.py:166,222
             outM = bestR;
-            const float* p = kL + (size_t)iL * A.kp_row;
-            const float uL = p[0], vL = p[1];
-            const int oL = (int)p[A.oct_idx];
             const float uR0 = kR[(size_t)bestR * A.kp_row];
             const double inv = (double)SG.isf[oL];
             const int su = __double2int_rn((double)uL * inv), sv = __double2int_rn((double)vL * inv);   // python round()

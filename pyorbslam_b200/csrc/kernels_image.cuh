@@ -84,48 +84,70 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Plan P, 
 // ------------------------------------------------------------------------------------------------
 // K5: GaussianBlur 7x7 sigma 2 of every level (ORBextractor.cpp:1084-1085), OpenCV fixed-point result:
 // kernel [18,34,48,56,48,34,18]/256 per axis, dst = (sum + 2^15) >> 16.
-// The bordered pyramid already holds the reflect-101 halo the blur needs.  Tile 64 x 16 per CTA.
+// The bordered pyramid already holds the reflect-101 halo the blur needs.
+// Register-resident separable filter, no shared memory: a warp owns a 128-column strip (lane = 4 output
+// columns = one 32-bit store), walks BLUR_RB rows down and keeps the last 7 horizontally filtered rows in
+// registers.  Per input row every lane issues ONE aligned 32-bit load; the two neighbouring words come from
+// warp shuffles (the level ROI starts at buffer column 19, so output word k needs input words k+4 .. k+6).
 // ------------------------------------------------------------------------------------------------
-#define BLUR_TW 64
-#define BLUR_TH 16
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Plan P, const u8* __restrict__ pyr, u8* __restrict__ blur) {
-    __shared__ u8 raw[BLUR_TH + 6][BLUR_TW + 8];
-    __shared__ unsigned short hs[BLUR_TH + 6][BLUR_TW];
+#define BLUR_TW 128
+#define BLUR_RB 32
+#define BLUR_WARPS 4
+#define BLUR_TH (BLUR_RB * BLUR_WARPS)
+__global__ void __launch_bounds__(BLUR_WARPS * 32) k_blur(const __grid_constant__ Plan P, const u8* __restrict__ pyr, u8* __restrict__ blur) {
     const int slot = blockIdx.y;
     int l = 0;
     while (l + 1 < P.nlevels && (int)blockIdx.x >= P.lv[l + 1].blur_cta_ofs) ++l;
     const LevelGeom& G = P.lv[l];
     const int t = blockIdx.x - G.blur_cta_ofs;
     const int ty = t / G.blur_tiles_x, tx = t - ty * G.blur_tiles_x;
-    const int x0 = tx * BLUR_TW, y0 = ty * BLUR_TH;
-    const u8* src = pyr + (size_t)slot * P.pyr_bytes + G.pyr_ofs;
-    // raw tile: ROI (x0-3 .. x0+66, y0-3 .. y0+18) -> bordered coords (+19); clamp to the buffer for partial tiles
-    for (int i = threadIdx.x; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
-        const int r = i / (BLUR_TW + 6), c = i - r * (BLUR_TW + 6);
-        const int by = min(y0 + r + ORB_EDGE - 3, G.rows - 1), bx = min(x0 + c + ORB_EDGE - 3, G.pitch - 1);
-        raw[r][c] = src[(size_t)by * G.pitch + bx];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
-        const u8* p = &raw[r][c];
-        hs[r][c] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncthreads();
-    // each thread: 4 consecutive x of one row -> one 32-bit store
-    const int r = threadIdx.x / (BLUR_TW / 4), c4 = (threadIdx.x - r * (BLUR_TW / 4)) * 4;
-    const int y = y0 + r, x = x0 + c4;
-    if (y < G.h && x < G.w) {
-        u32 v = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = tx * BLUR_TW + 4 * lane;                 // first of this lane's 4 output columns (ROI coords)
+    const int y0 = ty * BLUR_TH + warp * BLUR_RB;           // first output row of this warp
+    if (y0 >= G.h) return;                                  // warp-uniform
+    const u32* src = reinterpret_cast<const u32*>(pyr + (size_t)slot * P.pyr_bytes + G.pyr_ofs);
+    const int wpr = G.pitch >> 2;                            // words per buffer row
+    // input bytes for outputs x0..x0+3: ROI x0-3 .. x0+6 = buffer columns x0+16 .. x0+25 -> words (x0+16)/4 + {0,1,2}
+    const int w0 = min((x0 + 16) >> 2, wpr - 1);
+    const int wx = min(((tx * BLUR_TW + 16) >> 2) + 32 + (lane & 1), wpr - 1);   // lanes 0/1 fetch the two words past the strip
+    u8* dst = blur + (size_t)slot * P.blur_bytes + G.blur_ofs;
+    u32 h01[7], h23[7];                                      // 7 filtered rows, two 16-bit values per register
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = c4 + k;
-            const u32 acc = 18u * (hs[r][c] + hs[r + 6][c]) + 34u * (hs[r + 1][c] + hs[r + 5][c]) +
-                            48u * (hs[r + 2][c] + hs[r + 4][c]) + 56u * hs[r + 3][c];
-            v |= ((acc + 32768u) >> 16) << (8 * k);
+    for (int r = 0; r < BLUR_RB + 6; ++r) {
+        const int by = min(y0 + r - 3 + ORB_EDGE, G.rows - 1);
+        const u32* row = src + (size_t)by * wpr;
+        const u32 A = row[w0];
+        const u32 X = lane < 2 ? row[wx] : 0u;
+        u32 B = __shfl_down_sync(0xffffffffu, A, 1);
+        u32 C = __shfl_down_sync(0xffffffffu, A, 2);
+        const u32 X0 = __shfl_sync(0xffffffffu, X, 0), X1 = __shfl_sync(0xffffffffu, X, 1);
+        if (lane == 31) { B = X0; C = X1; }
+        if (lane == 30) C = X0;
+        const int a0 = A & 0xff, a1 = (A >> 8) & 0xff, a2 = (A >> 16) & 0xff, a3 = A >> 24;
+        const int a4 = B & 0xff, a5 = (B >> 8) & 0xff, a6 = (B >> 16) & 0xff, a7 = B >> 24;
+        const int a8 = C & 0xff, a9 = (C >> 8) & 0xff;
+        const u32 f0 = 18 * (a0 + a6) + 34 * (a1 + a5) + 48 * (a2 + a4) + 56 * a3;
+        const u32 f1 = 18 * (a1 + a7) + 34 * (a2 + a6) + 48 * (a3 + a5) + 56 * a4;
+        const u32 f2 = 18 * (a2 + a8) + 34 * (a3 + a7) + 48 * (a4 + a6) + 56 * a5;
+        const u32 f3 = 18 * (a3 + a9) + 34 * (a4 + a8) + 48 * (a5 + a7) + 56 * a6;
+        h01[r % 7] = f0 | (f1 << 16);
+        h23[r % 7] = f2 | (f3 << 16);
+        if (r >= 6) {
+            const int y = y0 + r - 6;
+            // rows r-6 .. r are in the ring; taps 0..6 <-> ring slots (r-6)%7 .. r%7
+            const u32 p0 = h01[(r - 6) % 7], p1 = h01[(r - 5) % 7], p2 = h01[(r - 4) % 7], p3 = h01[(r - 3) % 7],
+                      p4 = h01[(r - 2) % 7], p5 = h01[(r - 1) % 7], p6 = h01[r % 7];
+            const u32 q0 = h23[(r - 6) % 7], q1 = h23[(r - 5) % 7], q2 = h23[(r - 4) % 7], q3 = h23[(r - 3) % 7],
+                      q4 = h23[(r - 2) % 7], q5 = h23[(r - 1) % 7], q6 = h23[r % 7];
+#define BLUR_V(lo0, lo1, lo2, lo3, lo4, lo5, lo6) ((18u * ((lo0) + (lo6)) + 34u * ((lo1) + (lo5)) + 48u * ((lo2) + (lo4)) + 56u * (lo3) + 32768u) >> 16)
+            const u32 o0 = BLUR_V(p0 & 0xffff, p1 & 0xffff, p2 & 0xffff, p3 & 0xffff, p4 & 0xffff, p5 & 0xffff, p6 & 0xffff);
+            const u32 o1 = BLUR_V(p0 >> 16, p1 >> 16, p2 >> 16, p3 >> 16, p4 >> 16, p5 >> 16, p6 >> 16);
+            const u32 o2 = BLUR_V(q0 & 0xffff, q1 & 0xffff, q2 & 0xffff, q3 & 0xffff, q4 & 0xffff, q5 & 0xffff, q6 & 0xffff);
+            const u32 o3 = BLUR_V(q0 >> 16, q1 >> 16, q2 >> 16, q3 >> 16, q4 >> 16, q5 >> 16, q6 >> 16);
+#undef BLUR_V
+            if (y < G.h && x0 < G.w)   // blur pitch is a multiple of 64: the aligned 4-byte store may spill into padding only
+                *reinterpret_cast<u32*>(dst + (size_t)y * G.blur_pitch + x0) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
         }
-        // blur pitch is a multiple of 64, so the 4-byte store is aligned; bytes past w are padding
-        *reinterpret_cast<u32*>(blur + (size_t)slot * P.blur_bytes + G.blur_ofs + (size_t)y * G.blur_pitch + x) = v;
     }
 }
 
@@ -140,28 +162,44 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Plan P, co
 // ------------------------------------------------------------------------------------------------
 #define FAST_WARPS 8
 
-// 9-of-16 segment test + exact OpenCV corner score (cornerScore<16>): score = best - 1 with
-// best = max over the 16 arcs of 9 of min(v - p_k) and of min(p_k - v).  Returns 0 for non-corners at t.
-__device__ __forceinline__ int fast_score(const u8* p, int SP, int t) {
+// The 16 ring pixels of the Bresenham circle, clockwise from (0,+3) (OpenCV FAST pattern 16).
+__device__ __forceinline__ void fast_ring(const u8* p, int SP, int (&q)[16]) {
+    q[0] = p[3 * SP]; q[1] = p[3 * SP + 1]; q[2] = p[2 * SP + 2]; q[3] = p[SP + 3];
+    q[4] = p[3]; q[5] = p[-SP + 3]; q[6] = p[-2 * SP + 2]; q[7] = p[-3 * SP + 1];
+    q[8] = p[-3 * SP]; q[9] = p[-3 * SP - 1]; q[10] = p[-2 * SP - 2]; q[11] = p[-SP - 3];
+    q[12] = p[-3]; q[13] = p[SP - 3]; q[14] = p[2 * SP - 2]; q[15] = p[3 * SP - 1];
+}
+
+// cheap reject: every arc of 9 contains one pixel of each antipodal pair, so a corner needs (0 or 8) AND (4 or 12)
+// on the same side of the threshold band
+__device__ __forceinline__ bool fast_quick(const u8* p, int SP, int t) {
     const int v = p[0], hi = v + t, lo = v - t;
+    const int a = p[3 * SP], b = p[-3 * SP], c = p[3], d = p[-3];
+    const bool br = ((a > hi) | (b > hi)) & ((c > hi) | (d > hi));
+    const bool dk = ((a < lo) | (b < lo)) & ((c < lo) | (d < lo));
+    return br | dk;
+}
+
+// 9-of-16 segment test (strictly brighter than v+t or strictly darker than v-t on 9 contiguous ring pixels)
+__device__ __forceinline__ bool fast_is_corner(const u8* p, int SP, int t) {
     int q[16];
-    q[0] = p[3 * SP]; q[8] = p[-3 * SP];
-    int br = (q[0] > hi) | (q[8] > hi), dk = (q[0] < lo) | (q[8] < lo);
-    if (!(br | dk)) return 0;              // every 9-arc contains one pixel of each antipodal pair
-    q[4] = p[3]; q[12] = p[-3];
-    br &= (q[4] > hi) | (q[12] > hi); dk &= (q[4] < lo) | (q[12] < lo);
-    if (!(br | dk)) return 0;
-    q[1] = p[3 * SP + 1]; q[2] = p[2 * SP + 2]; q[3] = p[SP + 3];
-    q[5] = p[-SP + 3]; q[6] = p[-2 * SP + 2]; q[7] = p[-3 * SP + 1];
-    q[9] = p[-3 * SP - 1]; q[10] = p[-2 * SP - 2]; q[11] = p[-SP - 3];
-    q[13] = p[SP - 3]; q[14] = p[2 * SP - 2]; q[15] = p[3 * SP - 1];
+    fast_ring(p, SP, q);
+    const int v = p[0], hi = v + t, lo = v - t;
     u32 mb = 0, md = 0;
 #pragma unroll
     for (int k = 0; k < 16; ++k) { mb |= (u32)(q[k] > hi) << k; md |= (u32)(q[k] < lo) << k; }
     mb |= mb << 16; md |= md << 16;
     u32 rb = mb & (mb >> 1); rb &= rb >> 2; rb &= rb >> 4; rb &= mb >> 8;
     u32 rd = md & (md >> 1); rd &= rd >> 2; rd &= rd >> 4; rd &= md >> 8;
-    if (!((rb | rd) & 0xffffu)) return 0;
+    return ((rb | rd) & 0xffffu) != 0;
+}
+
+// exact OpenCV corner score (cornerScore<16>) of a pixel known to be a corner: best - 1 with
+// best = max over the 16 arcs of 9 of min(v - p_k) and of min(p_k - v).
+__device__ __forceinline__ int fast_corner_score(const u8* p, int SP) {
+    int q[16];
+    fast_ring(p, SP, q);
+    const int v = p[0];
     // sliding min / max over windows of 9 on the circle (doubling: 2, 4, 8, then +1).
     // Works on the biased differences D = 255 + v - p_k in [0, 510]: the bright side min(p_k - v) equals
     // 255 - max(D), so no negated operand ever feeds a max -- ptxas 12.9 (sm_100a, -O1 and above) drops the
@@ -182,13 +220,26 @@ __device__ __forceinline__ int fast_score(const u8* p, int SP, int t) {
         bestDark = max(bestDark, mn);          // 255 + max_arcs min(v - p)
         worstBright = min(worstBright, mx);    // 255 - max_arcs min(p - v)
     }
-    const int best = max(bestDark - 255, 255 - worstBright);
-    return best - 1;
+    return max(bestDark - 255, 255 - worstBright) - 1;
 }
 
+// segment test + score in one call (0 for non-corners at t); used by the unit harness
+__device__ __forceinline__ int fast_score(const u8* p, int SP, int t) {
+    if (!fast_quick(p, SP, t) || !fast_is_corner(p, SP, t)) return 0;
+    return fast_corner_score(p, SP);
+}
+
+// Work list entry: y << 6 | x inside the cell's detection window (both < 64), bit 15 = survives NMS.
+// Phases per cell (one warp), each on FULL warps thanks to in-place ordered compaction of the list:
+//   1 quick reject over all window pixels        -> list A (row-major)
+//   2 9-of-16 segment test on list A             -> list B (in place)
+//   3 exact score of list B                      -> score tile (zero elsewhere = "non-corner / outside scores 0")
+//   4 strict 8-neighbour NMS on list B; any survivor with score >= iniThFAST decides the threshold
+//   5 ordered emission of survivors with score >= T
 __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
                                                                 u32* __restrict__ cand, int* __restrict__ cellcnt,
-                                                                int SP /*strip pitch*/, int SR /*strip rows*/, int TP /*tile pitch*/, int TR /*tile rows*/) {
+                                                                int SP /*strip pitch*/, int SR /*strip rows*/, int TP /*tile pitch*/, int TR /*tile rows*/,
+                                                                int LC /*list capacity per warp*/) {
     extern __shared__ __align__(16) u8 smem[];
     u8* strip = smem;
     const int slot = blockIdx.y;
@@ -199,6 +250,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_con
     const int ci = local / G.fast_groups, g = local - ci * G.fast_groups;
     const int j0 = g * FAST_WARPS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 lt = (1u << lane) - 1;
     const int tLow = max(0, min(min(P.iniTh, P.minTh), 255));
 
     const int iniY = ORB_DET_ORIGIN + ci * G.hCell;
@@ -216,6 +268,9 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_con
             *reinterpret_cast<u32*>(strip + r * SP + 4 * c) = *reinterpret_cast<const u32*>(src + (size_t)r * G.pitch + 4 * c);
         }
     }
+    // zero this warp's score tile while the strip loads are in flight (the rim is what "outside the window scores 0" means)
+    u8* tile = smem + SP * SR + warp * (TP * TR);
+    for (int i = lane; i < (TP * TR) >> 2; i += 32) reinterpret_cast<u32*>(tile)[i] = 0u;
     __syncthreads();
 
     const int j = j0 + warp;
@@ -229,47 +284,65 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_con
         if (lane == 0) *cnt_out = 0;
         return;
     }
-    u8* tile = smem + SP * SR + warp * (TP * TR);
-    // zero the (ch+2) x (cw+2) score tile: the rim is what "outside the window scores 0" means
-    for (int i = lane; i < (ch + 2) * TP; i += 32) tile[i] = 0;
-    __syncwarp();
+    unsigned short* list = reinterpret_cast<unsigned short*>(smem + SP * SR + FAST_WARPS * (TP * TR)) + warp * LC;
     const u8* s0 = strip + 3 * SP + (iniX - sx0) + shift + 3;
-    for (int y = 0; y < ch; ++y)
-        for (int x = lane; x < cw; x += 32) {
-            const int s = fast_score(s0 + y * SP + x, SP, tLow);
-            if (s) tile[(y + 1) * TP + x + 1] = (u8)s;
-        }
-    __syncwarp();
-    const int iniTh = max(0, min(P.iniTh, 255)), minTh = max(0, min(P.minTh, 255));
-    // pass 1: does anything survive NMS at iniThFAST?
-    bool any_ini = false;
-    for (int y = 0; y < ch; ++y)
-        for (int x = lane; x < cw; x += 32) {
-            const u8* t = tile + (y + 1) * TP + x + 1;
-            const int s = t[0];
-            if (s >= iniTh && s > 0 && s > t[-1] && s > t[1] && s > t[-TP - 1] && s > t[-TP] && s > t[-TP + 1] &&
-                s > t[TP - 1] && s > t[TP] && s > t[TP + 1])
-                any_ini = true;
-        }
-    const int T = __any_sync(0xffffffffu, any_ini) ? iniTh : minTh;
-    // pass 2: ordered emission
-    u32* out = cand + (size_t)slot * P.cand_entries + G.cand_ofs + (size_t)cell * G.cell_cap;
-    int count = 0;
-    const int xrel0 = iniX - ORB_DET_ORIGIN + 3, yrel0 = iniY - ORB_DET_ORIGIN + 3;
+
+    // ---- phase 1 ----
+    int nA = 0;
     for (int y = 0; y < ch; ++y)
         for (int xb = 0; xb < cw; xb += 32) {
             const int x = xb + lane;
-            bool keep = false;
-            int s = 0;
-            if (x < cw) {
-                const u8* t = tile + (y + 1) * TP + x + 1;
-                s = t[0];
-                keep = s >= T && s > 0 && s > t[-1] && s > t[1] && s > t[-TP - 1] && s > t[-TP] && s > t[-TP + 1] &&
-                       s > t[TP - 1] && s > t[TP] && s > t[TP + 1];
-            }
-            const u32 m = __ballot_sync(0xffffffffu, keep);
-            if (keep) out[count + __popc(m & ((1u << lane) - 1))] = (u32)(xrel0 + x) | ((u32)(yrel0 + y) << 12) | ((u32)s << 24);
-            count += __popc(m);
+            const bool pass = x < cw && fast_quick(s0 + y * SP + x, SP, tLow);
+            const u32 m = __ballot_sync(0xffffffffu, pass);
+            if (pass) list[nA + __popc(m & lt)] = (unsigned short)((y << 6) | x);
+            nA += __popc(m);
         }
+    __syncwarp();
+    // ---- phase 2 ----
+    int nB = 0;
+    for (int b = 0; b < nA; b += 32) {
+        const int i = b + lane;
+        const int e = i < nA ? list[i] : 0;
+        const bool c = i < nA && fast_is_corner(s0 + (e >> 6) * SP + (e & 63), SP, tLow);
+        const u32 m = __ballot_sync(0xffffffffu, c);
+        __syncwarp();
+        if (c) list[nB + __popc(m & lt)] = (unsigned short)e;
+        nB += __popc(m);
+    }
+    __syncwarp();
+    // ---- phase 3 ----
+    for (int i = lane; i < nB; i += 32) {
+        const int e = list[i], y = e >> 6, x = e & 63;
+        const int s = fast_corner_score(s0 + y * SP + x, SP);
+        tile[(y + 1) * TP + x + 1] = (u8)s;
+    }
+    __syncwarp();
+    // ---- phase 4 ----
+    const int iniTh = max(0, min(P.iniTh, 255)), minTh = max(0, min(P.minTh, 255));
+    bool any_ini = false;
+    for (int i = lane; i < nB; i += 32) {
+        const int e = list[i];
+        const u8* t = tile + ((e >> 6) + 1) * TP + (e & 63) + 1;
+        const int s = t[0];
+        const bool keep = s > 0 && s > t[-1] && s > t[1] && s > t[-TP - 1] && s > t[-TP] && s > t[-TP + 1] &&
+                          s > t[TP - 1] && s > t[TP] && s > t[TP + 1];
+        if (keep) { list[i] = (unsigned short)(e | 0x8000); any_ini |= s >= iniTh; }
+    }
+    const int T = __any_sync(0xffffffffu, any_ini) ? iniTh : minTh;
+    __syncwarp();
+    // ---- phase 5 ----
+    u32* out = cand + (size_t)slot * P.cand_entries + G.cand_ofs + (size_t)cell * G.cell_cap;
+    int count = 0;
+    const int xrel0 = iniX - ORB_DET_ORIGIN + 3, yrel0 = iniY - ORB_DET_ORIGIN + 3;
+    for (int b = 0; b < nB; b += 32) {
+        const int i = b + lane;
+        const int e = i < nB ? list[i] : 0;
+        const int y = (e >> 6) & 63, x = e & 63;
+        const int s = tile[(y + 1) * TP + x + 1];
+        const bool keep = (e & 0x8000) && s >= T;
+        const u32 m = __ballot_sync(0xffffffffu, keep);
+        if (keep) out[count + __popc(m & lt)] = (u32)(xrel0 + x) | ((u32)(yrel0 + y) << 12) | ((u32)s << 24);
+        count += __popc(m);
+    }
     if (lane == 0) *cnt_out = count;
 }
