@@ -30,6 +30,7 @@ ORB = dict(nfeatures=2000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7
 H, W = 376, 1241
 MBF, FX = 386.1448, 718.856                                                       # configs/KITTI00-02.yaml:7,24
 METRIC, UNIT = "stereo_frames_per_sec", "frames/s"
+STREAMS = 1
 
 
 # ------------------------------------------------------------------------------------------------ geometry / bytes
@@ -169,7 +170,7 @@ def run_reference_arm(args):
 
 def workload_config(pairs, chunk):
     return {"workload": "BASELINE.json configs[2]: batch of synthetic KITTI00-02-shape stereo pairs, extract L+R + compute_stereo_matches",
-            "image": [H, W], **ORB, "bf": MBF, "fx": FX, "pairs_per_gpu_per_step": pairs, "chunk_pairs": chunk,
+            "image": [H, W], **ORB, "bf": MBF, "fx": FX, "pairs_per_gpu_per_step": pairs, "chunk_pairs": chunk, "concurrent_streams": STREAMS,
             "l2": "inputs of one step exceed the 126 MB L2 (0.93 MB per pair)", "parallelism": "frames sharded per GPU, no collective"}
 
 
@@ -263,13 +264,29 @@ def run_b200_arm(args):
         right[g:g + m] = torch.roll(br[:m], shifts=9 * (g // nb), dims=2)
     del bl, br
 
-    fe = StereoFrontend(ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"], H, W, P, device=local)
+    # `--streams` front-ends (each with its own workspace) run consecutive chunks concurrently on their own CUDA
+    # streams, so one chunk's latency-bound kernels (octree, small pyramid levels) fill the SMs the other leaves idle
+    NS = max(1, args.streams)
+    fes = [StereoFrontend(ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"], H, W, P, device=local)
+           for _ in range(NS)]
+    fe = fes[0]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)] if NS > 1 else [torch.cuda.current_stream(dev)]
     chunks = [(c, min(P, B - c)) for c in range(0, B, P)]
     outs = [fe.alloc_outputs(n) for _, n in chunks]
 
     def step():
-        for (c, n), o in zip(chunks, outs):
-            fe.run(left[c:c + n], right[c:c + n], MBF, FX, out=o)
+        if NS == 1:
+            for (c, n), o in zip(chunks, outs):
+                fe.run(left[c:c + n], right[c:c + n], MBF, FX, out=o)
+            return
+        main = torch.cuda.current_stream(dev)
+        for s in streams:
+            s.wait_stream(main)
+        for k, ((c, n), o) in enumerate(zip(chunks, outs)):
+            with torch.cuda.stream(streams[k % NS]):
+                fes[k % NS].run(left[c:c + n], right[c:c + n], MBF, FX, out=o)
+        for s in streams:
+            main.wait_stream(s)
 
     def barrier():
         torch.cuda.synchronize()
@@ -280,7 +297,8 @@ def run_b200_arm(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    fe.profile(True, max_calls=args.steps * len(chunks))
+    for f in fes:
+        f.profile(True, max_calls=args.steps * len(chunks))
     clocks = ClockSampler(local)
     l0 = _lib.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -292,9 +310,16 @@ def run_b200_arm(args):
     ms = e0.elapsed_time(e1)
     launches = _lib.kernel_launches() - l0
     clk = clocks.stop()
-    stage_ms, prof_calls, prof_pairs = fe.profile_read()
-    fe.profile(False)
-    ncand = fe.candidate_count(2 * chunks[-1][1]) / (2 * chunks[-1][1])
+    stage_ms, prof_calls, prof_pairs = {}, 0, 0
+    for f in fes:
+        sm_, pc_, pp_ = f.profile_read()
+        f.profile(False)
+        for k_, v_ in sm_.items():
+            stage_ms[k_] = stage_ms.get(k_, 0.0) + v_
+        prof_calls += pc_
+        prof_pairs += pp_
+    last_fe = fes[(len(chunks) - 1) % NS]
+    ncand = last_fe.candidate_count(2 * chunks[-1][1]) / (2 * chunks[-1][1])
     nkp = float(torch.cat([o["nkp"].float().flatten() for o in outs]).mean())
     matched = float(sum(int(((o["uRight"] >= 0) & (torch.arange(fe.capacity, device=dev)[None, :] < o["nkp"][0][:, None])).sum()) for o in outs)) / B
 
@@ -358,7 +383,7 @@ def run_b200_arm(args):
                                     "frac": B_frame * (value / world) / 1e9 / peak},
             "kernels": kernels,
             "workload_stats": {"keypoints_per_image": nkp, "fast_candidates_per_image": ncand, "stereo_matches_per_pair": matched,
-                               "workspace_bytes": fe.workspace_bytes()},
+                               "workspace_bytes": sum(f.workspace_bytes() for f in fes)},
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
@@ -377,8 +402,11 @@ def main():
     ap.add_argument("--chunk", type=int, default=128, help="pairs per kernel-sequence launch")
     ap.add_argument("--base-pairs", type=int, default=16, help="distinct synthetic scenes per rank")
     ap.add_argument("--e2e-pairs", type=int, default=4096)
+    ap.add_argument("--streams", type=int, default=1, help="front-ends running consecutive chunks concurrently (own workspace + stream each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global STREAMS
+    STREAMS = args.streams
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -5,7 +5,10 @@
 #include "plan.h"
 #include "../../include/b200orb_pattern31.h"
 
-__device__ __constant__ signed char c_pattern[1024] = {B200ORB_PATTERN_VALUES};
+// 256 test pairs x (x0, y0, x1, y1) as int8.  Lane i of a warp needs bytes 32*i .. 32*i+31 (descriptor byte i), i.e.
+// 8 consecutive 32-bit words; it reads them straight from this (L1/L2-resident) global array.  Constant memory
+// would serialise the 32 distinct addresses of a warp.
+__device__ __align__(16) const signed char g_pattern[1024] = {B200ORB_PATTERN_VALUES};
 
 // cv::fastAtan2 (degrees), scalar polynomial path
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
@@ -77,9 +80,6 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
                                                               const u8* __restrict__ blur, const u32* __restrict__ lvl_kp,
                                                               const int* __restrict__ lvl_cnt, float* __restrict__ kps,
                                                               u8* __restrict__ desc, int* __restrict__ nkp) {
-    __shared__ signed char pat[1024];
-    for (int i = threadIdx.x; i < 1024; i += DESC_WARPS * 32) pat[i] = c_pattern[i];
-    __syncthreads();
     const int slot = blockIdx.y, lane = threadIdx.x & 31;
     const int i = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
     const int* cnt = lvl_cnt + (size_t)slot * P.nlevels;
@@ -123,11 +123,15 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
     float a, b;
     glibc_sincosf(angle * factorPI, &b, &a);
     const u8* bc = blur + (size_t)slot * P.blur_bytes + G.blur_ofs + (size_t)y * G.blur_pitch + x;
-    const signed char* pp = pat + lane * 32;
+    const int4* pw = reinterpret_cast<const int4*>(g_pattern + lane * 32);
+    const int4 w0 = __ldg(pw), w1 = __ldg(pw + 1);
+    const int pwords[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float x0 = pp[4 * k], y0 = pp[4 * k + 1], x1 = pp[4 * k + 2], y1 = pp[4 * k + 3];
+        const int pk = pwords[k];
+        const float x0 = (float)(signed char)(pk & 0xff), y0 = (float)(signed char)((pk >> 8) & 0xff),
+                    x1 = (float)(signed char)((pk >> 16) & 0xff), y1 = (float)(signed char)(pk >> 24);
         const int t0 = bc[__float2int_rn(x0 * b + y0 * a) * G.blur_pitch + __float2int_rn(x0 * a - y0 * b)];
         const int t1 = bc[__float2int_rn(x1 * b + y1 * a) * G.blur_pitch + __float2int_rn(x1 * a - y1 * b)];
         val |= (t0 < t1) << k;
