@@ -247,6 +247,7 @@ def run_b200_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("B200ORB_NCCL_DEBUG", "WARN")    # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     B, P = args.pairs, args.chunk
