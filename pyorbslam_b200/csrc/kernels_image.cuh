@@ -180,15 +180,27 @@ __device__ __forceinline__ bool fast_quick(const u8* p, int SP, int t) {
     return br | dk;
 }
 
-// 9-of-16 segment test (strictly brighter than v+t or strictly darker than v-t on 9 contiguous ring pixels)
+// 9-of-16 segment test (strictly brighter than v+t or strictly darker than v-t on 9 contiguous ring pixels).
+// The 32 comparisons are done two ring pixels at a time in 16-bit lanes (SWAR): with pair = p_k | p_{k+8} << 16,
+//   pair + (0x7fff - hi) per lane sets bit 15 of a lane  <=>  p > hi        (no carry: p + 0x7fff - hi < 0x10000)
+//   (0x7fff + lo) - pair per lane sets bit 15 of a lane  <=>  p < lo        (no borrow: lane stays in [0x7e01, 0x80fe])
+// and one shift + one and-or drops bit 15 / bit 31 at mask positions k / k + 16.
 __device__ __forceinline__ bool fast_is_corner(const u8* p, int SP, int t) {
     int q[16];
     fast_ring(p, SP, q);
-    const int v = p[0], hi = v + t, lo = v - t;
-    u32 mb = 0, md = 0;
+    const int v = p[0];
+    const u32 kb = (u32)(0x7fff - (v + t)) * 0x00010001u;
+    const u32 kd = (u32)(0x7fff + (v - t)) * 0x00010001u;
+    u32 mb = 0, md = 0;   // bit k = ring position k (k < 8), bit k + 16 = ring position k + 8
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { mb |= (u32)(q[k] > hi) << k; md |= (u32)(q[k] < lo) << k; }
-    mb |= mb << 16; md |= md << 16;
+    for (int k = 0; k < 8; ++k) {
+        const u32 pair = (u32)q[k] | ((u32)q[k + 8] << 16);
+        mb |= ((pair + kb) >> (15 - k)) & (0x00010001u << k);
+        md |= ((kd - pair) >> (15 - k)) & (0x00010001u << k);
+    }
+    // unscramble to the circular order and double it: bits 0..15 = ring, bits 16..31 = ring again
+    mb = (mb & 0xffu) | ((mb >> 8) & 0xff00u); mb |= mb << 16;
+    md = (md & 0xffu) | ((md >> 8) & 0xff00u); md |= md << 16;
     u32 rb = mb & (mb >> 1); rb &= rb >> 2; rb &= rb >> 4; rb &= mb >> 8;
     u32 rd = md & (md >> 1); rd &= rd >> 2; rd &= rd >> 4; rd &= md >> 8;
     return ((rb | rd) & 0xffffu) != 0;
@@ -289,14 +301,28 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_con
 
     // ---- phase 1 ----
     int nA = 0;
-    for (int y = 0; y < ch; ++y)
-        for (int xb = 0; xb < cw; xb += 32) {
-            const int x = xb + lane;
-            const bool pass = x < cw && fast_quick(s0 + y * SP + x, SP, tLow);
+    if (cw <= 32) {             // the usual case (30-px cells): one row per step, pointer walks down the strip
+        const bool inx = lane < cw;
+        const u8* pr = s0 + lane;
+        unsigned short* lw = list;
+#pragma unroll 4
+        for (int y = 0; y < ch; ++y, pr += SP) {
+            const bool pass = inx && fast_quick(pr, SP, tLow);
             const u32 m = __ballot_sync(0xffffffffu, pass);
-            if (pass) list[nA + __popc(m & lt)] = (unsigned short)((y << 6) | x);
-            nA += __popc(m);
+            if (pass) lw[__popc(m & lt)] = (unsigned short)((y << 6) | lane);
+            lw += __popc(m);
         }
+        nA = (int)(lw - list);
+    } else {
+        for (int y = 0; y < ch; ++y)
+            for (int xb = 0; xb < cw; xb += 32) {
+                const int x = xb + lane;
+                const bool pass = x < cw && fast_quick(s0 + y * SP + x, SP, tLow);
+                const u32 m = __ballot_sync(0xffffffffu, pass);
+                if (pass) list[nA + __popc(m & lt)] = (unsigned short)((y << 6) | x);
+                nA += __popc(m);
+            }
+    }
     __syncwarp();
     // ---- phase 2 ----
     int nB = 0;
