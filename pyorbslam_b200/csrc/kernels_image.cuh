@@ -208,30 +208,34 @@ __device__ __forceinline__ bool fast_is_corner(const u8* p, int SP, int t) {
 
 // exact OpenCV corner score (cornerScore<16>) of a pixel known to be a corner: best - 1 with
 // best = max over the 16 arcs of 9 of min(v - p_k) and of min(p_k - v).
+// Works on the biased differences D_k = 255 + v - p_k in [0, 510]: the bright side min(p_k - v) equals
+// 255 - max(D), so no negated operand ever feeds a max -- ptxas 12.9 (sm_100a, -O1 and above) drops the
+// negation when it fuses max(x, -y) chains into VIMNMX3 (caught by tests/cuda_unit/fast_unit.cu).
+// Two ring positions (k, k + 8) share one register as 16-bit lanes, so position k + 8 is the lane-swapped
+// register of position k, and the sliding window of 9 = 3 x 3 is two passes of the native 3-input packed
+// min / max (VIMNMX3.S16x2): 16 + 16 instructions give all 16 arc minima and maxima.
+__device__ __forceinline__ u32 swap16(u32 x) { return __byte_perm(x, 0, 0x1032); }
 __device__ __forceinline__ int fast_corner_score(const u8* p, int SP) {
     int q[16];
     fast_ring(p, SP, q);
-    const int v = p[0];
-    // sliding min / max over windows of 9 on the circle (doubling: 2, 4, 8, then +1).
-    // Works on the biased differences D = 255 + v - p_k in [0, 510]: the bright side min(p_k - v) equals
-    // 255 - max(D), so no negated operand ever feeds a max -- ptxas 12.9 (sm_100a, -O1 and above) drops the
-    // negation when it fuses max(x, -y) chains into VIMNMX3 (caught by tests/cuda_unit/fast_unit.cu).
-    int d[16], a[16], b[16];
+    const u32 bias = (u32)(255 + p[0]) * 0x00010001u;
+    u32 D[10];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = 255 + v - q[k];
+    for (int k = 0; k < 8; ++k) D[k] = bias - ((u32)q[k] | ((u32)q[k + 8] << 16));   // no borrow: lanes stay in [0, 510]
+    D[8] = swap16(D[0]); D[9] = swap16(D[1]);
+    u32 n3[14], x3[14];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { a[k] = min(d[k], d[(k + 1) & 15]); b[k] = max(d[k], d[(k + 1) & 15]); }
-    int a4[16], b4[16];
+    for (int k = 0; k < 8; ++k) { n3[k] = __vimin3_s16x2(D[k], D[k + 1], D[k + 2]); x3[k] = __vimax3_s16x2(D[k], D[k + 1], D[k + 2]); }
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { a4[k] = min(a[k], a[(k + 2) & 15]); b4[k] = max(b[k], b[(k + 2) & 15]); }
-    int bestDark = 0, worstBright = 510;
+    for (int k = 8; k < 14; ++k) { n3[k] = swap16(n3[k - 8]); x3[k] = swap16(x3[k - 8]); }
+    u32 n9[8], x9[8];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int mn = min(min(a4[k], a4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int mx = max(max(b4[k], b4[(k + 4) & 15]), d[(k + 8) & 15]);
-        bestDark = max(bestDark, mn);          // 255 + max_arcs min(v - p)
-        worstBright = min(worstBright, mx);    // 255 - max_arcs min(p - v)
-    }
+    for (int k = 0; k < 8; ++k) { n9[k] = __vimin3_s16x2(n3[k], n3[k + 3], n3[k + 6]); x9[k] = __vimax3_s16x2(x3[k], x3[k + 3], x3[k + 6]); }
+    // best dark = max of the 16 arc minima; worst bright = min of the 16 arc maxima
+    u32 bd = __vimax3_s16x2(__vimax3_s16x2(n9[0], n9[1], n9[2]), __vimax3_s16x2(n9[3], n9[4], n9[5]), __vimax3_s16x2(n9[6], n9[7], n9[7]));
+    u32 wb = __vimin3_s16x2(__vimin3_s16x2(x9[0], x9[1], x9[2]), __vimin3_s16x2(x9[3], x9[4], x9[5]), __vimin3_s16x2(x9[6], x9[7], x9[7]));
+    const int bestDark = max((int)(bd & 0xffff), (int)(bd >> 16));          // 255 + max_arcs min(v - p)
+    const int worstBright = min((int)(wb & 0xffff), (int)(wb >> 16));       // 255 - max_arcs min(p - v)
     return max(bestDark - 255, 255 - worstBright) - 1;
 }
 
