@@ -143,23 +143,31 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
         maxcap = std::max(maxcap, G.kp_cap); maxcells = std::max(maxcells, nRows * nCols);
         if (l > 0) {   // cv::resize INTER_LINEAR tables, SURVEY.md App. A2
             const LevelGeom& S = P.lv[l - 1];
-            G.xtab_ofs = (int)hp.xtab.size(); G.ytab_ofs = (int)hp.ytab.size();
             const double sx_ = 1. / ((double)G.w / S.w), sy_ = 1. / ((double)G.h / S.h);
+            std::vector<XTab> xr(G.w);
+            std::vector<YTab> yr(G.h);
             for (int dx = 0; dx < G.w; ++dx) {
                 float fx = (float)((dx + 0.5) * sx_ - 0.5);
                 int sx = (int)floorf(fx);
                 fx -= sx;
                 if (sx < 0) { fx = 0; sx = 0; }
                 if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
-                hp.xtab.push_back(XTab{sx, sat_short(cv_round_f((1.f - fx) * 2048.f)), sat_short(cv_round_f(fx * 2048.f))});
+                xr[dx] = XTab{sx, sat_short(cv_round_f((1.f - fx) * 2048.f)), sat_short(cv_round_f(fx * 2048.f))};
             }
             for (int dy = 0; dy < G.h; ++dy) {
                 float fy = (float)((dy + 0.5) * sy_ - 0.5);
                 int sy = (int)floorf(fy);
                 fy -= sy;
-                hp.ytab.push_back(YTab{(short)std::min(std::max(sy, 0), S.h - 1), (short)std::min(std::max(sy + 1, 0), S.h - 1),
-                                       sat_short(cv_round_f((1.f - fy) * 2048.f)), sat_short(cv_round_f(fy * 2048.f))});
+                yr[dy] = YTab{(short)std::min(std::max(sy, 0), S.h - 1), (short)std::min(std::max(sy + 1, 0), S.h - 1),
+                              sat_short(cv_round_f((1.f - fy) * 2048.f)), sat_short(cv_round_f(fy * 2048.f))};
             }
+            // device tables are indexed by BORDERED coordinates: reflect-101 applied here, x padded to the pitch
+            auto refl = [](int p, int len) { if (len == 1) return 0; while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * len - 2 - p; return p; };
+            while (hp.xtab.size() % 4) hp.xtab.push_back(XTab{0, 0, 0});      // 32-byte alignment of each level's row
+            G.xtab_ofs = (int)hp.xtab.size(); G.ytab_ofs = (int)hp.ytab.size();
+            const int bw = G.w + 2 * ORB_EDGE;
+            for (int bx = 0; bx < G.pitch; ++bx) hp.xtab.push_back(xr[refl(std::min(bx, bw - 1) - ORB_EDGE, G.w)]);
+            for (int by = 0; by < G.rows; ++by) hp.ytab.push_back(yr[refl(by - ORB_EDGE, G.h)]);
         }
     }
     P.pyr_bytes = pyr; P.blur_bytes = blr; P.ncells = std::max(cells, 1); P.cand_entries = std::max(cand, 4);

@@ -51,6 +51,9 @@ __global__ void __launch_bounds__(256) k_border0(const __grid_constant__ Plan P,
 // Fixed point exactly as OpenCV's 8-bit linear path: 11-bit coefficients,
 // dst = (((b0*(T0>>4))>>16) + ((b1*(T1>>4))>>16) + 2) >> 2   (SURVEY.md App. A2).
 // ------------------------------------------------------------------------------------------------
+// The tables are indexed by BORDERED coordinates (the host applied the reflect-101 map and padded each row of
+// entries to the buffer pitch), so a thread's four column entries are one aligned 32-byte read (2 x LDG.128)
+// instead of four scattered 8-byte reads -- the kernel is L1-wavefront bound, not DRAM bound.
 __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Plan P, int l, u8* __restrict__ pyr,
                                                 const XTab* __restrict__ xtab, const YTab* __restrict__ ytab) {
     const LevelGeom& G = P.lv[l];
@@ -62,21 +65,23 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Plan P, 
     const int by = idx / words_per_row, bx = (idx - by * words_per_row) << 2;
     u8* base = pyr + (size_t)slot * P.pyr_bytes;
     const u8* src = base + S.pyr_ofs + (size_t)ORB_EDGE * S.pitch + ORB_EDGE;   // ROI origin of level l-1
-    const YTab yt = ytab[G.ytab_ofs + reflect101(by - ORB_EDGE, G.h)];
+    const YTab yt = ytab[G.ytab_ofs + by];
     const u8* r0 = src + (size_t)yt.y0 * S.pitch;
     const u8* r1 = src + (size_t)yt.y1 * S.pitch;
+    const int4* tp = reinterpret_cast<const int4*>(xtab + G.xtab_ofs + bx);
+    const int4 t01 = __ldg(tp), t23 = __ldg(tp + 1);
+    const int sxs[4] = {t01.x, t01.z, t23.x, t23.z};
+    const int cf[4] = {t01.y, t01.w, t23.y, t23.w};       // a0 | a1 << 16
+    const int bw = G.w + 2 * ORB_EDGE;
     u32 v = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int x = bx + k;
-        if (x < G.w + 2 * ORB_EDGE) {
-            const XTab xt = xtab[G.xtab_ofs + reflect101(x - ORB_EDGE, G.w)];
-            // when sx is the last column a1 == 0 and sx+1 reads the (valid) border pixel
-            const int T0 = r0[xt.sx] * xt.a0 + r0[xt.sx + 1] * xt.a1;
-            const int T1 = r1[xt.sx] * xt.a0 + r1[xt.sx + 1] * xt.a1;
-            const int d = (((yt.b0 * (T0 >> 4)) >> 16) + ((yt.b1 * (T1 >> 4)) >> 16) + 2) >> 2;
-            v |= (u32)(d & 0xff) << (8 * k);
-        }
+        // when sx is the last column a1 == 0 and sx+1 reads the (valid) border pixel
+        const int sx = sxs[k], a0 = (short)(cf[k] & 0xffff), a1 = cf[k] >> 16;
+        const int T0 = r0[sx] * a0 + r0[sx + 1] * a1;
+        const int T1 = r1[sx] * a0 + r1[sx + 1] * a1;
+        const int d = (((yt.b0 * (T0 >> 4)) >> 16) + ((yt.b1 * (T1 >> 4)) >> 16) + 2) >> 2;
+        if (bx + k < bw) v |= (u32)(d & 0xff) << (8 * k);
     }
     *reinterpret_cast<u32*>(base + G.pyr_ofs + (size_t)by * G.pitch + bx) = v;
 }
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(BLUR_WARPS * 32) k_blur(const __grid_constant_
     const int w0 = min((x0 + 16) >> 2, wpr - 1);
     const int wx = min(((tx * BLUR_TW + 16) >> 2) + 32 + (lane & 1), wpr - 1);   // lanes 0/1 fetch the two words past the strip
     u8* dst = blur + (size_t)slot * P.blur_bytes + G.blur_ofs;
-    u32 h01[7], h23[7];                                      // 7 filtered rows, two 16-bit values per register
+    u32 hb[7][4];                                            // ring of 7 horizontally filtered rows, 4 columns each
 #pragma unroll
     for (int r = 0; r < BLUR_RB + 6; ++r) {
         const int by = min(y0 + r - 3 + ORB_EDGE, G.rows - 1);
@@ -123,30 +128,25 @@ __global__ void __launch_bounds__(BLUR_WARPS * 32) k_blur(const __grid_constant_
         const u32 X0 = __shfl_sync(0xffffffffu, X, 0), X1 = __shfl_sync(0xffffffffu, X, 1);
         if (lane == 31) { B = X0; C = X1; }
         if (lane == 30) C = X0;
-        const int a0 = A & 0xff, a1 = (A >> 8) & 0xff, a2 = (A >> 16) & 0xff, a3 = A >> 24;
-        const int a4 = B & 0xff, a5 = (B >> 8) & 0xff, a6 = (B >> 16) & 0xff, a7 = B >> 24;
-        const int a8 = C & 0xff, a9 = (C >> 8) & 0xff;
-        const u32 f0 = 18 * (a0 + a6) + 34 * (a1 + a5) + 48 * (a2 + a4) + 56 * a3;
-        const u32 f1 = 18 * (a1 + a7) + 34 * (a2 + a6) + 48 * (a3 + a5) + 56 * a4;
-        const u32 f2 = 18 * (a2 + a8) + 34 * (a3 + a7) + 48 * (a4 + a6) + 56 * a5;
-        const u32 f3 = 18 * (a3 + a9) + 34 * (a4 + a8) + 48 * (a5 + a7) + 56 * a6;
-        h01[r % 7] = f0 | (f1 << 16);
-        h23[r % 7] = f2 | (f3 << 16);
+        const u32 a0 = A & 0xff, a1 = (A >> 8) & 0xff, a2 = (A >> 16) & 0xff, a3 = A >> 24;
+        const u32 a4 = B & 0xff, a5 = (B >> 8) & 0xff, a6 = (B >> 16) & 0xff, a7 = B >> 24;
+        const u32 a8 = C & 0xff, a9 = (C >> 8) & 0xff;
+        u32* hr = hb[r % 7];
+        hr[0] = 18 * (a0 + a6) + 34 * (a1 + a5) + 48 * (a2 + a4) + 56 * a3;
+        hr[1] = 18 * (a1 + a7) + 34 * (a2 + a6) + 48 * (a3 + a5) + 56 * a4;
+        hr[2] = 18 * (a2 + a8) + 34 * (a3 + a7) + 48 * (a4 + a6) + 56 * a5;
+        hr[3] = 18 * (a3 + a9) + 34 * (a4 + a8) + 48 * (a5 + a7) + 56 * a6;
         if (r >= 6) {
             const int y = y0 + r - 6;
-            // rows r-6 .. r are in the ring; taps 0..6 <-> ring slots (r-6)%7 .. r%7
-            const u32 p0 = h01[(r - 6) % 7], p1 = h01[(r - 5) % 7], p2 = h01[(r - 4) % 7], p3 = h01[(r - 3) % 7],
-                      p4 = h01[(r - 2) % 7], p5 = h01[(r - 1) % 7], p6 = h01[r % 7];
-            const u32 q0 = h23[(r - 6) % 7], q1 = h23[(r - 5) % 7], q2 = h23[(r - 4) % 7], q3 = h23[(r - 3) % 7],
-                      q4 = h23[(r - 2) % 7], q5 = h23[(r - 1) % 7], q6 = h23[r % 7];
-#define BLUR_V(lo0, lo1, lo2, lo3, lo4, lo5, lo6) ((18u * ((lo0) + (lo6)) + 34u * ((lo1) + (lo5)) + 48u * ((lo2) + (lo4)) + 56u * (lo3) + 32768u) >> 16)
-            const u32 o0 = BLUR_V(p0 & 0xffff, p1 & 0xffff, p2 & 0xffff, p3 & 0xffff, p4 & 0xffff, p5 & 0xffff, p6 & 0xffff);
-            const u32 o1 = BLUR_V(p0 >> 16, p1 >> 16, p2 >> 16, p3 >> 16, p4 >> 16, p5 >> 16, p6 >> 16);
-            const u32 o2 = BLUR_V(q0 & 0xffff, q1 & 0xffff, q2 & 0xffff, q3 & 0xffff, q4 & 0xffff, q5 & 0xffff, q6 & 0xffff);
-            const u32 o3 = BLUR_V(q0 >> 16, q1 >> 16, q2 >> 16, q3 >> 16, q4 >> 16, q5 >> 16, q6 >> 16);
-#undef BLUR_V
+            u32 o = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {   // taps 0..6 <-> ring slots (r-6)%7 .. r%7
+                const u32 acc = 18u * (hb[(r - 6) % 7][c] + hb[r % 7][c]) + 34u * (hb[(r - 5) % 7][c] + hb[(r - 1) % 7][c]) +
+                                48u * (hb[(r - 4) % 7][c] + hb[(r - 2) % 7][c]) + 56u * hb[(r - 3) % 7][c];
+                o |= ((acc + 32768u) >> 16) << (8 * c);
+            }
             if (y < G.h && x0 < G.w)   // blur pitch is a multiple of 64: the aligned 4-byte store may spill into padding only
-                *reinterpret_cast<u32*>(dst + (size_t)y * G.blur_pitch + x0) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+                *reinterpret_cast<u32*>(dst + (size_t)y * G.blur_pitch + x0) = o;
         }
     }
 }
@@ -248,8 +248,8 @@ __device__ __forceinline__ int fast_score(const u8* p, int SP, int t) {
 // Work list entry: y << 6 | x inside the cell's detection window (both < 64), bit 15 = survives NMS.
 // Phases per cell (one warp), each on FULL warps thanks to in-place ordered compaction of the list:
 //   1 quick reject over all window pixels        -> list A (row-major)
-//   2 9-of-16 segment test on list A             -> list B (in place)
-//   3 exact score of list B                      -> score tile (zero elsewhere = "non-corner / outside scores 0")
+//   2+3 exact corner strength of list A (packed 3-input min/max); entries with score >= threshold -> list B (in place)
+//       and the score tile (zero elsewhere = "non-corner / outside scores 0")
 //   4 strict 8-neighbour NMS on list B; any survivor with score >= iniThFAST decides the threshold
 //   5 ordered emission of survivors with score >= T
 __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
@@ -328,23 +328,23 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_con
             }
     }
     __syncwarp();
-    // ---- phase 2 ----
+    // ---- phases 2 + 3: exact corner strength of every quick-test survivor; corner at tLow <=> best > tLow <=>
+    // score >= tLow (a score of 0 can never win the strict NMS, so it is dropped like a non-corner) ----
+    const int tKeep = max(tLow, 1);
     int nB = 0;
     for (int b = 0; b < nA; b += 32) {
         const int i = b + lane;
         const int e = i < nA ? list[i] : 0;
-        const bool c = i < nA && fast_is_corner(s0 + (e >> 6) * SP + (e & 63), SP, tLow);
+        const int y = e >> 6, x = e & 63;
+        const int s = i < nA ? fast_corner_score(s0 + y * SP + x, SP) : 0;
+        const bool c = s >= tKeep;
         const u32 m = __ballot_sync(0xffffffffu, c);
         __syncwarp();
-        if (c) list[nB + __popc(m & lt)] = (unsigned short)e;
+        if (c) {
+            list[nB + __popc(m & lt)] = (unsigned short)e;
+            tile[(y + 1) * TP + x + 1] = (u8)s;
+        }
         nB += __popc(m);
-    }
-    __syncwarp();
-    // ---- phase 3 ----
-    for (int i = lane; i < nB; i += 32) {
-        const int e = list[i], y = e >> 6, x = e & 63;
-        const int s = fast_corner_score(s0 + y * SP + x, SP);
-        tile[(y + 1) * TP + x + 1] = (u8)s;
     }
     __syncwarp();
     // ---- phase 4 ----
