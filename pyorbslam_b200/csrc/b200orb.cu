@@ -298,6 +298,7 @@ struct Engine {
             SG.sf[l] = G.sf; SG.isf[l] = G.isf; SG.w[l] = G.w; SG.h[l] = G.h;
             SG.plog[l] = G.w + 2 * ORB_EDGE;                 // the reference's Mat step
             SG.pitch[l] = G.pitch;
+            SG.magic[l] = (unsigned)((0x100000000ULL + SG.plog[l] - 1) / SG.plog[l]);
             SG.off0[l] = ORB_EDGE * SG.plog[l] + ORB_EDGE;
             SG.base[l] = G.pyr_ofs;
         }
@@ -577,6 +578,7 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     for (int l = 0; l < nlevels; ++l) {
         SG.sf[l] = sf[l]; SG.isf[l] = isf[l]; SG.w[l] = lw[l]; SG.h[l] = lh[l];
         SG.plog[l] = lw[l]; SG.pitch[l] = lw[l]; SG.off0[l] = 0; SG.base[l] = total;
+        SG.magic[l] = lw[l] > 1 ? (unsigned)((0x100000000ULL + lw[l] - 1) / lw[l]) : 0xffffffffu;
         total += ((long long)lw[l] * lh[l] + 255) & ~255LL;
     }
     // host-side validation of what the reference would index (rows of vRowIndices, octaves)

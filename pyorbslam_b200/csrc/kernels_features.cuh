@@ -236,7 +236,8 @@ struct StereoArgs {
 
 __device__ __forceinline__ const u8* view_ptr(const u8* base, const StereoGeom& SG, int o, int row, int col) {
     const int lin = SG.off0[o] + row * SG.w[o] + col;
-    const int pr = lin / SG.plog[o];
+    int pr = (int)__umulhi((unsigned)lin, SG.magic[o]);           // lin / plog via ceil(2^32 / plog); may overshoot by one
+    if (pr * SG.plog[o] > lin) --pr;
     return base + SG.base[o] + (size_t)pr * SG.pitch[o] + (lin - pr * SG.plog[o]);
 }
 

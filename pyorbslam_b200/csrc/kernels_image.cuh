@@ -267,7 +267,6 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_con
     const int j0 = g * FAST_WARPS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 lt = (1u << lane) - 1;
-    const int tLow = max(0, min(min(P.iniTh, P.minTh), 255));
 
     const int iniY = ORB_DET_ORIGIN + ci * G.hCell;
     const int maxY = min(iniY + G.hCell + 6, G.maxBY);
@@ -303,63 +302,77 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_con
     unsigned short* list = reinterpret_cast<unsigned short*>(smem + SP * SR + FAST_WARPS * (TP * TR)) + warp * LC;
     const u8* s0 = strip + 3 * SP + (iniX - sx0) + shift + 3;
 
-    // ---- phase 1 ----
-    int nA = 0;
-    if (cw <= 32) {             // the usual case (30-px cells): one row per step, pointer walks down the strip
-        const bool inx = lane < cw;
-        const u8* pr = s0 + lane;
-        unsigned short* lw = list;
-#pragma unroll 4
-        for (int y = 0; y < ch; ++y, pr += SP) {
-            const bool pass = inx && fast_quick(pr, SP, tLow);
-            const u32 m = __ballot_sync(0xffffffffu, pass);
-            if (pass) lw[__popc(m & lt)] = (unsigned short)((y << 6) | lane);
-            lw += __popc(m);
-        }
-        nA = (int)(lw - list);
-    } else {
-        for (int y = 0; y < ch; ++y)
-            for (int xb = 0; xb < cw; xb += 32) {
-                const int x = xb + lane;
-                const bool pass = x < cw && fast_quick(s0 + y * SP + x, SP, tLow);
-                const u32 m = __ballot_sync(0xffffffffu, pass);
-                if (pass) list[nA + __popc(m & lt)] = (unsigned short)((y << 6) | x);
-                nA += __popc(m);
-            }
-    }
-    __syncwarp();
-    // ---- phases 2 + 3: exact corner strength of every quick-test survivor; corner at tLow <=> best > tLow <=>
-    // score >= tLow (a score of 0 can never win the strict NMS, so it is dropped like a non-corner) ----
-    const int tKeep = max(tLow, 1);
-    int nB = 0;
-    for (int b = 0; b < nA; b += 32) {
-        const int i = b + lane;
-        const int e = i < nA ? list[i] : 0;
-        const int y = e >> 6, x = e & 63;
-        const int s = i < nA ? fast_corner_score(s0 + y * SP + x, SP) : 0;
-        const bool c = s >= tKeep;
-        const u32 m = __ballot_sync(0xffffffffu, c);
-        __syncwarp();
-        if (c) {
-            list[nB + __popc(m & lt)] = (unsigned short)e;
-            tile[(y + 1) * TP + x + 1] = (u8)s;
-        }
-        nB += __popc(m);
-    }
-    __syncwarp();
-    // ---- phase 4 ----
+    // Threshold schedule = the reference's own (ORBextractor.cpp:808-815): detect at iniThFAST; only if nothing survives
+    // the NMS, detect again at minThFAST.  Survivors at T are exactly the strict local maxima among corners with
+    // score >= T (corners below T count 0), so running the whole pipeline at T first is equivalent to thresholding a
+    // minThFAST score map -- and far cheaper for textured cells, whose quick-test pass rate at 20 is a fraction of that at 7.
     const int iniTh = max(0, min(P.iniTh, 255)), minTh = max(0, min(P.minTh, 255));
-    bool any_ini = false;
-    for (int i = lane; i < nB; i += 32) {
-        const int e = list[i];
-        const u8* t = tile + ((e >> 6) + 1) * TP + (e & 63) + 1;
-        const int s = t[0];
-        const bool keep = s > 0 && s > t[-1] && s > t[1] && s > t[-TP - 1] && s > t[-TP] && s > t[-TP + 1] &&
-                          s > t[TP - 1] && s > t[TP] && s > t[TP + 1];
-        if (keep) { list[i] = (unsigned short)(e | 0x8000); any_ini |= s >= iniTh; }
+    int T = iniTh, nB = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // ---- phase 1 ----
+        int nA = 0;
+        if (cw <= 32) {             // the usual case (30-px cells): one row per step, pointer walks down the strip
+            const bool inx = lane < cw;
+            const u8* pr = s0 + lane;
+            unsigned short* lw = list;
+#pragma unroll 4
+            for (int y = 0; y < ch; ++y, pr += SP) {
+                const bool pass = inx && fast_quick(pr, SP, T);
+                const u32 m = __ballot_sync(0xffffffffu, pass);
+                if (pass) lw[__popc(m & lt)] = (unsigned short)((y << 6) | lane);
+                lw += __popc(m);
+            }
+            nA = (int)(lw - list);
+        } else {
+            for (int y = 0; y < ch; ++y)
+                for (int xb = 0; xb < cw; xb += 32) {
+                    const int x = xb + lane;
+                    const bool pass = x < cw && fast_quick(s0 + y * SP + x, SP, T);
+                    const u32 m = __ballot_sync(0xffffffffu, pass);
+                    if (pass) list[nA + __popc(m & lt)] = (unsigned short)((y << 6) | x);
+                    nA += __popc(m);
+                }
+        }
+        __syncwarp();
+        // ---- phases 2 + 3: exact corner strength of every quick-test survivor; corner at T <=> best > T <=> score >= T
+        // (a score of 0 can never win the strict NMS, so it is dropped like a non-corner) ----
+        const int tKeep = max(T, 1);
+        nB = 0;
+        for (int b = 0; b < nA; b += 32) {
+            const int i = b + lane;
+            const int e = i < nA ? list[i] : 0;
+            const int y = e >> 6, x = e & 63;
+            const int s = i < nA ? fast_corner_score(s0 + y * SP + x, SP) : 0;
+            const bool c = s >= tKeep;
+            const u32 m = __ballot_sync(0xffffffffu, c);
+            __syncwarp();
+            if (c) {
+                list[nB + __popc(m & lt)] = (unsigned short)e;
+                tile[(y + 1) * TP + x + 1] = (u8)s;
+            }
+            nB += __popc(m);
+        }
+        __syncwarp();
+        // ---- phase 4: strict 8-neighbour NMS inside the window ----
+        bool any = false;
+        for (int i = lane; i < nB; i += 32) {
+            const int e = list[i];
+            const u8* t = tile + ((e >> 6) + 1) * TP + (e & 63) + 1;
+            const int s = t[0];
+            const bool keep = s > t[-1] && s > t[1] && s > t[-TP - 1] && s > t[-TP] && s > t[-TP + 1] &&
+                              s > t[TP - 1] && s > t[TP] && s > t[TP + 1];
+            if (keep) { list[i] = (unsigned short)(e | 0x8000); any = true; }
+        }
+        __syncwarp();
+        if (__any_sync(0xffffffffu, any) || minTh >= T) break;      // vKeysCell non-empty, or the retry cannot add anything
+        for (int i = lane; i < nB; i += 32) {                        // clear the tile for the second attempt
+            const int e = list[i];
+            tile[((e >> 6) + 1) * TP + (e & 63) + 1] = 0;
+        }
+        __syncwarp();
+        T = minTh;
+        nB = 0;
     }
-    const int T = __any_sync(0xffffffffu, any_ini) ? iniTh : minTh;
-    __syncwarp();
     // ---- phase 5 ----
     u32* out = cand + (size_t)slot * P.cand_entries + G.cand_ofs + (size_t)cell * G.cell_cap;
     int count = 0;
@@ -369,7 +382,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_con
         const int e = i < nB ? list[i] : 0;
         const int y = (e >> 6) & 63, x = e & 63;
         const int s = tile[(y + 1) * TP + x + 1];
-        const bool keep = (e & 0x8000) && s >= T;
+        const bool keep = (e & 0x8000) != 0;
         const u32 m = __ballot_sync(0xffffffffu, keep);
         if (keep) out[count + __popc(m & lt)] = (u32)(xrel0 + x) | ((u32)(yrel0 + y) << 12) | ((u32)s << 24);
         count += __popc(m);

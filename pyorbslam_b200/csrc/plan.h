@@ -49,6 +49,7 @@ struct StereoGeom {
     float sf[ORB_MAX_LEVELS], isf[ORB_MAX_LEVELS];
     int w[ORB_MAX_LEVELS], h[ORB_MAX_LEVELS];
     int plog[ORB_MAX_LEVELS];    // logical pitch of the buffer the view is cut from (w+38 resident, w uploaded)
+    unsigned magic[ORB_MAX_LEVELS];   // ceil(2^32 / plog): division by plog as multiply-high + one correction
     int pitch[ORB_MAX_LEVELS];   // physical pitch
     int off0[ORB_MAX_LEVELS];    // logical linear offset of view element (0,0): 19*plog+19 resident, 0 uploaded
     long long base[ORB_MAX_LEVELS];  // byte offset of the level inside one image's blob
