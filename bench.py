@@ -182,7 +182,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -219,6 +219,19 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, so the pinned staging buffers are first-touched
+    on that NUMA node (matters once several ranks stream 30+ GB/s each through the host)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception as e:      # affinity is an optimisation only
+        return f"unavailable: {e}"
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_b200_arm(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -246,6 +259,7 @@ def run_b200_arm(args):
         raise RuntimeError("bench.py needs a CUDA device: pyorbslam_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)    # pinned host buffers should live on the GPU's own NUMA node
     if world > 1:
         os.environ["NCCL_DEBUG"] = os.environ.get("B200ORB_NCCL_DEBUG", "WARN")    # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
@@ -332,8 +346,10 @@ def run_b200_arm(args):
 
     # ---- end to end through the host-buffer C-ABI call ----
     Be = min(B, args.e2e_pairs)
-    lh = left[:Be].cpu().pin_memory()
-    rh = right[:Be].cpu().pin_memory()
+    lh = torch.empty((Be, H, W), dtype=torch.uint8, pin_memory=True)
+    rh = torch.empty((Be, H, W), dtype=torch.uint8, pin_memory=True)
+    lh.copy_(left[:Be])
+    rh.copy_(right[:Be])
     oh = fe.alloc_outputs(Be, pinned_host=True)
     for _ in range(2):
         fe.run_host(lh, rh, MBF, FX, out=oh)
@@ -384,7 +400,7 @@ def run_b200_arm(args):
                                     "frac": B_frame * (value / world) / 1e9 / peak},
             "kernels": kernels,
             "workload_stats": {"keypoints_per_image": nkp, "fast_candidates_per_image": ncand, "stereo_matches_per_pair": matched,
-                               "workspace_bytes": sum(f.workspace_bytes() for f in fes)},
+                               "workspace_bytes": sum(f.workspace_bytes() for f in fes), "rank0_cpu_affinity": numa if isinstance(numa, str) else f"{len(numa)} cpus: {numa[0]}-{numa[-1]}"},
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
@@ -402,7 +418,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=4096, help="stereo pairs per GPU per step (BASELINE.json configs[2]: 4096)")
     ap.add_argument("--chunk", type=int, default=128, help="pairs per kernel-sequence launch")
     ap.add_argument("--base-pairs", type=int, default=16, help="distinct synthetic scenes per rank")
-    ap.add_argument("--e2e-pairs", type=int, default=4096)
+    ap.add_argument("--e2e-pairs", type=int, default=2048, help="pairs per end-to-end step (pinned host memory: 0.93 MB in + 0.25 MB out per pair)")
     ap.add_argument("--streams", type=int, default=1, help="front-ends running consecutive chunks concurrently (own workspace + stream each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -91,6 +91,18 @@ int b200orb_get_level_candidates(b200orb_extractor* e, int level, int cap, int* 
 int b200orb_stereo(b200orb_extractor* left, b200orb_extractor* right, double mbf, float fx,
                    float* uRight, float* depth, int* matchIdx);
 
+/* Same with options and the SAD minimum of every accepted match (sadDist, optional, -1 = no match).
+ * flags = 0 is exactly b200orb_stereo, i.e. exactly the reference.  The two flags are opt-in extensions for users who
+ * want upstream ORB-SLAM2 behaviour instead; the reference does NOT behave this way:
+ *   B200ORB_STEREO_MEDIAN_CULL   drop matches whose SAD minimum is >= 1.5f*1.4f*median (upstream ComputeStereoMatches;
+ *                                in the reference vDistIdx is filled and then discarded, Frame.py:185,279)
+ *   B200ORB_STEREO_DENSE_PYRAMID take SAD windows from the true level image instead of the step-ignoring view the
+ *                                reference's Mat caster hands to Python (opencv_type_casters.h:230-239) */
+#define B200ORB_STEREO_MEDIAN_CULL 1
+#define B200ORB_STEREO_DENSE_PYRAMID 2
+int b200orb_stereo_ex(b200orb_extractor* left, b200orb_extractor* right, double mbf, float fx, int flags,
+                      float* uRight, float* depth, int* matchIdx, int* sadDist);
+
 /* general form on caller-supplied host data (any keypoints, e.g. the stereo-only sweep):
  * kps*: float[n][3] = (x, y, octave); pyr*: nlevels pointers to the GetImagePyramid() views, level l is
  * uint8[lh[l]][lw[l]]; sf/isf: GetScaleFactors()/GetInverseScaleFactors(). */
@@ -134,6 +146,9 @@ int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint
 int b200orb_batch_run_host(b200orb_batch* b, const uint8_t* h_left, const uint8_t* h_right, int n_pairs,
                            double mbf, float fx, float* h_kps, uint8_t* h_desc, int32_t* h_nkp,
                            float* h_uRight, float* h_depth, int32_t* h_matchIdx);
+
+/* stereo options of the batched path (same flags as b200orb_stereo_ex; default 0 = the reference's behaviour) */
+int b200orb_batch_set_stereo_flags(b200orb_batch* b, int flags);
 
 /* diagnostic: total number of FAST candidates (the octree kernel's input) in the first n_images slots of the last
  * run -- bench.py uses it for the octree kernel's algorithmic byte count */

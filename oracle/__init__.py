@@ -44,10 +44,10 @@ def lib():
         _LIB.orbo_level_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _LIB.orbo_level_keypoints.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _LIB.orbo_sincos_exhaustive_mismatches.restype = C.c_long
-        _LIB.orbo_stereo.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
-                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, C.c_void_p, C.c_double, C.c_float,
-                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _LIB.orbo_stereo_ex.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_double, C.c_float,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     return _LIB
 
 
@@ -211,8 +211,23 @@ class OracleExtractor:
 
 
 # ---------------------------------------------------------------- stereo (C restatement)
-def stereo(kpsL, descL, kpsR, descR, sf, isf, pyrL, pyrR, mbf, fx):
-    """kps*: [n,3] float32 (x, y, octave); pyr*: list of caster views.  Returns uRight, depth, bestIdx, bestDist."""
+def median_cull(uR, dep, sad):
+    """Upstream ORB-SLAM2's outlier cull at the end of ComputeStereoMatches (NOT in the reference):
+    sort the accepted matches by SAD minimum, median = element [n // 2], thDist = 1.5f * 1.4f * median, drop dist >= thDist."""
+    uR, dep = uR.copy(), dep.copy()
+    idx = np.nonzero(sad >= 0)[0]
+    if len(idx):
+        d = np.sort(sad[idx])
+        th = np.float32(np.float32(1.5) * np.float32(1.4)) * np.float32(d[len(d) // 2])
+        drop = idx[~(sad[idx].astype(np.float32) < th)]
+        uR[drop] = -1
+        dep[drop] = -1
+    return uR, dep
+
+
+def stereo(kpsL, descL, kpsR, descR, sf, isf, pyrL, pyrR, mbf, fx, with_sad=False):
+    """kps*: [n,3] float32 (x, y, octave); pyr*: list of caster views (or of true level images for the "dense pyramid"
+    option).  Returns uRight, depth, bestIdx, bestDist (+ the SAD minima with with_sad=True)."""
     kpsL = np.ascontiguousarray(kpsL, np.float32)
     kpsR = np.ascontiguousarray(kpsR, np.float32)
     descL = np.ascontiguousarray(descL, np.uint8)
@@ -231,9 +246,12 @@ def stereo(kpsL, descL, kpsR, descR, sf, isf, pyrL, pyrR, mbf, fx):
     dep = np.empty(n, np.float32)
     bi = np.empty(n, np.int32)
     bd = np.empty(n, np.int32)
-    rc = lib().orbo_stereo(n, _p(kpsL), _p(descL), len(kpsR), _p(kpsR), _p(descR), L, _p(sf), _p(isf),
-                           C.cast(PL, C.c_void_p), C.cast(PR, C.c_void_p), _p(lw), _p(lh),
-                           float(mbf), float(np.float32(fx)), _p(uR), _p(dep), _p(bi), _p(bd))
+    sad = np.empty(n, np.int32)
+    rc = lib().orbo_stereo_ex(n, _p(kpsL), _p(descL), len(kpsR), _p(kpsR), _p(descR), L, _p(sf), _p(isf),
+                              C.cast(PL, C.c_void_p), C.cast(PR, C.c_void_p), _p(lw), _p(lh),
+                              float(mbf), float(np.float32(fx)), _p(uR), _p(dep), _p(bi), _p(bd), _p(sad))
     if rc != 0:
         raise IndexError("stereo oracle: a keypoint row/window leaves the pyramid view (the reference raises here)")
+    if with_sad:
+        return uR, dep, bi, bd, sad
     return uR, dep, bi, bd

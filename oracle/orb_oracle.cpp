@@ -415,10 +415,22 @@ void orbo_level_caster_view(void* h, int l, u8* out) {
 // kpsL/kpsR: [n][3] floats (x, y, octave).  pyrL/pyrR: per level pointer to the caster view (h_l x w_l).
 // Outputs: uRight/depth (-1 = no match), bestIdx (Hamming winner or -1 if bestDist >= 75), bestDist.
 // Returns 0, or -1 if a window would leave the view (the reference would raise there).
+int orbo_stereo_ex(int NL, const float* kpsL, const u8* descL, int NR, const float* kpsR, const u8* descR,
+                   int nlevels, const float* sf, const float* isf, const u8* const* pyrL, const u8* const* pyrR,
+                   const int* lw, const int* lh, double mbf, float fx,
+                   float* uRight, float* depth, int* bestIdx, int* bestDistOut, int* sadOut);
 int orbo_stereo(int NL, const float* kpsL, const u8* descL, int NR, const float* kpsR, const u8* descR,
                 int nlevels, const float* sf, const float* isf, const u8* const* pyrL, const u8* const* pyrR,
                 const int* lw, const int* lh, double mbf, float fx,
                 float* uRight, float* depth, int* bestIdx, int* bestDistOut) {
+    return orbo_stereo_ex(NL, kpsL, descL, NR, kpsR, descR, nlevels, sf, isf, pyrL, pyrR, lw, lh, mbf, fx, uRight, depth, bestIdx,
+                          bestDistOut, nullptr);
+}
+// sadOut (optional): the SAD minimum pushed to vDistIdx for accepted matches (Frame.py:279), -1 otherwise
+int orbo_stereo_ex(int NL, const float* kpsL, const u8* descL, int NR, const float* kpsR, const u8* descR,
+                   int nlevels, const float* sf, const float* isf, const u8* const* pyrL, const u8* const* pyrR,
+                   const int* lw, const int* lh, double mbf, float fx,
+                   float* uRight, float* depth, int* bestIdx, int* bestDistOut, int* sadOut) {
     const int nRows = lh[0];
     const float mbf32 = (float)mbf;
     const float mb = mbf32 / fx;       // Frame.py:43  (python float / np.float32 -> float32)
@@ -435,6 +447,7 @@ int orbo_stereo(int NL, const float* kpsL, const u8* descL, int NR, const float*
     int rc = 0;
     for (int iL = 0; iL < NL; ++iL) {
         uRight[iL] = -1.f; depth[iL] = -1.f;
+        if (sadOut) sadOut[iL] = -1;
         if (bestIdx) bestIdx[iL] = -1;
         if (bestDistOut) bestDistOut[iL] = 100;
         const float uL = kpsL[3 * iL], vL = kpsL[3 * iL + 1];
@@ -484,6 +497,7 @@ int orbo_stereo(int NL, const float* kpsL, const u8* descL, int NR, const float*
         float bestuR = sf[oL] * ((float)(sr + bestInc) + deltaR);
         float disparity = uL - bestuR;
         if (0 <= disparity && disparity < maxD) {
+            if (sadOut) sadOut[iL] = bestSad;
             if (disparity <= 0) {   // Frame.py:273-275 (python-float branch)
                 depth[iL] = (float)(mbf / 0.01);
                 uRight[iL] = (float)((double)uL - 0.01);

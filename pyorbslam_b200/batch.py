@@ -32,6 +32,10 @@ class StereoFrontend:
                 pass
             self._h = None
 
+    def set_stereo_options(self, median_cull=False, dense_pyramid=False):
+        """Opt-in upstream-ORB-SLAM2 behaviour (not the reference's): see B200ORB_STEREO_* in include/b200orb.h."""
+        _lib.check(_lib.lib().b200orb_batch_set_stereo_flags(self._h, (1 if median_cull else 0) | (2 if dense_pyramid else 0)))
+
     def workspace_bytes(self):
         return int(_lib.lib().b200orb_batch_workspace_bytes(self._h))
 

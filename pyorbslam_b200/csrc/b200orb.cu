@@ -288,7 +288,8 @@ struct Engine {
         CU_TRY(cudaGetLastError());
         return 0;
     }
-    void stereo_geom(StereoGeom& SG) const {
+    // flags: B200ORB_STEREO_DENSE_PYRAMID -> SAD windows on the true level image instead of the reference's sheared view
+    void stereo_geom(StereoGeom& SG, int flags = 0) const {
         const Plan& P = hp.P;
         memset(&SG, 0, sizeof(SG));
         SG.nlevels = P.nlevels;
@@ -300,6 +301,7 @@ struct Engine {
             SG.pitch[l] = G.pitch;
             SG.magic[l] = (unsigned)((0x100000000ULL + SG.plog[l] - 1) / SG.plog[l]);
             SG.off0[l] = ORB_EDGE * SG.plog[l] + ORB_EDGE;
+            SG.vstride[l] = (flags & B200ORB_STEREO_DENSE_PYRAMID) ? SG.plog[l] : G.w;
             SG.base[l] = G.pyr_ofs;
         }
     }
@@ -314,7 +316,7 @@ void fill_stereo_consts(StereoArgs& A, double mbf, float fx) {
 
 // row index of the right keypoints, then the matcher.  A.rowStart / A.sorted / A.idx_stride must point at
 // (nRows + 1) and idx_stride ints per pair of scratch.
-int launch_stereo(const StereoGeom& SG, StereoArgs A, int max_left, int pairs, cudaStream_t st) {
+int launch_stereo(const StereoGeom& SG, StereoArgs A, int max_left, int pairs, cudaStream_t st, int flags = 0) {
     if (pairs < 1 || max_left < 1) return 0;
     float smax = 1.f;
     for (int l = 0; l < SG.nlevels; ++l) smax = std::max(smax, SG.sf[l]);
@@ -326,6 +328,11 @@ int launch_stereo(const StereoGeom& SG, StereoArgs A, int max_left, int pairs, c
     dim3 grid((max_left + ST_WARPS - 1) / ST_WARPS, pairs);
     k_stereo<<<grid, ST_WARPS * 32, 0, st>>>(SG, A);
     ++g_launches;
+    if (flags & B200ORB_STEREO_MEDIAN_CULL) {
+        if (!A.sadDist) return fail(B200ORB_E_ARG, "median cull needs a sadDist buffer");
+        k_median_cull<<<pairs, MC_THREADS, 0, st>>>(A.nL, A.n_stride, A.out_stride, A.sadDist, A.uRight, A.depth);
+        ++g_launches;
+    }
     CU_TRY(cudaGetLastError());
     return 0;
 }
@@ -340,7 +347,7 @@ struct b200orb_extractor {
     cudaStream_t st = nullptr;
     u8* d_img = nullptr; size_t img_cap = 0;
     float* d_kps = nullptr; u8* d_desc = nullptr; int* d_nkp = nullptr;
-    float *d_uR = nullptr, *d_depth = nullptr; int* d_match = nullptr;
+    float *d_uR = nullptr, *d_depth = nullptr; int *d_match = nullptr, *d_sad = nullptr;
     int out_cap = 0;
     int n = -1;          // keypoints of the last call, -1 = none yet
     bool empty_last = false;
@@ -357,6 +364,8 @@ struct b200orb_batch {
     float* d_uR[2] = {nullptr, nullptr}; float* d_dep[2] = {nullptr, nullptr}; int* d_mi[2] = {nullptr, nullptr};
     bool host_ready = false;
     long long host_bytes = 0;
+    int stereo_flags = 0;
+    int* d_sad = nullptr;     // [P][C], only with the median cull
     // per-kernel timing (b200orb_batch_profile): a pool of event sets, one set per run_device call
     std::vector<cudaEvent_t> prof_ev;
     std::vector<int> prof_pairs;
@@ -393,7 +402,7 @@ void b200orb_extractor_destroy(b200orb_extractor* e) {
         cudaSetDevice(e->eng.device);
         e->eng.release();
         cudaFree(e->d_img); cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_nkp);
-        cudaFree(e->d_uR); cudaFree(e->d_depth); cudaFree(e->d_match);
+        cudaFree(e->d_uR); cudaFree(e->d_depth); cudaFree(e->d_match); cudaFree(e->d_sad);
         if (e->st) cudaStreamDestroy(e->st);
     }
     delete e;
@@ -430,14 +439,15 @@ int b200orb_extract(b200orb_extractor* e, const uint8_t* image, int H, int W, in
         e->img_cap = (size_t)H * W;
     }
     if (e->out_cap != P.kp_total) {
-        cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_nkp); cudaFree(e->d_uR); cudaFree(e->d_depth); cudaFree(e->d_match);
-        e->d_kps = nullptr; e->d_desc = nullptr; e->d_nkp = nullptr; e->d_uR = e->d_depth = nullptr; e->d_match = nullptr;
+        cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_nkp); cudaFree(e->d_uR); cudaFree(e->d_depth); cudaFree(e->d_match); cudaFree(e->d_sad);
+        e->d_kps = nullptr; e->d_desc = nullptr; e->d_nkp = nullptr; e->d_uR = e->d_depth = nullptr; e->d_match = nullptr; e->d_sad = nullptr;
         CU_TRY(cudaMalloc((void**)&e->d_kps, (size_t)P.kp_total * 6 * 4));
         CU_TRY(cudaMalloc((void**)&e->d_desc, (size_t)P.kp_total * 32));
         CU_TRY(cudaMalloc((void**)&e->d_nkp, 4));
         CU_TRY(cudaMalloc((void**)&e->d_uR, (size_t)P.kp_total * 4));
         CU_TRY(cudaMalloc((void**)&e->d_depth, (size_t)P.kp_total * 4));
         CU_TRY(cudaMalloc((void**)&e->d_match, (size_t)P.kp_total * 4));
+        CU_TRY(cudaMalloc((void**)&e->d_sad, (size_t)P.kp_total * 4));
         e->out_cap = P.kp_total;
     }
     CU_TRY(cudaMemcpyAsync(e->d_img, image, (size_t)H * W, cudaMemcpyHostToDevice, e->st));
@@ -527,6 +537,11 @@ int b200orb_get_level_candidates(b200orb_extractor* e, int level, int cap, int* 
 }
 
 int b200orb_stereo(b200orb_extractor* L, b200orb_extractor* R, double mbf, float fx, float* uRight, float* depth, int* matchIdx) {
+    return b200orb_stereo_ex(L, R, mbf, fx, 0, uRight, depth, matchIdx, nullptr);
+}
+
+int b200orb_stereo_ex(b200orb_extractor* L, b200orb_extractor* R, double mbf, float fx, int flags, float* uRight, float* depth, int* matchIdx,
+                      int* sadDist) {
     if (!L || !R || !uRight || !depth) return fail(B200ORB_E_ARG, "NULL argument");
     if (L->n < 0 || R->n < 0) return fail(B200ORB_E_STATE, "both extractors need an extract() call first");
     if (L->n == 0) return 0;
@@ -540,22 +555,23 @@ int b200orb_stereo(b200orb_extractor* L, b200orb_extractor* R, double mbf, float
         return fail(B200ORB_E_ARG, "left and right extractors have different geometry");
     CU_TRY(cudaSetDevice(L->eng.device));
     StereoGeom SG;
-    L->eng.stereo_geom(SG);
+    L->eng.stereo_geom(SG, flags);
     StereoArgs A;
     memset(&A, 0, sizeof(A));
     A.kpsL = L->d_kps; A.descL = L->d_desc; A.nL = L->d_nkp;
     A.kpsR = R->d_kps; A.descR = R->d_desc; A.nR = R->d_nkp;
     A.pyrL = L->eng.d_pyr; A.pyrR = R->eng.d_pyr;
     A.kp_row = 6; A.oct_idx = 5; A.out_stride = PL.kp_total;
-    A.uRight = L->d_uR; A.depth = L->d_depth; A.matchIdx = L->d_match; A.status = L->eng.d_status;
+    A.uRight = L->d_uR; A.depth = L->d_depth; A.matchIdx = L->d_match; A.status = L->eng.d_status; A.sadDist = L->d_sad;
     A.rowStart = L->eng.d_rowstart; A.sorted = L->eng.d_sorted; A.idx_stride = PL.kp_total;
     fill_stereo_consts(A, mbf, fx);
     CU_TRY(cudaMemsetAsync(L->eng.d_status, 0, 4, L->st));
-    TRY(launch_stereo(SG, A, L->n, 1, L->st));
+    TRY(launch_stereo(SG, A, L->n, 1, L->st, flags));
     int status = 0;
     CU_TRY(cudaMemcpyAsync(uRight, L->d_uR, (size_t)L->n * 4, cudaMemcpyDeviceToHost, L->st));
     CU_TRY(cudaMemcpyAsync(depth, L->d_depth, (size_t)L->n * 4, cudaMemcpyDeviceToHost, L->st));
     if (matchIdx) CU_TRY(cudaMemcpyAsync(matchIdx, L->d_match, (size_t)L->n * 4, cudaMemcpyDeviceToHost, L->st));
+    if (sadDist) CU_TRY(cudaMemcpyAsync(sadDist, L->d_sad, (size_t)L->n * 4, cudaMemcpyDeviceToHost, L->st));
     CU_TRY(cudaMemcpyAsync(&status, L->eng.d_status, 4, cudaMemcpyDeviceToHost, L->st));
     CU_TRY(cudaStreamSynchronize(L->st));
     if (status) return fail(B200ORB_E_RANGE, "a SAD window leaves the pyramid view (the reference raises IndexError/ValueError here)");
@@ -577,7 +593,7 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     long long total = 0;
     for (int l = 0; l < nlevels; ++l) {
         SG.sf[l] = sf[l]; SG.isf[l] = isf[l]; SG.w[l] = lw[l]; SG.h[l] = lh[l];
-        SG.plog[l] = lw[l]; SG.pitch[l] = lw[l]; SG.off0[l] = 0; SG.base[l] = total;
+        SG.plog[l] = lw[l]; SG.pitch[l] = lw[l]; SG.off0[l] = 0; SG.base[l] = total; SG.vstride[l] = lw[l];
         SG.magic[l] = lw[l] > 1 ? (unsigned)((0x100000000ULL + lw[l] - 1) / lw[l]) : 0xffffffffu;
         total += ((long long)lw[l] * lh[l] + 255) & ~255LL;
     }
@@ -661,6 +677,7 @@ void b200orb_batch_destroy(b200orb_batch* b) {
     cudaSetDevice(b->eng.device);
     b->eng.release();
     for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
+    cudaFree(b->d_sad);
     for (int i = 0; i < 2; ++i) {
         cudaFree(b->d_in[i]); cudaFree(b->d_kps[i]); cudaFree(b->d_desc[i]); cudaFree(b->d_nkp[i]);
         cudaFree(b->d_uR[i]); cudaFree(b->d_dep[i]); cudaFree(b->d_mi[i]);
@@ -696,7 +713,7 @@ int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint
     }
     TRY(b->eng.extract(d_left, d_right, n_pairs, 2 * n_pairs, d_kps, d_desc, d_nkp, st, evs));
     StereoGeom SG;
-    b->eng.stereo_geom(SG);
+    b->eng.stereo_geom(SG, b->stereo_flags);
     StereoArgs A;
     memset(&A, 0, sizeof(A));
     A.kpsL = d_kps; A.kpsR = d_kps + (size_t)n_pairs * C * 6;
@@ -708,8 +725,19 @@ int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint
     A.uRight = d_uRight; A.depth = d_depth; A.matchIdx = d_matchIdx; A.status = b->eng.d_status;
     A.rowStart = b->eng.d_rowstart; A.sorted = b->eng.d_sorted; A.idx_stride = (int)C;
     fill_stereo_consts(A, mbf, fx);
-    TRY(launch_stereo(SG, A, (int)C, n_pairs, st));
+    if (b->stereo_flags & B200ORB_STEREO_MEDIAN_CULL) {
+        if (!b->d_sad) CU_TRY(cudaMalloc((void**)&b->d_sad, (size_t)b->P * C * 4));
+        A.sadDist = b->d_sad;
+    }
+    TRY(launch_stereo(SG, A, (int)C, n_pairs, st, b->stereo_flags));
     if (evs) CU_TRY(cudaEventRecord(evs[B200ORB_NSTAGE], st));
+    return 0;
+}
+
+int b200orb_batch_set_stereo_flags(b200orb_batch* b, int flags) {
+    if (!b) return fail(B200ORB_E_ARG, "NULL batch");
+    if (flags & ~(B200ORB_STEREO_MEDIAN_CULL | B200ORB_STEREO_DENSE_PYRAMID)) return fail(B200ORB_E_ARG, "unknown stereo flag");
+    b->stereo_flags = flags;
     return 0;
 }
 

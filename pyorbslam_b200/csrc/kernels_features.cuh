@@ -232,10 +232,11 @@ struct StereoArgs {
     float mbf32, mb, maxD;
     double mbf;
     float* uRight; float* depth; int* matchIdx; int* status;
+    int* sadDist;                                           // optional: SAD minimum of accepted matches, -1 otherwise
 };
 
 __device__ __forceinline__ const u8* view_ptr(const u8* base, const StereoGeom& SG, int o, int row, int col) {
-    const int lin = SG.off0[o] + row * SG.w[o] + col;
+    const int lin = SG.off0[o] + row * SG.vstride[o] + col;
     int pr = (int)__umulhi((unsigned)lin, SG.magic[o]);           // lin / plog via ceil(2^32 / plog); may overshoot by one
     if (pr * SG.plog[o] > lin) --pr;
     return base + SG.base[o] + (size_t)pr * SG.pitch[o] + (lin - pr * SG.plog[o]);
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo(const __grid_constant_
         const int bestDist = best >> 20, bestR = best & 0xfffff;
         const size_t oi = (size_t)pair * A.out_stride + iL;
         float outU = -1.f, outD = -1.f;
-        int outM = -1;
+        int outM = -1, outS = -1;
         if (bestDist < 75) {    // thOrbDist = (TH_HIGH + TH_LOW) / 2, Frame.py:166,222
             outM = bestR;
             const float uR0 = kR[(size_t)bestR * A.kp_row];
@@ -334,6 +335,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo(const __grid_constant_
                         const float bestuR = SG.sf[oL] * ((float)(sr + bestInc - 5) + deltaR);   // Frame.py:269
                         const float disparity = uL - bestuR;
                         if (0.f <= disparity && disparity < A.maxD) {                    // Frame.py:272
+                            outS = bestSad;                                              // vDistIdx.append((bestDist, iL)), :279
                             if (disparity <= 0.f) {                                      // python-float branch, :273-275
                                 outD = (float)(A.mbf / 0.01);
                                 outU = (float)((double)uL - 0.01);
@@ -350,6 +352,62 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo(const __grid_constant_
             A.uRight[oi] = outU;
             A.depth[oi] = outD;
             if (A.matchIdx) A.matchIdx[oi] = outM;
+            if (A.sadDist) A.sadDist[oi] = outS;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Optional extension (NOT in the reference, whose vDistIdx is dead code -- SURVEY.md F7): upstream ORB-SLAM2's
+// median-distance outlier cull at the end of ComputeStereoMatches: with the accepted matches' SAD minima sorted,
+// median = element [n / 2], thDist = 1.5f * 1.4f * median, every match with dist >= thDist is dropped.
+// One CTA per pair; the median is found by a two-level counting select on the integer SAD values (<= 61 710).
+// ------------------------------------------------------------------------------------------------
+#define MC_THREADS 256
+__global__ void __launch_bounds__(MC_THREADS) k_median_cull(const int* __restrict__ nL, int n_stride, int out_stride,
+                                                            const int* __restrict__ sadDist, float* __restrict__ uRight,
+                                                            float* __restrict__ depth) {
+    __shared__ int hist[256];
+    __shared__ int sel[3];     // [0] matches, [1] selected high byte, [2] rank inside it
+    const int pair = blockIdx.x, n = nL[(size_t)pair * n_stride];
+    const int* sd = sadDist + (size_t)pair * out_stride;
+    for (int i = threadIdx.x; i < 256; i += MC_THREADS) hist[i] = 0;
+    if (threadIdx.x == 0) sel[0] = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < n; i += MC_THREADS) {
+        const int d = sd[i];
+        if (d >= 0) { atomicAdd(&hist[min(d >> 8, 255)], 1); ++mine; }
+    }
+    atomicAdd(&sel[0], mine);
+    __syncthreads();
+    const int m = sel[0];
+    if (m == 0) return;
+    if (threadIdx.x == 0) {
+        int rank = m / 2, b = 0;
+        while (rank >= hist[b]) { rank -= hist[b]; ++b; }
+        sel[1] = b; sel[2] = rank;
+    }
+    __syncthreads();
+    const int hb = sel[1];
+    const int rank = sel[2];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += MC_THREADS) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += MC_THREADS) {
+        const int d = sd[i];
+        if (d >= 0 && min(d >> 8, 255) == hb) atomicAdd(&hist[d & 255], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int r = rank, b = 0;
+        while (r >= hist[b]) { r -= hist[b]; ++b; }
+        sel[1] = (hb << 8) | b;
+    }
+    __syncthreads();
+    const float thDist = (1.5f * 1.4f) * (float)sel[1];
+    for (int i = threadIdx.x; i < n; i += MC_THREADS) {
+        const int d = sd[i];
+        if (d >= 0 && !((float)d < thDist)) { uRight[(size_t)pair * out_stride + i] = -1.f; depth[(size_t)pair * out_stride + i] = -1.f; }
     }
 }

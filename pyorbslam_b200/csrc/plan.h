@@ -52,6 +52,7 @@ struct StereoGeom {
     unsigned magic[ORB_MAX_LEVELS];   // ceil(2^32 / plog): division by plog as multiply-high + one correction
     int pitch[ORB_MAX_LEVELS];   // physical pitch
     int off0[ORB_MAX_LEVELS];    // logical linear offset of view element (0,0): 19*plog+19 resident, 0 uploaded
+    int vstride[ORB_MAX_LEVELS]; // logical offset between view rows: w for the reference's sheared caster view, plog for the true image
     long long base[ORB_MAX_LEVELS];  // byte offset of the level inside one image's blob
     int nRows;                   // rows of level 0 (Frame.py:167)
 };

@@ -24,14 +24,22 @@ def _to_lists(uR, dep):
     return u, d
 
 
-def stereo_resident(extL, extR, mbf, fx):
+MEDIAN_CULL = 1      # B200ORB_STEREO_MEDIAN_CULL   -- upstream ORB-SLAM2 behaviour, NOT the reference's
+DENSE_PYRAMID = 2    # B200ORB_STEREO_DENSE_PYRAMID -- true level images instead of the reference's sheared view (F6)
+OPTIONS = {"flags": 0}   # what the installed Frame.compute_stereo_matches uses; 0 = exactly the reference
+
+
+def stereo_resident(extL, extR, mbf, fx, flags=0, with_sad=False):
     n = extL._last_n
     uR = np.empty(max(n, 0), np.float32)
     dep = np.empty(max(n, 0), np.float32)
     mi = np.empty(max(n, 0), np.int32)
+    sad = np.empty(max(n, 0), np.int32)
     if n > 0:
-        _lib.check(_lib.lib().b200orb_stereo(extL._h, extR._h, float(mbf), float(np.float32(fx)),
-                                             uR.ctypes.data, dep.ctypes.data, mi.ctypes.data))
+        _lib.check(_lib.lib().b200orb_stereo_ex(extL._h, extR._h, float(mbf), float(np.float32(fx)), int(flags),
+                                                uR.ctypes.data, dep.ctypes.data, mi.ctypes.data, sad.ctypes.data))
+    if with_sad:
+        return uR, dep, mi, sad
     return uR, dep, mi
 
 
@@ -70,7 +78,7 @@ def compute_stereo_matches(self):
                 and getattr(self, "mDescriptorsRight", None) is extR._last_desc
                 and extL._last_n == self.N)
     if resident:
-        uR, dep, _ = stereo_resident(extL, extR, self.mbf, fx)
+        uR, dep, _ = stereo_resident(extL, extR, self.mbf, fx, flags=OPTIONS["flags"])
     else:
         kL = np.array([[k.pt[0], k.pt[1], k.octave] for k in self.mvKeys], np.float32).reshape(-1, 3)
         kR = np.array([[k.pt[0], k.pt[1], k.octave] for k in self.mvKeysRight], np.float32).reshape(-1, 3)
@@ -80,8 +88,11 @@ def compute_stereo_matches(self):
     self.mvuRight, self.mvDepth = _to_lists(uR, dep)
 
 
-def install(frame_cls):
-    """Frame.compute_stereo_matches = the GPU matcher.  Returns the original method (to restore / compare)."""
+def install(frame_cls, median_cull=False, dense_pyramid=False):
+    """Frame.compute_stereo_matches = the GPU matcher.  Returns the original method (to restore / compare).
+    The two keyword options switch on upstream-ORB-SLAM2 behaviour the reference does not have (device-resident path
+    only); leave them off for parity with the reference."""
+    OPTIONS["flags"] = (MEDIAN_CULL if median_cull else 0) | (DENSE_PYRAMID if dense_pyramid else 0)
     original = frame_cls.compute_stereo_matches
     frame_cls.compute_stereo_matches = compute_stereo_matches
     return original

@@ -153,6 +153,16 @@ def test_extractor_vs_oracle_seeded(case):
     _same(kg, dg, ko, do)
 
 
+@pytest.mark.parametrize("ini,mn", [(5, 20), (10, 0), (0, 0), (300, -5), (40, 39), (7, 7)])
+def test_threshold_schedule_edge_cases_vs_oracle(ini, mn):
+    """iniThFAST below / equal to / far above minThFAST, zero and out-of-range thresholds (cv::FAST clamps to [0, 255])."""
+    img = make_stereo_pair(13, 200, 400)[0]
+    params = (400, 1.2, 4, ini, mn)
+    kg, dg = ORBextractor(*params).extract_arrays(img)
+    ko, do = O.OracleExtractor(*params).extract_arrays(img)
+    _same(kg, dg, ko, do)
+
+
 def test_stage_by_stage_vs_oracle():
     img = make_stereo_pair(2)[0]
     g, o = ORBextractor(*KITTI), O.OracleExtractor(*KITTI)
@@ -319,3 +329,45 @@ def test_device_fast_score_unit_harness():
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
     lines = [l for l in out.splitlines() if "bad" in l]
     assert len(lines) == 3 and all(" bad 0 " in l for l in lines), out
+
+
+def test_opt_in_upstream_options_median_cull_and_dense_pyramid():
+    """Extensions that the reference does NOT have (parity unpinned by the reference -- checked
+    against the oracle's restatement of upstream ORB-SLAM2's cull, and against the oracle fed true level images)."""
+    import torch
+    from pyorbslam_b200 import StereoFrontend
+    from pyorbslam_b200.stereo import DENSE_PYRAMID, MEDIAN_CULL
+    L, R = make_stereo_pair(0)
+    gL, gR = ORBextractor(*KITTI), ORBextractor(*KITTI)
+    kL, dL = gL.extract_arrays(L)
+    kR, dR = gR.extract_arrays(R)
+    oL, oR = O.OracleExtractor(*KITTI), O.OracleExtractor(*KITTI)
+    oL.extract_arrays(L)
+    oR.extract_arrays(R)
+    args = (kL[:, [0, 1, 5]], dL, kR[:, [0, 1, 5]], dR, oL.sf, oL.isf)
+    # flags = 0 with sadDist: same matches as the plain call, SAD minima equal the oracle's
+    u0, d0, m0, s0 = stereo_resident(gL, gR, 386.1448, 718.856, flags=0, with_sad=True)
+    ou, od, oi, _, osad = O.stereo(*args, oL.GetImagePyramid(), oR.GetImagePyramid(), 386.1448, 718.856, with_sad=True)
+    assert np.array_equal(u0.view(np.uint32), ou.view(np.uint32)) and np.array_equal(s0, osad)
+    # median cull
+    u1, d1, m1 = stereo_resident(gL, gR, 386.1448, 718.856, flags=MEDIAN_CULL)
+    cu, cd = O.median_cull(ou, od, osad)
+    assert np.array_equal(u1.view(np.uint32), cu.view(np.uint32)) and np.array_equal(d1.view(np.uint32), cd.view(np.uint32))
+    assert 0 < (u1 >= 0).sum() < (u0 >= 0).sum()
+    # dense (un-sheared) pyramid: oracle on the true level images
+    trueL = [oL.level_bordered(l)[19:-19, 19:-19] for l in range(8)]
+    trueR = [oR.level_bordered(l)[19:-19, 19:-19] for l in range(8)]
+    u2, d2, m2 = stereo_resident(gL, gR, 386.1448, 718.856, flags=DENSE_PYRAMID)
+    du, dd, di, _ = O.stereo(*args, trueL, trueR, 386.1448, 718.856)
+    assert np.array_equal(u2.view(np.uint32), du.view(np.uint32)) and np.array_equal(m2, di)
+    assert (u2 >= 0).sum() >= (u0 >= 0).sum()       # the true image can only help the SAD refinement
+    # both, through the batch API
+    fe = StereoFrontend(*KITTI, 376, 1241, 2)
+    fe.set_stereo_options(median_cull=True, dense_pyramid=True)
+    out = fe.run(torch.from_numpy(np.stack([L, L])).cuda(), torch.from_numpy(np.stack([R, R])).cuda(), 386.1448, 718.856)
+    torch.cuda.synchronize()
+    _, _, _, _, dsad = O.stereo(*args, trueL, trueR, 386.1448, 718.856, with_sad=True)
+    bu, bd = O.median_cull(du, dd, dsad)
+    n = len(kL)
+    assert np.array_equal(out["uRight"][1, :n].cpu().numpy().view(np.uint32), bu.view(np.uint32))
+    assert np.array_equal(out["depth"][0, :n].cpu().numpy().view(np.uint32), bd.view(np.uint32))

@@ -76,3 +76,15 @@ def test_stereo_identical_views_match_themselves():
     disp = k[ok, 0] - uR[ok]
     assert (disp > 0).all() and (disp <= e.sf[k[ok, 5].astype(int)] + 0.011).all()
     assert np.allclose(dep[ok], np.float32(100.0) / disp, rtol=1e-4)
+
+
+def test_median_cull_restatement_semantics():
+    # upstream ORB-SLAM2: sorted SAD minima, median = element [n // 2], thDist = 1.5f * 1.4f * median, drop dist >= thDist
+    sad = np.array([-1, 10, 40, 20, -1, 30, 100, 63, 62], np.int32)
+    u = np.arange(9, dtype=np.float32) + 1
+    d = u * 2
+    cu, cd = O.median_cull(u, d, sad)
+    # accepted = [10, 20, 30, 40, 62, 63, 100] -> median = 40 -> thDist = 2.1f * 40 = 84 -> only 100 is dropped
+    assert cu.tolist() == [1, 2, 3, 4, 5, 6, -1, 8, 9] and cd[6] == -1
+    cu, _ = O.median_cull(u, d, np.full(9, -1, np.int32))
+    assert np.array_equal(cu, u)
