@@ -203,13 +203,14 @@ struct Engine {
     u8 *d_pyr = nullptr, *d_blur = nullptr;
     u32 *d_cand = nullptr, *d_scratch = nullptr, *d_lvlkp = nullptr;
     int *d_cellcnt = nullptr, *d_lvlcnt = nullptr, *d_status = nullptr, *d_rowstart = nullptr, *d_sorted = nullptr;
+    int2* d_rmeta = nullptr;
     XTab* d_xtab = nullptr;
     YTab* d_ytab = nullptr;
     long long bytes = 0;
 
     void release() {
         cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_cand); cudaFree(d_scratch); cudaFree(d_lvlkp);
-        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_sorted);
+        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_sorted); cudaFree(d_rmeta); d_rmeta = nullptr;
         d_pyr = d_blur = nullptr; d_cand = d_scratch = d_lvlkp = nullptr; d_cellcnt = d_lvlcnt = d_status = d_rowstart = d_sorted = nullptr;
         d_xtab = nullptr; d_ytab = nullptr; planned = false; bytes = 0;
     }
@@ -235,6 +236,7 @@ struct Engine {
         TRY(alloc(&d_status, 1));
         TRY(alloc(&d_rowstart, (size_t)S * (P.lv[0].h + 1)));
         TRY(alloc(&d_sorted, (size_t)S * P.kp_total));
+        TRY(alloc(&d_rmeta, (size_t)S * P.kp_total));
         TRY(alloc(&d_xtab, hp.xtab.size()));
         TRY(alloc(&d_ytab, hp.ytab.size()));
         CU_TRY(cudaMemset(d_pyr, 0, (size_t)S * P.pyr_bytes));
@@ -322,8 +324,8 @@ int launch_stereo(const StereoGeom& SG, StereoArgs A, int max_left, int pairs, c
     for (int l = 0; l < SG.nlevels; ++l) smax = std::max(smax, SG.sf[l]);
     A.reach = (int)ceil(2.0 * smax) + 2;
     const size_t smem = (size_t)(2 * SG.nRows + 1) * sizeof(int);
-    k_rowindex<<<pairs, RI_THREADS, smem, st>>>(A.kpsR, A.nR, A.kp_stride, A.n_stride, A.kp_row, SG.nRows, (int*)A.rowStart, (int*)A.sorted,
-                                                A.idx_stride, A.status);
+    k_rowindex<<<pairs, RI_THREADS, smem, st>>>(A.kpsR, A.nR, A.kp_stride, A.n_stride, A.kp_row, A.oct_idx, SG, (int*)A.rowStart,
+                                                (int*)A.sorted, (int2*)A.rmeta, A.idx_stride, A.status);
     ++g_launches;
     dim3 grid((max_left + ST_WARPS - 1) / ST_WARPS, pairs);
     k_stereo<<<grid, ST_WARPS * 32, 0, st>>>(SG, A);
@@ -563,7 +565,7 @@ int b200orb_stereo_ex(b200orb_extractor* L, b200orb_extractor* R, double mbf, fl
     A.pyrL = L->eng.d_pyr; A.pyrR = R->eng.d_pyr;
     A.kp_row = 6; A.oct_idx = 5; A.out_stride = PL.kp_total;
     A.uRight = L->d_uR; A.depth = L->d_depth; A.matchIdx = L->d_match; A.status = L->eng.d_status; A.sadDist = L->d_sad;
-    A.rowStart = L->eng.d_rowstart; A.sorted = L->eng.d_sorted; A.idx_stride = PL.kp_total;
+    A.rowStart = L->eng.d_rowstart; A.sorted = L->eng.d_sorted; A.rmeta = L->eng.d_rmeta; A.idx_stride = PL.kp_total;
     fill_stereo_consts(A, mbf, fx);
     CU_TRY(cudaMemsetAsync(L->eng.d_status, 0, 4, L->st));
     TRY(launch_stereo(SG, A, L->n, 1, L->st, flags));
@@ -612,8 +614,9 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     u8 *d_blob = nullptr, *d_dL = nullptr, *d_dR = nullptr;
     float *d_kL = nullptr, *d_kR = nullptr, *d_u = nullptr, *d_d = nullptr;
     int *d_m = nullptr, *d_n = nullptr, *d_rs = nullptr, *d_so = nullptr;
+    int2* d_rm = nullptr;
     int rc = 0;
-    auto cleanup = [&]() { cudaFree(d_blob); cudaFree(d_dL); cudaFree(d_dR); cudaFree(d_kL); cudaFree(d_kR); cudaFree(d_u); cudaFree(d_d); cudaFree(d_m); cudaFree(d_n); cudaFree(d_rs); cudaFree(d_so); };
+    auto cleanup = [&]() { cudaFree(d_blob); cudaFree(d_dL); cudaFree(d_dR); cudaFree(d_kL); cudaFree(d_kR); cudaFree(d_u); cudaFree(d_d); cudaFree(d_m); cudaFree(d_n); cudaFree(d_rs); cudaFree(d_so); cudaFree(d_rm); };
 #define CU_TRY2(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(B200ORB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
     CU_TRY2(cudaMalloc((void**)&d_blob, (size_t)total * 2));
     CU_TRY2(cudaMalloc((void**)&d_kL, (size_t)nLeft * 12));
@@ -626,6 +629,7 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     CU_TRY2(cudaMalloc((void**)&d_n, 12));
     CU_TRY2(cudaMalloc((void**)&d_rs, (size_t)(lh[0] + 1) * 4));
     CU_TRY2(cudaMalloc((void**)&d_so, (size_t)std::max(nRight, 1) * 4));
+    CU_TRY2(cudaMalloc((void**)&d_rm, (size_t)std::max(nRight, 1) * 8));
     for (int l = 0; l < nlevels; ++l) {
         CU_TRY2(cudaMemcpy(d_blob + SG.base[l], pyrL[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice));
         CU_TRY2(cudaMemcpy(d_blob + total + SG.base[l], pyrR[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice));
@@ -644,7 +648,7 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     A.pyrL = d_blob; A.pyrR = d_blob + total;
     A.kp_row = 3; A.oct_idx = 2; A.out_stride = nLeft;
     A.uRight = d_u; A.depth = d_d; A.matchIdx = d_m; A.status = d_n + 2;
-    A.rowStart = d_rs; A.sorted = d_so; A.idx_stride = std::max(nRight, 1);
+    A.rowStart = d_rs; A.sorted = d_so; A.rmeta = d_rm; A.idx_stride = std::max(nRight, 1);
     fill_stereo_consts(A, mbf, fx);
     rc = launch_stereo(SG, A, nLeft, 1, nullptr);
     if (rc) { cleanup(); return rc; }
@@ -723,7 +727,7 @@ int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint
     A.kp_stride = (long long)C * 6; A.desc_stride = (long long)C * 32; A.pyr_stride = P.pyr_bytes;
     A.kp_row = 6; A.oct_idx = 5; A.out_stride = (int)C;
     A.uRight = d_uRight; A.depth = d_depth; A.matchIdx = d_matchIdx; A.status = b->eng.d_status;
-    A.rowStart = b->eng.d_rowstart; A.sorted = b->eng.d_sorted; A.idx_stride = (int)C;
+    A.rowStart = b->eng.d_rowstart; A.sorted = b->eng.d_sorted; A.rmeta = b->eng.d_rmeta; A.idx_stride = (int)C;
     fill_stereo_consts(A, mbf, fx);
     if (b->stereo_flags & B200ORB_STEREO_MEDIAN_CULL) {
         if (!b->d_sad) CU_TRY(cudaMalloc((void**)&b->d_sad, (size_t)b->P * C * 4));

@@ -161,9 +161,13 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
 // One CTA per right image.
 // ------------------------------------------------------------------------------------------------
 #define RI_THREADS 256
+// It also writes, per right keypoint, the 8 bytes the matcher needs: uR and minr | maxr << 12 | octave << 24, where
+// minr = floor(y - 2s), maxr = ceil(y + 2s) are evaluated in double exactly like Frame.py:173-176.
 __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict__ kpsR, const int* __restrict__ nR, long long kp_stride,
-                                                         int n_stride, int kp_row, int nRows, int* __restrict__ rowStart,
-                                                         int* __restrict__ sorted, int idx_stride, int* __restrict__ status) {
+                                                         int n_stride, int kp_row, int oct_idx, const __grid_constant__ StereoGeom SG,
+                                                         int* __restrict__ rowStart, int* __restrict__ sorted, int2* __restrict__ rmeta,
+                                                         int idx_stride, int* __restrict__ status) {
+    const int nRows = SG.nRows;
     extern __shared__ int ri_hist[];     // nRows + 1 counters, then nRows cursors
     __shared__ int ri_tmp[RI_THREADS / 32 + 1];
     const int pair = blockIdx.x;
@@ -171,6 +175,7 @@ __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict
     const float* k = kpsR + (size_t)pair * kp_stride;
     int* rs = rowStart + (size_t)pair * (nRows + 1);
     int* so = sorted + (size_t)pair * idx_stride;
+    int2* rm = rmeta + (size_t)pair * idx_stride;
     int* cursor = ri_hist + nRows + 1;
     for (int i = threadIdx.x; i <= nRows; i += RI_THREADS) ri_hist[i] = 0;
     __syncthreads();
@@ -200,7 +205,12 @@ __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict
     for (int i = threadIdx.x; i <= nRows; i += RI_THREADS) { rs[i] = ri_hist[i]; if (i < nRows) cursor[i] = ri_hist[i]; }
     __syncthreads();
     for (int j = threadIdx.x; j < n; j += RI_THREADS) {
-        const int row = (int)k[(size_t)j * kp_row + 1];
+        const float* r = k + (size_t)j * kp_row;
+        const int row = (int)r[1];
+        const int o = min(max((int)r[oct_idx], 0), SG.nlevels - 1);
+        const double y = (double)r[1], reach = 2.0 * (double)SG.sf[o];
+        const int minr = min(max((int)floor(y - reach), 0), 4095), maxr = min(max((int)ceil(y + reach), 0), 4095);
+        rm[j] = make_int2(__float_as_int(r[0]), minr | (maxr << 12) | (o << 24));
         if (row < 0 || row >= nRows) continue;
         so[atomicAdd(&cursor[row], 1)] = j;
     }
@@ -227,7 +237,7 @@ struct StereoArgs {
     int n_stride;                                           // stride of nL / nR between pairs (ints)
     int kp_row, oct_idx;                                    // floats per keypoint row, index of the octave
     int out_stride;                                         // rows per pair in the outputs
-    const int* rowStart; const int* sorted; int idx_stride; // row index of the right keypoints (k_rowindex)
+    const int* rowStart; const int* sorted; const int2* rmeta; int idx_stride; // row index + metadata of the right keypoints (k_rowindex)
     int reach;                                              // bins to visit on each side of the left keypoint's row
     float mbf32, mb, maxD;
     double mbf;
@@ -267,13 +277,13 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo(const __grid_constant_
         const uint4* dl = reinterpret_cast<const uint4*>(dL + (size_t)iL * 32);
         const uint4 l0 = dl[0], l1 = dl[1];
         const int c0 = rs[max(row - A.reach, 0)], c1 = rs[min(row + A.reach + 1, SG.nRows)];
+        const int2* rm = A.rmeta + (size_t)pair * A.idx_stride;
         for (int c = c0 + lane; c < c1; c += 32) {
             const int j = so[c];
-            const float* r = kR + (size_t)j * A.kp_row;
-            const float uR = r[0];
-            const int oR = (int)r[A.oct_idx];
-            const double y = (double)r[1], reach = 2.0 * (double)SG.sf[oR];
-            if (row < (int)floor(y - reach) || row > (int)ceil(y + reach) || oR < oL - 1 || oR > oL + 1 || !(minU <= uR) || !(uR <= uL)) continue;
+            const int2 m = rm[j];
+            const float uR = __int_as_float(m.x);
+            const int oR = m.y >> 24, minr = m.y & 0xfff, maxr = (m.y >> 12) & 0xfff;
+            if (row < minr || row > maxr || oR < oL - 1 || oR > oL + 1 || !(minU <= uR) || !(uR <= uL)) continue;
             const uint4* dr = reinterpret_cast<const uint4*>(dR + (size_t)j * 32);
             const uint4 r0 = __ldg(dr), r1 = __ldg(dr + 1);
             const unsigned d = __popc(l0.x ^ r0.x) + __popc(l0.y ^ r0.y) + __popc(l0.z ^ r0.z) + __popc(l0.w ^ r0.w) +
@@ -311,16 +321,18 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo(const __grid_constant_
                 const int lc = wl[5 * 11 + 5];
                 int dist[11];
 #pragma unroll
-                for (int inc = 0; inc < 11; ++inc) {
-                    const int rc = wr[5 * 21 + inc + 5];
-                    int s = 0;
-                    for (int t = lane; t < 121; t += 32) {
-                        const int r = t / 11, cc = t - r * 11;
-                        s += abs((wl[t] - lc) - (wr[r * 21 + cc + inc] - rc));
-                    }
+                for (int inc = 0; inc < 11; ++inc) dist[inc] = 0;
+                for (int t = lane; t < 121; t += 32) {        // this lane's pixels; all 11 shifts per pixel
+                    const int r = t / 11, cc = t - r * 11;
+                    const int lv = wl[t] - lc;
+                    const unsigned char* rp = wr + r * 21 + cc;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    dist[inc] = s;
+                    for (int inc = 0; inc < 11; ++inc) dist[inc] += abs(lv - (rp[inc] - wr[5 * 21 + inc + 5]));
+                }
+#pragma unroll
+                for (int inc = 0; inc < 11; ++inc) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) dist[inc] += __shfl_xor_sync(0xffffffffu, dist[inc], o);
                 }
                 __syncwarp();
                 int bestInc = 0, bestSad = dist[0];
