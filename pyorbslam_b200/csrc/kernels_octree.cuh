@@ -16,7 +16,7 @@
 #pragma once
 #include "plan.h"
 
-#define OCT_THREADS 256
+#define OCT_THREADS 512
 #define OCT_WARPS (OCT_THREADS / 32)
 
 struct OctNodes {      // one generation of the node list (structure of arrays in shared memory)
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     int* cellOfs = (int*)sp; sp += (size_t)capC * 4;
     int* misc = (int*)sp;             // [0..8] scan tmp, [16] m, [17..] flags
     int* tmp = misc;
-    int* sh_m = misc + 16;
+    int* sh_m = misc + 40;
 
     int* out_cnt = lvl_cnt + (size_t)slot * P.nlevels + l;
     u32* out_kp = lvl_kp + (size_t)slot * P.kp_total + G.kp_ofs;
