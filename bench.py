@@ -31,10 +31,23 @@ H, W = 376, 1241
 MBF, FX = 386.1448, 718.856                                                       # configs/KITTI00-02.yaml:7,24
 METRIC, UNIT = "stereo_frames_per_sec", "frames/s"
 STREAMS = 1
+WORKLOAD_NAME = "BASELINE.json configs[2]: batch of synthetic KITTI00-02-shape stereo pairs, extract L+R + compute_stereo_matches"
 
 
 # ------------------------------------------------------------------------------------------------ geometry / bytes
-def level_sizes(Hh=H, Ww=W, nlevels=8, scale=1.2):
+WORKLOADS = {
+    # BASELINE.json configs[2] (the metric's configuration): KITTI00-02 camera and ORB settings
+    "kitti": dict(H=376, W=1241, orb=dict(nfeatures=2000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7), pairs=4096, chunk=128,
+                  name="BASELINE.json configs[2]: batch of synthetic KITTI00-02-shape stereo pairs, extract L+R + compute_stereo_matches"),
+    # BASELINE.json configs[3]: bandwidth stress (not the headline metric; run with --no-cpu-baseline, the CPU path needs ~10 s per frame)
+    "hires": dict(H=1440, W=2560, orb=dict(nfeatures=8000, scaleFactor=1.2, nlevels=12, iniThFAST=20, minThFAST=7), pairs=256, chunk=64,
+                  name="BASELINE.json configs[3]: synthetic 2560x1440 stereo pairs, 8000 features, 12 levels"),
+}
+
+
+def level_sizes(Hh=None, Ww=None, nlevels=None, scale=None):
+    Hh, Ww = Hh or H, Ww or W
+    nlevels, scale = nlevels or ORB["nlevels"], scale or ORB["scaleFactor"]
     s, out = np.float32(1.0), []
     for l in range(nlevels):
         if l:
@@ -119,7 +132,7 @@ class CpuReference:
         self.workers = workers or max(1, min(os.cpu_count() or 1, 32))
         self.pool = mp.get_context("fork").Pool(self.workers)
         from pyorbslam_b200.synthetic import make_stereo_pair
-        self.pairs = [make_stereo_pair(i) for i in range(min(self.workers, 8))]   # a few distinct frames, reused round-robin
+        self.pairs = [make_stereo_pair(i, H, W) for i in range(min(self.workers, 8))]   # a few distinct frames, reused round-robin
 
     def step(self, n_pairs):
         work = [(self.pairs[i % len(self.pairs)][0], self.pairs[i % len(self.pairs)][1], self.use_ref) for i in range(n_pairs)]
@@ -135,7 +148,7 @@ class CpuReference:
     def describe(self, n_pairs, res):
         te = float(np.mean([r[0] for r in res]))
         ts = float(np.mean([r[1] for r in res]))
-        return (f"{n_pairs} synthetic 1241x376 pairs per step over {self.workers} worker processes; per frame on one core: "
+        return (f"{n_pairs} synthetic {W}x{H} pairs per step over {self.workers} worker processes; per frame on one core: "
                 f"extract L+R + KeyPoint lists + pyramids {te*1e3:.0f} ms "
                 f"({'reference ORBextractor.cpp compiled -O3 against oracle/cvshim scalar primitives' if self.use_ref else 'oracle port'}), "
                 f"compute_stereo_matches {ts*1e3:.0f} ms (Python restatement, reference structure)")
@@ -169,7 +182,7 @@ def run_reference_arm(args):
 
 
 def workload_config(pairs, chunk):
-    return {"workload": "BASELINE.json configs[2]: batch of synthetic KITTI00-02-shape stereo pairs, extract L+R + compute_stereo_matches",
+    return {"workload": WORKLOAD_NAME,
             "image": [H, W], **ORB, "bf": MBF, "fx": FX, "pairs_per_gpu_per_step": pairs, "chunk_pairs": chunk, "concurrent_streams": STREAMS,
             "l2": "inputs of one step exceed the 126 MB L2 (0.93 MB per pair)", "parallelism": "frames sharded per GPU, no collective"}
 
@@ -268,7 +281,7 @@ def run_b200_arm(args):
     nb = args.base_pairs
     # synthetic batch: `nb` distinct scenes per rank, frame i = scene (i % nb) rolled horizontally by 9 * (i // nb) px
     # in BOTH views (disparities unchanged; every frame lands differently on the FAST cell grid)
-    base = [make_stereo_pair(1000 * rank + i) for i in range(nb)]
+    base = [make_stereo_pair(1000 * rank + i, H, W) for i in range(nb)]
     bl = torch.from_numpy(np.stack([p[0] for p in base])).to(dev)
     br = torch.from_numpy(np.stack([p[1] for p in base])).to(dev)
     left = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
@@ -367,6 +380,28 @@ def run_b200_arm(args):
     # the e2e result must equal the device-resident one (same frames)
     same = bool((oh["nkp"][:, :chunks[0][1]] == outs[0]["nkp"].cpu()).all())
 
+    # ---- latency of the reference-compatible single-frame API (config 2: what one Frame.__init__ costs) ----
+    dropin = None
+    if rank == 0:
+        from pyorbslam_b200 import ORBextractor
+        from pyorbslam_b200.stereo import stereo_resident
+        prm = (ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"])
+        eL, eR = ORBextractor(*prm, device=local), ORBextractor(*prm, device=local)
+        L0, R0 = left[0].cpu().numpy(), right[0].cpu().numpy()
+
+        def one_frame():
+            kl, dl = eL.operator_kd(L0)                       # Frame.ExtractORB(0) incl. the 6-tuple list
+            kr, dr = eR.operator_kd(R0)
+            pl, pr = eL.GetImagePyramid(), eR.GetImagePyramid()   # Frame.py:59-60
+            return stereo_resident(eL, eR, MBF, FX)           # Frame.compute_stereo_matches
+        for _ in range(3):
+            one_frame()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            one_frame()
+        dropin = {"ms_per_frame": 1e3 * (time.perf_counter() - t0) / 20,
+                  "what": "ORBextractor.operator_kd x2 (tuple lists) + GetImagePyramid x2 + compute_stereo_matches through the drop-in Python API, one pair at a time"}
+
     if rank == 0:
         per_image, stereo_pp, B_frame = algorithmic_bytes(ORB["nfeatures"])
         per_image["octree"] = 4 * ncand + 4 * nkp
@@ -402,6 +437,7 @@ def run_b200_arm(args):
             "workload_stats": {"keypoints_per_image": nkp, "fast_candidates_per_image": ncand, "stereo_matches_per_pair": matched,
                                "workspace_bytes": sum(f.workspace_bytes() for f in fes), "rank0_cpu_affinity": numa if isinstance(numa, str) else f"{len(numa)} cpus: {numa[0]}-{numa[-1]}"},
         }
+        line["dropin_single_frame_latency"] = dropin
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
@@ -415,15 +451,21 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=4096, help="stereo pairs per GPU per step (BASELINE.json configs[2]: 4096)")
-    ap.add_argument("--chunk", type=int, default=128, help="pairs per kernel-sequence launch")
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS), help="kitti = the headline metric's configuration")
+    ap.add_argument("--pairs", type=int, default=None, help="stereo pairs per GPU per step (kitti: 4096 = BASELINE.json configs[2])")
+    ap.add_argument("--chunk", type=int, default=None, help="pairs per kernel-sequence launch (kitti: 128)")
     ap.add_argument("--base-pairs", type=int, default=16, help="distinct synthetic scenes per rank")
     ap.add_argument("--e2e-pairs", type=int, default=2048, help="pairs per end-to-end step (pinned host memory: 0.93 MB in + 0.25 MB out per pair)")
     ap.add_argument("--streams", type=int, default=1, help="front-ends running consecutive chunks concurrently (own workspace + stream each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    global STREAMS
+    global STREAMS, H, W, ORB, WORKLOAD_NAME
     STREAMS = args.streams
+    wl = WORKLOADS[args.workload]
+    H, W, ORB, WORKLOAD_NAME = wl["H"], wl["W"], wl["orb"], wl["name"]
+    args.pairs = args.pairs or wl["pairs"]
+    args.chunk = args.chunk or wl["chunk"]
+    args.e2e_pairs = min(args.e2e_pairs, args.pairs)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -74,6 +74,9 @@ int b200orb_max_keypoints(const b200orb_extractor* e);
  * That sheared view is what Frame.compute_stereo_matches reads; we return exactly it. */
 int b200orb_level_size(const b200orb_extractor* e, int level, int* w, int* h);
 int b200orb_get_pyramid_level(b200orb_extractor* e, int level, uint8_t* out /* h*w bytes */);
+/* all levels of GetImagePyramid() in one call: the views of level 0, 1, ... concatenated (sum of h_l * w_l bytes, which must
+ * be <= cap); one device synchronisation instead of one per level */
+int b200orb_get_pyramid_all(b200orb_extractor* e, uint8_t* out, long long cap);
 /* the true level image (dense h*w copy of the ROI) and its 7x7 sigma-2 blur -- diagnostics / parity tests */
 int b200orb_get_level_image(b200orb_extractor* e, int level, int blurred, uint8_t* out /* h*w bytes */);
 /* FAST candidates fed to DistributeOctTree for one level, int[cap][3] = (x, y, response), coordinates

@@ -40,6 +40,7 @@ def lib():
     l.b200orb_max_keypoints.argtypes = [vp]
     l.b200orb_level_size.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     l.b200orb_get_pyramid_level.argtypes = [vp, i32, vp]
+    l.b200orb_get_pyramid_all.argtypes = [vp, vp, C.c_longlong]
     l.b200orb_get_level_image.argtypes = [vp, i32, i32, vp]
     l.b200orb_get_level_candidates.argtypes = [vp, i32, i32, vp, C.POINTER(i32)]
     l.b200orb_stereo.argtypes = [vp, vp, f64, f32, vp, vp, vp]

@@ -351,6 +351,7 @@ struct b200orb_extractor {
     float* d_kps = nullptr; u8* d_desc = nullptr; int* d_nkp = nullptr;
     float *d_uR = nullptr, *d_depth = nullptr; int *d_match = nullptr, *d_sad = nullptr;
     int out_cap = 0;
+    u8* h_stage = nullptr; size_t stage_cap = 0;   // pinned staging for GetImagePyramid
     int n = -1;          // keypoints of the last call, -1 = none yet
     bool empty_last = false;
 };
@@ -406,6 +407,7 @@ void b200orb_extractor_destroy(b200orb_extractor* e) {
         cudaFree(e->d_img); cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_nkp);
         cudaFree(e->d_uR); cudaFree(e->d_depth); cudaFree(e->d_match); cudaFree(e->d_sad);
         if (e->st) cudaStreamDestroy(e->st);
+        if (e->h_stage) cudaFreeHost(e->h_stage);
     }
     delete e;
 }
@@ -497,6 +499,40 @@ int b200orb_get_pyramid_level(b200orb_extractor* e, int level, uint8_t* out) {
     CU_TRY(cudaStreamSynchronize(e->st));
     // the caster's step-ignoring copy: rows*cols contiguous bytes from the ROI start (opencv_type_casters.h:230-239)
     memcpy(out, tmp.data() + (size_t)ORB_EDGE * plog + ORB_EDGE, (size_t)G.w * G.h);
+    return 0;
+}
+
+int b200orb_get_pyramid_all(b200orb_extractor* e, uint8_t* out, long long cap) {
+    TRY(need_pyramid(e, 0));
+    if (!out) return fail(B200ORB_E_ARG, "out is NULL");
+    CU_TRY(cudaSetDevice(e->eng.device));
+    const Plan& P = e->eng.hp.P;
+    size_t need = 0, total = 0;
+    for (int l = 0; l < P.nlevels; ++l) { need += (size_t)(P.lv[l].w + 2 * ORB_EDGE) * P.lv[l].rows; total += (size_t)P.lv[l].w * P.lv[l].h; }
+    if ((long long)total > cap) return fail(B200ORB_E_ARG, "output buffer too small for the pyramid views");
+    if (need > e->stage_cap) {
+        if (e->h_stage) cudaFreeHost(e->h_stage);
+        e->h_stage = nullptr; e->stage_cap = 0;
+        CU_TRY(cudaHostAlloc((void**)&e->h_stage, need, cudaHostAllocDefault));
+        e->stage_cap = need;
+    }
+    size_t off = 0;
+    for (int l = 0; l < P.nlevels; ++l) {     // all levels in flight, one synchronisation
+        const LevelGeom& G = P.lv[l];
+        const int plog = G.w + 2 * ORB_EDGE;
+        CU_TRY(cudaMemcpy2DAsync(e->h_stage + off, plog, e->eng.d_pyr + G.pyr_ofs, G.pitch, plog, G.rows, cudaMemcpyDeviceToHost, e->st));
+        off += (size_t)plog * G.rows;
+    }
+    CU_TRY(cudaStreamSynchronize(e->st));
+    off = 0;
+    size_t o = 0;
+    for (int l = 0; l < P.nlevels; ++l) {     // the caster's step-ignoring copy (opencv_type_casters.h:230-239), level by level
+        const LevelGeom& G = P.lv[l];
+        const int plog = G.w + 2 * ORB_EDGE;
+        memcpy(out + o, e->h_stage + off + (size_t)ORB_EDGE * plog + ORB_EDGE, (size_t)G.w * G.h);
+        o += (size_t)G.w * G.h;
+        off += (size_t)plog * G.rows;
+    }
     return 0;
 }
 

@@ -94,12 +94,13 @@ class ORBextractor:
         return w.value, h.value
 
     def GetImagePyramid(self):
-        out = []
-        for l in range(self._nlevels):
-            w, h = self.level_size(l)
-            v = np.empty((h, w), np.uint8)
-            _lib.check(_lib.lib().b200orb_get_pyramid_level(self._h, l, v.ctypes.data))
-            out.append(v)
+        sizes = [self.level_size(l) for l in range(self._nlevels)]
+        buf = np.empty(sum(w * h for w, h in sizes), np.uint8)        # one owning buffer; the levels are views of it
+        _lib.check(_lib.lib().b200orb_get_pyramid_all(self._h, buf.ctypes.data, buf.size))
+        out, o = [], 0
+        for w, h in sizes:
+            out.append(buf[o:o + w * h].reshape(h, w))
+            o += w * h
         return out
 
     # ---- diagnostics used by the parity tests ----
