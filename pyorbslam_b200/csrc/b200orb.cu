@@ -258,7 +258,7 @@ struct Engine {
         const Plan& P = hp.P;
         {
             const LevelGeom& G = P.lv[0];
-            dim3 grid(((G.pitch >> 2) * G.rows + 255) / 256, n);
+            dim3 grid(((G.pitch >> 4) * G.rows + 255) / 256, n);
             k_border0<<<grid, 256, 0, st>>>(P, imgA, imgB, splitA, d_pyr);
             ++g_launches;
             if (evs) cudaEventRecord(evs[1], st);

@@ -16,32 +16,39 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 
 // ------------------------------------------------------------------------------------------------
 // K1a: level 0 = input image + 19-px BORDER_REFLECT_101 (ComputePyramid, ORBextractor.cpp:1125-1129).
-// One thread writes 4 consecutive bytes of the bordered buffer (one 32-bit store).
 // imgA holds slots [0, splitA), imgB the rest (left / right image batches).
 // ------------------------------------------------------------------------------------------------
+// One thread writes 16 consecutive bytes of the bordered buffer (one 128-bit store).  Interior spans read five
+// aligned 32-bit words of the (arbitrarily aligned) source row and funnel-shift them into place.
 __global__ void __launch_bounds__(256) k_border0(const __grid_constant__ Plan P, const u8* __restrict__ imgA,
                                                  const u8* __restrict__ imgB, int splitA, u8* __restrict__ pyr) {
     const LevelGeom& G = P.lv[0];
     const int slot = blockIdx.y;
-    const int words_per_row = G.pitch >> 2;
+    const int vec_per_row = G.pitch >> 4;                       // pitch is a multiple of 64
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= words_per_row * G.rows) return;
-    const int by = idx / words_per_row, bx = (idx - by * words_per_row) << 2;
+    if (idx >= vec_per_row * G.rows) return;
+    const int by = idx / vec_per_row, bx = (idx - by * vec_per_row) << 4;
     const u8* img = slot < splitA ? imgA + (size_t)slot * P.H * P.W : imgB + (size_t)(slot - splitA) * P.H * P.W;
     const u8* srow = img + (size_t)reflect101(by - ORB_EDGE, P.H) * P.W;
-    u32 v = 0;
     const int x0 = bx - ORB_EDGE;
-    if (x0 >= 0 && x0 + 3 < P.W) {
-        v = srow[x0] | (srow[x0 + 1] << 8) | (srow[x0 + 2] << 16) | ((u32)srow[x0 + 3] << 24);
+    u32 v[4] = {0u, 0u, 0u, 0u};
+    if (x0 >= 0 && x0 + 19 < P.W) {                              // interior (the 5th word may touch 3 bytes past the span)
+        const size_t addr = reinterpret_cast<size_t>(srow + x0);
+        const u32* wp = reinterpret_cast<const u32*>(addr & ~(size_t)3);
+        const int sh = 8 * (int)(addr & 3);
+        const u32 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+        v[0] = __funnelshift_r(w0, w1, sh); v[1] = __funnelshift_r(w1, w2, sh);
+        v[2] = __funnelshift_r(w2, w3, sh); v[3] = __funnelshift_r(w3, w4, sh);
     } else {
+        const int bw = G.w + 2 * ORB_EDGE;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int x = bx + k;
-            u32 b = x < G.w + 2 * ORB_EDGE ? srow[reflect101(x - ORB_EDGE, P.W)] : 0;
-            v |= b << (8 * k);
+        for (int k = 0; k < 16; ++k) {
+            const int x = bx + k;
+            const u32 b = x < bw ? srow[reflect101(x - ORB_EDGE, P.W)] : 0;
+            v[k >> 2] |= b << (8 * (k & 3));
         }
     }
-    *reinterpret_cast<u32*>(pyr + (size_t)slot * P.pyr_bytes + G.pyr_ofs + (size_t)by * G.pitch + bx) = v;
+    *reinterpret_cast<uint4*>(pyr + (size_t)slot * P.pyr_bytes + G.pyr_ofs + (size_t)by * G.pitch + bx) = make_uint4(v[0], v[1], v[2], v[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -116,7 +123,14 @@ __global__ void __launch_bounds__(BLUR_WARPS * 32) k_blur(const __grid_constant_
     const int w0 = min((x0 + 16) >> 2, wpr - 1);
     const int wx = min(((tx * BLUR_TW + 16) >> 2) + 32 + (lane & 1), wpr - 1);   // lanes 0/1 fetch the two words past the strip
     u8* dst = blur + (size_t)slot * P.blur_bytes + G.blur_ofs;
-    u32 hb[7][4];                                            // ring of 7 horizontally filtered rows, 4 columns each
+    // Horizontal pass: the 7 taps of one output are two 4-byte dot products (DP4A) on byte windows cut out of the three
+    // source words with funnel shifts.  Vertical pass: consecutive filtered rows (16-bit values) are kept packed in pairs
+    // P[k] = (h[k], h[k+1]) so that 6 of the 7 taps are three 2-way dot products (DP2A) and the 7th one multiply-add.
+    const u32 KH0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);     // taps 0..3
+    const u32 KH1 = 48u | (34u << 8) | (18u << 16);                    // taps 4..6 (byte 3 = 0)
+    const u32 KV01 = 18u | (34u << 8), KV23 = 48u | (56u << 8), KV45 = 48u | (34u << 8);
+    u32 hp[7][4];      // ring of packed pairs: hp[k % 7][c] = h_k[c] | h_{k+1}[c] << 16
+    u32 hprev[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int r = 0; r < BLUR_RB + 6; ++r) {
         const int by = min(y0 + r - 3 + ORB_EDGE, G.rows - 1);
@@ -128,26 +142,33 @@ __global__ void __launch_bounds__(BLUR_WARPS * 32) k_blur(const __grid_constant_
         const u32 X0 = __shfl_sync(0xffffffffu, X, 0), X1 = __shfl_sync(0xffffffffu, X, 1);
         if (lane == 31) { B = X0; C = X1; }
         if (lane == 30) C = X0;
-        const u32 a0 = A & 0xff, a1 = (A >> 8) & 0xff, a2 = (A >> 16) & 0xff, a3 = A >> 24;
-        const u32 a4 = B & 0xff, a5 = (B >> 8) & 0xff, a6 = (B >> 16) & 0xff, a7 = B >> 24;
-        const u32 a8 = C & 0xff, a9 = (C >> 8) & 0xff;
-        u32* hr = hb[r % 7];
-        hr[0] = 18 * (a0 + a6) + 34 * (a1 + a5) + 48 * (a2 + a4) + 56 * a3;
-        hr[1] = 18 * (a1 + a7) + 34 * (a2 + a6) + 48 * (a3 + a5) + 56 * a4;
-        hr[2] = 18 * (a2 + a8) + 34 * (a3 + a7) + 48 * (a4 + a6) + 56 * a5;
-        hr[3] = 18 * (a3 + a9) + 34 * (a4 + a8) + 48 * (a5 + a7) + 56 * a6;
+        u32 hc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {   // output column c: source bytes c .. c+6 of the 12-byte window (A, B, C)
+            const u32 lo = c ? __funnelshift_r(A, B, 8 * c) : A;
+            const u32 hi = c ? __funnelshift_r(B, C, 8 * c) : B;
+            hc[c] = __dp4a(hi, KH1, __dp4a(lo, KH0, 0u));
+        }
+        if (r >= 1) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) hp[(r - 1) % 7][c] = hprev[c] | (hc[c] << 16);
+        }
         if (r >= 6) {
             const int y = y0 + r - 6;
             u32 o = 0;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {   // taps 0..6 <-> ring slots (r-6)%7 .. r%7
-                const u32 acc = 18u * (hb[(r - 6) % 7][c] + hb[r % 7][c]) + 34u * (hb[(r - 5) % 7][c] + hb[(r - 1) % 7][c]) +
-                                48u * (hb[(r - 4) % 7][c] + hb[(r - 2) % 7][c]) + 56u * hb[(r - 3) % 7][c];
-                o |= ((acc + 32768u) >> 16) << (8 * c);
+            for (int c = 0; c < 4; ++c) {   // rows r-6 .. r: pairs (r-6,r-5), (r-4,r-3), (r-2,r-1) + row r
+                u32 acc = 18u * hc[c] + 32768u;
+                acc = __dp2a_lo(hp[(r - 6) % 7][c], KV01, acc);
+                acc = __dp2a_lo(hp[(r - 4) % 7][c], KV23, acc);
+                acc = __dp2a_lo(hp[(r - 2) % 7][c], KV45, acc);
+                o |= (acc >> 16) << (8 * c);
             }
             if (y < G.h && x0 < G.w)   // blur pitch is a multiple of 64: the aligned 4-byte store may spill into padding only
                 *reinterpret_cast<u32*>(dst + (size_t)y * G.blur_pitch + x0) = o;
         }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) hprev[c] = hc[c];
     }
 }
 
