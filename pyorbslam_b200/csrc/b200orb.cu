@@ -265,8 +265,10 @@ struct Engine {
         }
         for (int l = 1; l < P.nlevels; ++l) {
             const LevelGeom& G = P.lv[l];
-            dim3 grid(((G.pitch >> 2) * G.rows + 255) / 256, n);
-            k_resize<<<grid, 256, 0, st>>>(P, l, d_pyr, d_xtab, d_ytab);
+            dim3 grid(((G.pitch >> 2) * ((G.rows + 1) / 2) + 255) / 256, n);
+            // the word-window fast path needs the 4 columns of a thread to span <= 10 source bytes: scale < 2
+            const int fast_ok = (double)P.lv[l - 1].w / G.w < 1.95 ? 1 : 0;
+            k_resize<<<grid, 256, 0, st>>>(P, l, fast_ok, d_pyr, d_xtab, d_ytab);
             ++g_launches;
         }
         if (evs) cudaEventRecord(evs[2], st);

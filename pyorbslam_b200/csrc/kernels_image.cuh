@@ -59,38 +59,97 @@ __global__ void __launch_bounds__(256) k_border0(const __grid_constant__ Plan P,
 // dst = (((b0*(T0>>4))>>16) + ((b1*(T1>>4))>>16) + 2) >> 2   (SURVEY.md App. A2).
 // ------------------------------------------------------------------------------------------------
 // The tables are indexed by BORDERED coordinates (the host applied the reflect-101 map and padded each row of
-// entries to the buffer pitch), so a thread's four column entries are one aligned 32-byte read (2 x LDG.128)
-// instead of four scattered 8-byte reads -- the kernel is L1-wavefront bound, not DRAM bound.
-__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Plan P, int l, u8* __restrict__ pyr,
+// entries to the buffer pitch), so a thread's four column entries are one aligned 32-byte read (2 x LDG.128).
+// One thread = 4 columns x 2 rows of the bordered output.  Interior threads (the vast majority) read each source row
+// they need as three aligned 32-bit words (the 4 columns span <= 10 source bytes for scale factors < 2), pick the
+// (p[sx], p[sx+1]) byte pair of every column with one PRMT and form the horizontal interpolation with one 2-way dot
+// product (DP2A) against the packed 11-bit coefficients; two consecutive output rows usually share a source row.
+// Border threads (reflected, non-monotonic columns) and scale factors >= 2 take the per-byte path.
+__device__ __forceinline__ u32 rs_vert(int T0, int T1, int b0, int b1) {
+    return (u32)(((((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2) & 0xff);
+}
+
+__global__ void __launch_bounds__(256, 6) k_resize(const __grid_constant__ Plan P, int l, int fast_ok, u8* __restrict__ pyr,
                                                 const XTab* __restrict__ xtab, const YTab* __restrict__ ytab) {
     const LevelGeom& G = P.lv[l];
     const LevelGeom& S = P.lv[l - 1];
     const int slot = blockIdx.y;
     const int words_per_row = G.pitch >> 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= words_per_row * G.rows) return;
-    const int by = idx / words_per_row, bx = (idx - by * words_per_row) << 2;
+    const int rp = idx / words_per_row;                     // row pair
+    const int by = rp << 1, bx = (idx - rp * words_per_row) << 2;
+    if (by >= G.rows) return;
+    const bool two = by + 1 < G.rows;
     u8* base = pyr + (size_t)slot * P.pyr_bytes;
-    const u8* src = base + S.pyr_ofs + (size_t)ORB_EDGE * S.pitch + ORB_EDGE;   // ROI origin of level l-1
-    const YTab yt = ytab[G.ytab_ofs + by];
-    const u8* r0 = src + (size_t)yt.y0 * S.pitch;
-    const u8* r1 = src + (size_t)yt.y1 * S.pitch;
+    const u8* srcb = base + S.pyr_ofs;                       // bordered buffer of level l-1 (ROI at +19, +19)
+    const YTab ya = ytab[G.ytab_ofs + by], yb = ytab[G.ytab_ofs + (two ? by + 1 : by)];
     const int4* tp = reinterpret_cast<const int4*>(xtab + G.xtab_ofs + bx);
     const int4 t01 = __ldg(tp), t23 = __ldg(tp + 1);
     const int sxs[4] = {t01.x, t01.z, t23.x, t23.z};
-    const int cf[4] = {t01.y, t01.w, t23.y, t23.w};       // a0 | a1 << 16
+    const u32 cf[4] = {(u32)t01.y, (u32)t01.w, (u32)t23.y, (u32)t23.w};       // a0 | a1 << 16 (both in [0, 2048])
     const int bw = G.w + 2 * ORB_EDGE;
-    u32 v = 0;
+    u32 va = 0, vb = 0;
+    const int xi = bx - ORB_EDGE;
+    if (fast_ok && xi >= 0 && xi + 3 < G.w) {
+        // byte offset of column j's left sample inside the 12-byte window that starts at the aligned word of column 0
+        const int c0 = sxs[0] + ORB_EDGE, wb = c0 >> 2;
+        int o[4]; u32 sel[4]; bool hi[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        // when sx is the last column a1 == 0 and sx+1 reads the (valid) border pixel
-        const int sx = sxs[k], a0 = (short)(cf[k] & 0xffff), a1 = cf[k] >> 16;
-        const int T0 = r0[sx] * a0 + r0[sx + 1] * a1;
-        const int T1 = r1[sx] * a0 + r1[sx + 1] * a1;
-        const int d = (((yt.b0 * (T0 >> 4)) >> 16) + ((yt.b1 * (T1 >> 4)) >> 16) + 2) >> 2;
-        if (bx + k < bw) v |= (u32)(d & 0xff) << (8 * k);
+        for (int j = 0; j < 4; ++j) {
+            o[j] = sxs[j] + ORB_EDGE - (wb << 2);            // 0 .. 10
+            hi[j] = o[j] > 6;                                 // pair comes from words (1, 2) instead of (0, 1)
+            const int k = hi[j] ? o[j] - 4 : o[j];
+            sel[j] = (u32)k | ((u32)(k + 1) << 4);            // PRMT selector: result byte 0 = window byte k, byte 1 = k + 1
+        }
+        const int spw = S.pitch >> 2;
+        const u32* wsrc = reinterpret_cast<const u32*>(srcb) + wb;
+        int Ta[4], Tb[4];                                      // horizontal results of the two source rows in flight
+        auto hrow = [&](int sy, int (&T)[4]) {
+            const u32* r = wsrc + (size_t)(sy + ORB_EDGE) * spw;
+            const u32 w0 = r[0], w1 = r[1], w2 = r[2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const u32 pr = __byte_perm(hi[j] ? w1 : w0, hi[j] ? w2 : w1, sel[j]);
+                T[j] = (int)__dp2a_lo(cf[j], pr, 0u);         // p[sx] * a0 + p[sx+1] * a1
+            }
+        };
+        hrow(ya.y0, Ta);
+        hrow(ya.y1, Tb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) va |= rs_vert(Ta[j], Tb[j], ya.b0, ya.b1) << (8 * j);
+        if (two) {
+            if (yb.y0 == ya.y1) {                              // usual case at scale 1.2: the rows overlap by one source row
+                hrow(yb.y1, Ta);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) vb |= rs_vert(Tb[j], Ta[j], yb.b0, yb.b1) << (8 * j);
+            } else {
+                if (yb.y0 != ya.y0) hrow(yb.y0, Ta);
+                if (yb.y1 != ya.y1) hrow(yb.y1, Tb);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) vb |= rs_vert(Ta[j], Tb[j], yb.b0, yb.b1) << (8 * j);
+            }
+        }
+    } else {
+        const u8* roi = srcb + (size_t)ORB_EDGE * S.pitch + ORB_EDGE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (bx + k < bw) {
+                // when sx is the last column a1 == 0 and sx+1 reads the (valid) border pixel
+                const int sx = sxs[k], a0 = (int)(cf[k] & 0xffff), a1 = (int)(cf[k] >> 16);
+                const u8* r0 = roi + (size_t)ya.y0 * S.pitch + sx;
+                const u8* r1 = roi + (size_t)ya.y1 * S.pitch + sx;
+                va |= rs_vert(r0[0] * a0 + r0[1] * a1, r1[0] * a0 + r1[1] * a1, ya.b0, ya.b1) << (8 * k);
+                if (two) {
+                    const u8* q0 = roi + (size_t)yb.y0 * S.pitch + sx;
+                    const u8* q1 = roi + (size_t)yb.y1 * S.pitch + sx;
+                    vb |= rs_vert(q0[0] * a0 + q0[1] * a1, q1[0] * a0 + q1[1] * a1, yb.b0, yb.b1) << (8 * k);
+                }
+            }
+        }
     }
-    *reinterpret_cast<u32*>(base + G.pyr_ofs + (size_t)by * G.pitch + bx) = v;
+    u8* dst = base + G.pyr_ofs + (size_t)by * G.pitch + bx;
+    *reinterpret_cast<u32*>(dst) = va;
+    if (two) *reinterpret_cast<u32*>(dst + G.pitch) = vb;
 }
 
 // ------------------------------------------------------------------------------------------------
