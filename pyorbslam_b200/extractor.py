@@ -12,8 +12,17 @@ from . import _lib
 
 
 class ORBextractor:
-    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0):
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0, reuse_identical_input=True):
+        """reuse_identical_input: the reference's Frame.copy() runs the whole Frame constructor again on the same two
+        images (Frame.py:75-77, called at Tracking.py:267,306), i.e. it extracts every tracked frame twice.  When the image
+        passed to operator_kd is byte-identical to the previous call's, the (deterministic) results still resident on the
+        device are returned again instead of being recomputed; a byte compare of 0.5 MB costs ~25 us."""
         self._h = None
+        self._reuse = bool(reuse_identical_input)
+        self._last_image = None
+        self._last_kps = None
+        self._cached_desc = None
+        self.reused_calls = 0
         h = C.c_void_p()
         _lib.check(_lib.lib().b200orb_extractor_create(int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST),
                                                        int(minThFAST), int(device), C.byref(h)))
@@ -70,6 +79,12 @@ class ORBextractor:
             # reads the buffer as if it were 8-bit gray; we refuse instead of reproducing undefined behaviour
             raise RuntimeError("image must be 8-bit single channel (CV_8UC1)")
         image = np.ascontiguousarray(image)
+        if (self._reuse and self._last_image is not None and self._last_image.shape == image.shape
+                and np.array_equal(self._last_image, image)):
+            self.reused_calls += 1
+            desc = self._cached_desc.copy()        # owning copies, like every call (the private cache is never handed out)
+            self._last_desc = desc                 # identity token for the device-resident stereo path
+            return self._last_kps.copy(), desc
         n = C.c_int(0)
         H, W = image.shape
         _lib.check(_lib.lib().b200orb_extract(self._h, image.ctypes.data, H, W, C.byref(n)))
@@ -80,6 +95,10 @@ class ORBextractor:
             _lib.check(_lib.lib().b200orb_get_results(self._h, kps.ctypes.data, desc.ctypes.data))
         self._last_desc = desc
         self._last_n = n
+        if self._reuse:
+            self._last_image = image.copy()
+            self._last_kps = kps.copy()
+            self._cached_desc = desc.copy()
         return kps, desc
 
     def operator_kd(self, image):

@@ -371,3 +371,31 @@ def test_opt_in_upstream_options_median_cull_and_dense_pyramid():
     n = len(kL)
     assert np.array_equal(out["uRight"][1, :n].cpu().numpy().view(np.uint32), bu.view(np.uint32))
     assert np.array_equal(out["depth"][0, :n].cpu().numpy().view(np.uint32), bd.view(np.uint32))
+
+
+def test_identical_input_is_not_recomputed_but_results_are_fresh_copies():
+    """Frame.copy() re-runs Frame.__init__ on the same images (Frame.py:75-77): the second operator_kd on a byte-identical
+    image returns the resident results again (new owning arrays), and the resident stereo path still works afterwards."""
+    L, R = make_stereo_pair(0)
+    eL, eR = ORBextractor(*KITTI), ORBextractor(*KITTI)
+    k1, d1 = eL.extract_arrays(L)
+    eR.extract_arrays(R)
+    u1, _, m1 = stereo_resident(eL, eR, 386.1448, 718.856)
+    before = _lib.kernel_launches()
+    k2, d2 = eL.extract_arrays(L.copy())                   # another ndarray object, same bytes
+    assert _lib.kernel_launches() == before and eL.reused_calls == 1
+    assert k2 is not k1 and d2 is not d1 and np.array_equal(k1, k2) and np.array_equal(d1, d2)
+    d2[0, 0] ^= 0xff                                        # callers own what they get
+    k3, d3 = eL.extract_arrays(L)
+    assert np.array_equal(d3, d1)
+    u2, _, m2 = stereo_resident(eL, eR, 386.1448, 718.856)
+    assert np.array_equal(u1.view(np.uint32), u2.view(np.uint32)) and np.array_equal(m1, m2)
+    L2 = L.copy()
+    L2[100, 100] ^= 1                                       # one bit differs -> recomputed
+    eL.extract_arrays(L2)
+    assert _lib.kernel_launches() > before
+    off = ORBextractor(*KITTI, reuse_identical_input=False)
+    off.extract_arrays(L)
+    b2 = _lib.kernel_launches()
+    off.extract_arrays(L)
+    assert _lib.kernel_launches() > b2
