@@ -404,6 +404,33 @@ def run_b200_arm(args):
         dropin = {"ms_per_frame": 1e3 * (time.perf_counter() - t0) / 20,
                   "what": "ORBextractor.operator_kd x2 (tuple lists) + GetImagePyramid x2 + compute_stereo_matches through the drop-in Python API, one pair at a time"}
 
+    # ---- BoW transform of one frame's descriptors (Frame.compute_BoW), GPU vs the Python restatement ----
+    bow_extra = None
+    if rank == 0 and not args.no_cpu_baseline:
+        import types
+        from oracle.bow_py import Vocabulary, make_vocab_text          # checker / CPU baseline leg only
+        from pyorbslam_b200.bow import GpuVocabulary
+        voc = Vocabulary.from_text(make_vocab_text(seed=3, k=10, L=4, p_early_leaf=0.0, p_zero_weight=0.0))
+        model = types.SimpleNamespace(L=voc.L, nodes=[types.SimpleNamespace(children=voc.children[i], descriptor=None if i == 0 else voc.desc[i],
+                                                                           weight=voc.weight[i], word_id=voc.word_id[i]) for i in range(len(voc.children))])
+        gv = GpuVocabulary(model, device=local)
+        _, desc0 = eL.operator_kd(L0)
+        for _ in range(3):
+            gv.transform(desc0, 4)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            gbv, gfv = gv.transform(desc0, 4)
+        gpu_ms = 1e3 * (time.perf_counter() - t0) / 20
+        ns = 200
+        t0 = time.perf_counter()
+        voc.transform(desc0[:ns], 4)
+        cpu_ms = 1e3 * (time.perf_counter() - t0) * len(desc0) / ns
+        obv, ofv = voc.transform(desc0[:ns], 4)
+        sbv, sfv = gv.transform(desc0[:ns].copy(), 4)
+        bow_extra = {"features": int(len(desc0)), "vocabulary": "synthetic k=10 L=4 (11 110 nodes)", "gpu_ms_per_frame": gpu_ms,
+                     "cpu_python_ms_per_frame_extrapolated": cpu_ms, "cpu_sample_features": ns,
+                     "identical_on_sample": list(obv.items()) == list(sbv.items()) and list(ofv.items()) == list(sfv.items())}
+
     if rank == 0:
         per_image, stereo_pp, B_frame = algorithmic_bytes(ORB["nfeatures"])
         per_image["octree"] = 4 * ncand + 4 * nkp
@@ -440,6 +467,7 @@ def run_b200_arm(args):
                                "workspace_bytes": sum(f.workspace_bytes() for f in fes), "rank0_cpu_affinity": numa if isinstance(numa, str) else f"{len(numa)} cpus: {numa[0]}-{numa[-1]}"},
         }
         line["dropin_single_frame_latency"] = dropin
+        line["bow_transform_8f_rank2"] = bow_extra
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

@@ -166,6 +166,26 @@ int b200orb_batch_candidate_count(b200orb_batch* b, int n_images, long long* tot
 int b200orb_batch_profile(b200orb_batch* b, int enable, int max_calls);
 int b200orb_batch_profile_read(b200orb_batch* b, float* ms_per_stage, int* n_calls, long long* n_pairs);
 
+/* ---------------------------------------------------------------------------------------------
+ * BoW transform of the descriptors -- the tree descent of
+ * TemplatedVocabulary.transform_feature (pyDBoW/TemplatedVocabulary.py:139-163) with FORB.distance
+ * (pyDBoW/FORB.py:31-33), called through Frame.compute_BoW (Frame.py:123-125).
+ * The vocabulary is given as arrays: node 0 is the root; the children of node i are child_ids[child_begin[i] ..
+ * child_begin[i+1]) in the reference's child order; node_desc is uint8[n_nodes][32] (row 0 unused).
+ * For every descriptor the transform returns the leaf it ends in (first strict minimum at every level) and the node
+ * it passes at depth nid_level = L - levelsup (-1 if its path is shorter).  Word ids, weights, L1 normalisation and
+ * the dictionaries are assembled by the caller exactly as the reference does (pyorbslam_b200/bow.py).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct b200orb_vocab b200orb_vocab;
+int b200orb_vocab_create(int n_nodes, const int32_t* child_begin, const int32_t* child_ids, const uint8_t* node_desc,
+                         int device, b200orb_vocab** out);
+void b200orb_vocab_destroy(b200orb_vocab* v);
+/* descriptors from host memory: uint8[n][32] */
+int b200orb_vocab_transform(b200orb_vocab* v, const uint8_t* desc, int n, int nid_level, int32_t* leaf_node, int32_t* level_node);
+/* descriptors still resident on the device from the extractor's last b200orb_extract (no upload) */
+int b200orb_vocab_transform_resident(b200orb_vocab* v, b200orb_extractor* e, int nid_level, int32_t* leaf_node,
+                                     int32_t* level_node);
+
 /* pinned host memory helpers for callers without their own allocator */
 int b200orb_host_alloc(void** p, size_t bytes);
 int b200orb_host_free(void* p);

@@ -358,6 +358,14 @@ struct b200orb_extractor {
     bool empty_last = false;
 };
 
+struct b200orb_vocab {
+    int device = 0, n_nodes = 0;
+    int *d_child_begin = nullptr, *d_child_ids = nullptr;
+    u8* d_node_desc = nullptr;
+    // scratch for transform calls
+    u8* d_desc = nullptr; int *d_leaf = nullptr, *d_level = nullptr; int cap = 0;
+};
+
 struct b200orb_batch {
     Engine eng;
     int P = 0, H = 0, W = 0;
@@ -897,6 +905,85 @@ int b200orb_batch_run_host(b200orb_batch* b, const uint8_t* h_left, const uint8_
     CU_TRY(cudaStreamSynchronize(b->s_out));
     CU_TRY(cudaStreamSynchronize(b->s_comp));
     return 0;
+}
+
+// ---------------------------------------------------------------- vocabulary (BoW transform)
+int b200orb_vocab_create(int n_nodes, const int32_t* child_begin, const int32_t* child_ids, const uint8_t* node_desc, int device,
+                         b200orb_vocab** out) {
+    if (!out) return fail(B200ORB_E_ARG, "out is NULL");
+    *out = nullptr;
+    if (n_nodes < 1 || !child_begin || !node_desc) return fail(B200ORB_E_ARG, "bad vocabulary arrays");
+    const int nch = child_begin[n_nodes];
+    if (child_begin[0] != 0 || nch < 0 || (nch > 0 && !child_ids)) return fail(B200ORB_E_ARG, "bad child CSR");
+    for (int i = 0; i < n_nodes; ++i)
+        if (child_begin[i + 1] < child_begin[i] || child_begin[i + 1] - child_begin[i] > 65535) return fail(B200ORB_E_ARG, "bad child CSR");
+    for (int c = 0; c < nch; ++c)
+        if (child_ids[c] <= 0 || child_ids[c] >= n_nodes) return fail(B200ORB_E_ARG, "child id out of range");
+    CU_TRY(cudaSetDevice(device));
+    b200orb_vocab* v = new b200orb_vocab;
+    v->device = device; v->n_nodes = n_nodes;
+    auto bail = [&](cudaError_t e, const char* what) { b200orb_vocab_destroy(v); return fail(B200ORB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); };
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&v->d_child_begin, (size_t)(n_nodes + 1) * 4)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void**)&v->d_child_ids, (size_t)std::max(nch, 1) * 4)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void**)&v->d_node_desc, (size_t)n_nodes * 32)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemcpy(v->d_child_begin, child_begin, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
+    if (nch && (e = cudaMemcpy(v->d_child_ids, child_ids, (size_t)nch * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
+    if ((e = cudaMemcpy(v->d_node_desc, node_desc, (size_t)n_nodes * 32, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
+    *out = v;
+    return 0;
+}
+
+void b200orb_vocab_destroy(b200orb_vocab* v) {
+    if (!v) return;
+    cudaSetDevice(v->device);
+    cudaFree(v->d_child_begin); cudaFree(v->d_child_ids); cudaFree(v->d_node_desc);
+    cudaFree(v->d_desc); cudaFree(v->d_leaf); cudaFree(v->d_level);
+    delete v;
+}
+
+static int vocab_run(b200orb_vocab* v, const u8* d_desc, int n, int nid_level, int32_t* leaf_node, int32_t* level_node, cudaStream_t st) {
+    if (n > v->cap) {
+        cudaFree(v->d_leaf); cudaFree(v->d_level); cudaFree(v->d_desc);
+        v->d_leaf = v->d_level = nullptr; v->d_desc = nullptr; v->cap = 0;
+        CU_TRY(cudaMalloc((void**)&v->d_leaf, (size_t)n * 4));
+        CU_TRY(cudaMalloc((void**)&v->d_level, (size_t)n * 4));
+        CU_TRY(cudaMalloc((void**)&v->d_desc, (size_t)n * 32));
+        v->cap = n;
+    }
+    k_vocab_descend<<<(n + VOC_WARPS - 1) / VOC_WARPS, VOC_WARPS * 32, 0, st>>>(d_desc ? d_desc : v->d_desc, n, v->d_child_begin, v->d_child_ids,
+                                                                                v->d_node_desc, nid_level, v->d_leaf, v->d_level);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(leaf_node, v->d_leaf, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(level_node, v->d_level, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int b200orb_vocab_transform(b200orb_vocab* v, const uint8_t* desc, int n, int nid_level, int32_t* leaf_node, int32_t* level_node) {
+    if (!v || !leaf_node || !level_node || n < 0 || (n > 0 && !desc)) return fail(B200ORB_E_ARG, "bad argument");
+    if (n == 0) return 0;
+    CU_TRY(cudaSetDevice(v->device));
+    if (n > v->cap) {       // make room first so the upload has a target
+        cudaFree(v->d_leaf); cudaFree(v->d_level); cudaFree(v->d_desc);
+        v->d_leaf = v->d_level = nullptr; v->d_desc = nullptr; v->cap = 0;
+        CU_TRY(cudaMalloc((void**)&v->d_leaf, (size_t)n * 4));
+        CU_TRY(cudaMalloc((void**)&v->d_level, (size_t)n * 4));
+        CU_TRY(cudaMalloc((void**)&v->d_desc, (size_t)n * 32));
+        v->cap = n;
+    }
+    CU_TRY(cudaMemcpy(v->d_desc, desc, (size_t)n * 32, cudaMemcpyHostToDevice));
+    return vocab_run(v, nullptr, n, nid_level, leaf_node, level_node, nullptr);
+}
+
+int b200orb_vocab_transform_resident(b200orb_vocab* v, b200orb_extractor* e, int nid_level, int32_t* leaf_node, int32_t* level_node) {
+    if (!v || !e || !leaf_node || !level_node) return fail(B200ORB_E_ARG, "NULL argument");
+    if (e->n < 0) return fail(B200ORB_E_STATE, "no extract() call yet");
+    if (e->n == 0) return 0;
+    if (e->eng.device != v->device) return fail(B200ORB_E_ARG, "vocabulary and extractor live on different devices");
+    CU_TRY(cudaSetDevice(v->device));
+    return vocab_run(v, e->d_desc, e->n, nid_level, leaf_node, level_node, e->st);
 }
 
 int b200orb_host_alloc(void** p, size_t bytes) {

@@ -423,3 +423,42 @@ __global__ void __launch_bounds__(MC_THREADS) k_median_cull(const int* __restric
         if (d >= 0 && !((float)d < thDist)) { uRight[(size_t)pair * out_stride + i] = -1.f; depth[(size_t)pair * out_stride + i] = -1.f; }
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// SURVEY.md 8(f) rank 2 -- BoW transform of the descriptors: the tree descent of
+// pyDBoW/TemplatedVocabulary.py:139-163 (transform_feature).  One warp per descriptor; at every level lane c
+// computes the Hamming distance to child c (FORB.distance, pyDBoW/FORB.py:31-33, as __popc over 2 x 16-byte loads)
+// and the warp takes the minimum of (dist << 8 | c): the reference's "first strict minimum in child order".
+// Outputs per feature: the leaf it ends in and the node it passes at depth `nid_level` (-1 if its path is shorter);
+// the weighting / dictionary assembly (and the reference's stale-node-id quirk) stay on the host.
+// ------------------------------------------------------------------------------------------------
+#define VOC_WARPS 8
+__global__ void __launch_bounds__(VOC_WARPS * 32) k_vocab_descend(const u8* __restrict__ desc, int n, const int* __restrict__ child_begin,
+                                                                  const int* __restrict__ child_ids, const u8* __restrict__ node_desc,
+                                                                  int nid_level, int* __restrict__ leaf_node, int* __restrict__ level_node) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * VOC_WARPS + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const uint4* dp = reinterpret_cast<const uint4*>(desc + (size_t)i * 32);
+    const uint4 f0 = dp[0], f1 = dp[1];
+    int node = 0, level = 0, at_level = -1;
+    for (;;) {
+        const int cb = child_begin[node], ce = child_begin[node + 1];
+        if (cb == ce) break;                                  // is_leaf()
+        unsigned best = 0xffffffffu;
+        for (int c = cb + lane; c < ce; c += 32) {
+            const int id = child_ids[c];
+            const uint4* np = reinterpret_cast<const uint4*>(node_desc + (size_t)id * 32);
+            const uint4 a = __ldg(np), b = __ldg(np + 1);
+            const unsigned d = __popc(f0.x ^ a.x) + __popc(f0.y ^ a.y) + __popc(f0.z ^ a.z) + __popc(f0.w ^ a.w) +
+                               __popc(f1.x ^ b.x) + __popc(f1.y ^ b.y) + __popc(f1.z ^ b.z) + __popc(f1.w ^ b.w);
+            best = min(best, (d << 16) | (unsigned)(c - cb));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        node = child_ids[cb + (int)(best & 0xffff)];
+        ++level;
+        if (level == nid_level) at_level = node;
+    }
+    if (lane == 0) { leaf_node[i] = node; level_node[i] = at_level; }
+}

@@ -5,6 +5,7 @@ Same constructor keywords, same nine methods, same return types: `operator_kd(im
 casters (opencv_type_casters.h:106-108, 205-240).  The results and the image pyramid also stay resident on the
 device, so the patched `Frame.compute_stereo_matches` (stereo.py) can match without re-uploading anything."""
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -12,6 +13,8 @@ from . import _lib
 
 
 class ORBextractor:
+    _live = weakref.WeakSet()      # extractors whose last results may still be resident (bow.py looks descriptors up here)
+
     def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0, reuse_identical_input=True):
         """reuse_identical_input: the reference's Frame.copy() runs the whole Frame constructor again on the same two
         images (Frame.py:75-77, called at Tracking.py:267,306), i.e. it extracts every tracked frame twice.  When the image
@@ -27,6 +30,7 @@ class ORBextractor:
         _lib.check(_lib.lib().b200orb_extractor_create(int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST),
                                                        int(minThFAST), int(device), C.byref(h)))
         self._h = h
+        ORBextractor._live.add(self)
         self._nlevels = int(nlevels)
         self._last_desc = None      # identity token: the descriptor array handed out by the last operator_kd
         self._last_n = -1

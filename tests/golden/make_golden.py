@@ -76,6 +76,35 @@ def main():
     np.savez_compressed(os.path.join(HERE, "hires_extract_digest.npz"), image_sha=sha(big), n=len(k4), kps_sha=sha(k4),
                         desc_sha=sha(d4), per_level=np.bincount(k4[:, 5].astype(int), minlength=12))
     print("hires", len(k4))
+    bow_case()
+
+
+def bow_case():
+    """the reference's own pyDBoW classes on a small synthetic vocabulary."""
+    import tempfile
+    from pyDBoW.TemplatedVocabulary import TemplatedVocabulary   # the reference's own class
+    from oracle.bow_py import make_vocab_text
+    text = make_vocab_text()
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        f.write(text)
+        path = f.name
+    voc = TemplatedVocabulary(k=5, L=3, weighting="TF_IDF", scoring="L1_NORM")      # System.py:38
+    assert voc.load_from_text_file(path)
+    os.unlink(path)
+    L, _ = make_stereo_pair(7, 240, 640)
+    _, desc = RefExtractor(1000, 1.2, 6, 20, 7).extract_arrays(L)
+    desc = desc[:400]
+    out = {}
+    for lu in (4, 2, 1):
+        bv, fv = voc.transform(desc, lu)
+        out[f"bv_keys_{lu}"] = np.array(list(bv.keys()), np.int64)
+        out[f"bv_vals_{lu}"] = np.array(list(bv.values()), np.float64)
+        out[f"fv_keys_{lu}"] = np.array(list(fv.keys()), np.int64)
+        out[f"fv_lens_{lu}"] = np.array([len(v) for v in fv.values()], np.int64)
+        out[f"fv_idx_{lu}"] = np.array([i for v in fv.values() for i in v], np.int64)
+    np.savez_compressed(os.path.join(HERE, "bow_small.npz"), vocab_sha=hashlib.sha256(text.encode()).hexdigest(), desc=desc,
+                        n_nodes=len(voc.nodes), n_words=len(voc.words), **out)
+    print("bow", len(voc.nodes), "nodes", len(voc.words), "words", {k: len(v) for k, v in out.items() if k.startswith("bv_keys")})
 
 
 if __name__ == "__main__":
