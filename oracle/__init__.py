@@ -25,7 +25,8 @@ def build(force=False):
     srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.cpp", "cvprims.hpp")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
-        subprocess.check_call(["make", "-s", "-C", _HERE, os.path.join(_HERE, "liborb_oracle.so")])
+        import sys
+        subprocess.check_call(["make", "-s", "-C", _HERE, os.path.join(_HERE, "liborb_oracle.so")], stdout=sys.stderr)
     return so
 
 

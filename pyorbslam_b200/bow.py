@@ -9,7 +9,6 @@ dictionary assembly stays in Python, reproducing the reference's accumulation or
     # Frame.compute_BoW() -> voc.transform(self.mDescriptors, 4) now runs on the GPU, same return value
 """
 import ctypes as C
-import weakref
 from collections import OrderedDict
 
 import numpy as np

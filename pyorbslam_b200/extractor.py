@@ -105,10 +105,17 @@ class ORBextractor:
             self._cached_desc = desc.copy()
         return kps, desc
 
+    _TUPLE_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4")])
+
     def operator_kd(self, image):
         kps, desc = self.extract_arrays(image)
-        rows = kps.tolist()
-        return [(r[0], r[1], r[2], r[3], r[4], int(r[5])) for r in rows], desc
+        # list of (float, float, float, float, float, int) tuples like the KeyPoint caster (opencv_type_casters.h:107);
+        # a structured array's tolist() builds them at C speed
+        rec = np.empty(len(kps), self._TUPLE_DTYPE)
+        for j, name in enumerate(("x", "y", "size", "angle", "response")):
+            rec[name] = kps[:, j]
+        rec["octave"] = kps[:, 5].astype(np.int32)
+        return rec.tolist(), desc
 
     # ---- GetImagePyramid, ORBextractor.h:84-86 through the Mat caster ----
     def level_size(self, level):
