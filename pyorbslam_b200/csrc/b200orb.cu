@@ -91,7 +91,8 @@ struct HostPlan {
     int fast_SP = 0, fast_SR = 0, fast_TP = 0, fast_TR = 0, fast_LC = 0;
     size_t fast_smem = 0;
     int oct_capN = 0, oct_capK = 0, oct_capC = 0;
-    size_t oct_smem = 0;
+    size_t oct_smem = 0, oct_node_stride = 0;
+    bool oct_global_nodes = false;
 };
 
 inline short sat_short(int v) { return (short)(v < -32768 ? -32768 : v > 32767 ? 32767 : v); }
@@ -183,12 +184,16 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
     if (hp.fast_smem > 200 * 1024) return fail(B200ORB_E_ARG, "cell size too large for the FAST kernel's shared memory");
     hp.oct_capN = round_up(maxcap + 8, 4);
     hp.oct_capC = round_up(std::max(maxcells, 1), 4);
-    const size_t fixed = oct_smem_bytes(hp.oct_capN, 0, hp.oct_capC);
+    // node arrays go to shared memory when they fit next to >= 2048 keys in ~200 KB, else to a global scratch block
+    const size_t nodeB = oct_node_bytes(hp.oct_capN);
+    hp.oct_global_nodes = nodeB + oct_base_bytes(2048, hp.oct_capC) > 200 * 1024;
+    const size_t fixed = oct_base_bytes(0, hp.oct_capC) + (hp.oct_global_nodes ? 0 : nodeB);
+    if (fixed + 1024 * 8 > 200 * 1024) return fail(B200ORB_E_ARG, "image has too many FAST cells per level for the octree kernel's shared memory");
     long long room = 100 * 1024 - (long long)fixed;
     if (room < 4096 * 8) room = 200 * 1024 - (long long)fixed;
-    if (room < 1024 * 8) return fail(B200ORB_E_ARG, "nfeatures too large for the octree kernel's shared memory");
-    hp.oct_capK = (int)(room / 8) & ~3;
-    hp.oct_smem = oct_smem_bytes(hp.oct_capN, hp.oct_capK, hp.oct_capC);
+    hp.oct_capK = (int)std::min<long long>(room / 8, 16384) & ~3;
+    hp.oct_node_stride = (nodeB + 255) & ~(size_t)255;
+    hp.oct_smem = oct_base_bytes(hp.oct_capK, hp.oct_capC) + (hp.oct_global_nodes ? 0 : nodeB);
     return 0;
 }
 
@@ -204,13 +209,14 @@ struct Engine {
     u32 *d_cand = nullptr, *d_scratch = nullptr, *d_lvlkp = nullptr;
     int *d_cellcnt = nullptr, *d_lvlcnt = nullptr, *d_status = nullptr, *d_rowstart = nullptr, *d_sorted = nullptr;
     int2* d_rmeta = nullptr;
+    unsigned char* d_octnodes = nullptr;     // node arrays of k_octree when they do not fit in shared memory
     XTab* d_xtab = nullptr;
     YTab* d_ytab = nullptr;
     long long bytes = 0;
 
     void release() {
         cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_cand); cudaFree(d_scratch); cudaFree(d_lvlkp);
-        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_sorted); cudaFree(d_rmeta); d_rmeta = nullptr;
+        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_sorted); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr;
         d_pyr = d_blur = nullptr; d_cand = d_scratch = d_lvlkp = nullptr; d_cellcnt = d_lvlcnt = d_status = d_rowstart = d_sorted = nullptr;
         d_xtab = nullptr; d_ytab = nullptr; planned = false; bytes = 0;
     }
@@ -237,6 +243,7 @@ struct Engine {
         TRY(alloc(&d_rowstart, (size_t)S * (P.lv[0].h + 1)));
         TRY(alloc(&d_sorted, (size_t)S * P.kp_total));
         TRY(alloc(&d_rmeta, (size_t)S * P.kp_total));
+        if (hp.oct_global_nodes) TRY(alloc(&d_octnodes, (size_t)S * P.nlevels * hp.oct_node_stride));
         TRY(alloc(&d_xtab, hp.xtab.size()));
         TRY(alloc(&d_ytab, hp.ytab.size()));
         CU_TRY(cudaMemset(d_pyr, 0, (size_t)S * P.pyr_bytes));
@@ -282,7 +289,7 @@ struct Engine {
         }
         if (evs) cudaEventRecord(evs[4], st);
         k_octree<<<dim3(P.nlevels, n), OCT_THREADS, hp.oct_smem, st>>>(P, d_cand, d_cellcnt, d_scratch, d_lvlkp, d_lvlcnt, hp.oct_capN,
-                                                                      hp.oct_capK, hp.oct_capC);
+                                                                      hp.oct_capK, hp.oct_capC, d_octnodes, hp.oct_node_stride);
         ++g_launches;
         if (evs) cudaEventRecord(evs[5], st);
         k_describe<<<dim3((P.kp_total + DESC_WARPS - 1) / DESC_WARPS, n), DESC_WARPS * 32, 0, st>>>(P, d_pyr, d_blur, d_lvlkp, d_lvlcnt, d_kps,

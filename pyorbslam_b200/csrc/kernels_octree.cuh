@@ -118,36 +118,34 @@ __device__ __forceinline__ int4 warp_partition(const u32* __restrict__ src, u32*
     return make_int4(c0, c1, c2, c3);
 }
 
-// shared-memory bytes needed for node capacity capN, key capacity capK, cell capacity capC
-__host__ __device__ inline size_t oct_smem_bytes(int capN, int capK, int capC) {
-    size_t b = 0;
-    b += (size_t)2 * capK * 4;                 // keys[2]
-    b += (size_t)2 * capN * (8 + 4 + 4 + 4);   // two node generations
-    b += (size_t)capN * 16;                    // child counts
-    b += (size_t)capN * 4 * 4;                 // rankOf, ordIdx, scanA, scanB
-    b += (size_t)capN * 8;                     // sort keys
-    b += (size_t)capC * 4;                     // cell offsets
-    b += 64 * 4;                               // misc
-    return b;
-}
+// bytes of the node arrays for node capacity capN (two node generations, child counts, rank/order/scan arrays, sort keys)
+__host__ __device__ inline size_t oct_node_bytes(int capN) { return (size_t)capN * (2 * (8 + 4 + 4 + 4) + 16 + 4 * 4 + 8); }
+// shared-memory bytes of the key buffers, cell offsets and scratch
+__host__ __device__ inline size_t oct_base_bytes(int capK, int capC) { return (size_t)2 * capK * 4 + (size_t)capC * 4 + 64 * 4; }
 
 __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ Plan P, const u32* __restrict__ cand,
                                                         const int* __restrict__ cellcnt, u32* __restrict__ scratch,
                                                         u32* __restrict__ lvl_kp, int* __restrict__ lvl_cnt,
-                                                        int capN, int capK, int capC) {
+                                                        int capN, int capK, int capC, unsigned char* gnodes, size_t gnode_stride) {
     extern __shared__ __align__(16) unsigned char oct_smem[];
     const int l = blockIdx.x, slot = blockIdx.y;
     const LevelGeom& G = P.lv[l];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // ---- carve shared memory ----
+    // ---- carve memory: key buffers, cell offsets and scratch always in shared memory; the node arrays (80 B per node)
+    // follow them in shared memory, or live in a global scratch block when the level quota is too large for that ----
     unsigned char* sp = oct_smem;
+    u32* smemKeys0 = (u32*)sp; sp += (size_t)capK * 4;
+    u32* smemKeys1 = (u32*)sp; sp += (size_t)capK * 4;
+    int* cellOfs = (int*)sp; sp += (size_t)capC * 4;
+    int* misc = (int*)sp; sp += 64 * 4;      // [0..32] scan tmp, [40] m
+    int* tmp = misc;
+    int* sh_m = misc + 40;
+    if (gnodes) sp = gnodes + ((size_t)slot * gridDim.x + l) * gnode_stride;
     unsigned long long* skeys = (unsigned long long*)sp; sp += (size_t)capN * 8;
     int4* cc = (int4*)sp; sp += (size_t)capN * 16;
     short4* boxA = (short4*)sp; sp += (size_t)capN * 8;
     short4* boxB = (short4*)sp; sp += (size_t)capN * 8;
-    u32* smemKeys0 = (u32*)sp; sp += (size_t)capK * 4;
-    u32* smemKeys1 = (u32*)sp; sp += (size_t)capK * 4;
     int* begA = (int*)sp; sp += (size_t)capN * 4;  int* begB = (int*)sp; sp += (size_t)capN * 4;
     int* cntA = (int*)sp; sp += (size_t)capN * 4;  int* cntB = (int*)sp; sp += (size_t)capN * 4;
     int* metaA = (int*)sp; sp += (size_t)capN * 4; int* metaB = (int*)sp; sp += (size_t)capN * 4;
@@ -155,10 +153,6 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     int* ordIdx = (int*)sp; sp += (size_t)capN * 4;
     int* scanA = (int*)sp; sp += (size_t)capN * 4;
     int* scanB = (int*)sp; sp += (size_t)capN * 4;
-    int* cellOfs = (int*)sp; sp += (size_t)capC * 4;
-    int* misc = (int*)sp;             // [0..8] scan tmp, [16] m, [17..] flags
-    int* tmp = misc;
-    int* sh_m = misc + 40;
 
     int* out_cnt = lvl_cnt + (size_t)slot * P.nlevels + l;
     u32* out_kp = lvl_kp + (size_t)slot * P.kp_total + G.kp_ofs;

@@ -163,6 +163,49 @@ def test_threshold_schedule_edge_cases_vs_oracle(ini, mn):
     _same(kg, dg, ko, do)
 
 
+def _adversarial(case):
+    rng = np.random.default_rng(77)
+    H, W = 300, 620
+    if case == "clustered":            # all corners in one small patch: deep, unbalanced tree, "no growth" termination
+        img = np.full((H, W), 120, np.uint8)
+        img[100:160, 400:470] = rng.integers(0, 256, (60, 70), dtype=np.uint8)
+        return img, (500, 1.2, 5, 20, 7)
+    if case == "periodic_ties":        # a lattice of identical blobs: equal responses everywhere (first-wins ties, NMS ties)
+        img = np.full((H, W), 60, np.uint8)
+        for y in range(24, H - 24, 12):
+            for x in range(24, W - 24, 12):
+                img[y:y + 4, x:x + 4] = 200
+        return img, (800, 1.2, 6, 20, 7)
+    if case == "quota_tiny":
+        return make_stereo_pair(14, H, W)[0], (10, 1.2, 4, 20, 7)
+    if case == "quota_zero":
+        return make_stereo_pair(14, H, W)[0], (0, 1.2, 3, 20, 7)
+    if case == "quota_huge":           # more features wanted than corners exist: every node ends as a leaf
+        return make_stereo_pair(14, H, W)[0], (30000, 1.2, 4, 20, 7)
+    if case == "two_blobs":            # two isolated corners
+        img = np.full((H, W), 30, np.uint8)
+        img[50:58, 60:68] = 250
+        img[200:206, 500:509] = 250
+        return img, (300, 1.2, 4, 20, 7)
+    if case == "lines":                # long edges: corners only at the ends, most cells retry and stay empty
+        img = np.full((H, W), 90, np.uint8)
+        img[:, 300:302] = 255
+        img[150:153, :] = 0
+        return img, (400, 1.2, 5, 20, 7)
+    raise KeyError(case)
+
+
+@pytest.mark.parametrize("case", ["clustered", "periodic_ties", "quota_tiny", "quota_zero", "quota_huge", "two_blobs", "lines"])
+def test_octree_and_nms_adversarial_inputs_vs_oracle(case):
+    img, params = _adversarial(case)
+    kg, dg = ORBextractor(*params).extract_arrays(img)
+    ko, do = O.OracleExtractor(*params).extract_arrays(img)
+    if len(ko) == 0:
+        assert len(kg) == 0
+    else:
+        _same(kg, dg, ko, do)
+
+
 def test_stage_by_stage_vs_oracle():
     img = make_stereo_pair(2)[0]
     g, o = ORBextractor(*KITTI), O.OracleExtractor(*KITTI)
