@@ -173,7 +173,7 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
     }
     P.pyr_bytes = pyr; P.blur_bytes = blr; P.ncells = std::max(cells, 1); P.cand_entries = std::max(cand, 4);
     P.kp_total = std::max(kpt, 1); P.fast_ctas = fctas; P.blur_ctas = bctas; P.max_cells_level = maxcells;
-    hp.fast_SP = round_up(3 + FAST_WARPS * maxw + 6 + 4, 4);
+    hp.fast_SP = round_up(15 + FAST_WARPS * maxw + 6 + 16, 16);   // rows are bulk-copied in 16-byte units from a 16-byte aligned start
     hp.fast_SR = maxh + 6;
     hp.fast_TP = round_up(maxw + 2, 4);
     hp.fast_TR = maxh + 2;

@@ -232,6 +232,35 @@ __global__ void __launch_bounds__(BLUR_WARPS * 32) k_blur(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA bulk-copy helpers (cp.async.bulk global -> shared with mbarrier completion; SASS: UBLKCP + SYNCS).
+// Used to stage the FAST strip: the copy engine moves whole rows while the warps prepare their tiles, and nobody
+// spends LSU instructions or registers on the staging.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// bounded wait: a byte-count mistake must end in a trap, never in a hung GPU
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
+    u32 done = 0;
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2: FAST-9/16 per 30-px cell with the iniThFAST -> minThFAST retry (ORBextractor.cpp:788-828) and
 // cv::FAST's cell-confined strict non-max suppression.
 // One CTA = one strip of FAST_WARPS consecutive cells of a cell row: the raw strip (cells + 3-px rim) is
@@ -354,19 +383,25 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_con
     const int sx0 = ORB_DET_ORIGIN + j0 * G.wCell;
     const int sx1 = min(ORB_DET_ORIGIN + min(j0 + FAST_WARPS, G.nCols) * G.wCell + 6, G.maxBX);
     const int srows = maxY - iniY;
-    const int bufx0 = sx0 + ORB_EDGE, ax0 = bufx0 & ~3, shift = bufx0 - ax0;
-    if (!rowSkip && sx1 > sx0) {
-        const int nw = (shift + (sx1 - sx0) + 3) >> 2;
+    // stage the strip with the copy engine: one bulk copy per row (16-byte aligned on both sides), completion counted on an
+    // mbarrier; meanwhile every warp zeroes its score tile
+    __shared__ unsigned long long strip_bar;
+    const int bufx0 = sx0 + ORB_EDGE, ax0 = bufx0 & ~15, shift = bufx0 - ax0;
+    const bool have_strip = !rowSkip && sx1 > sx0;
+    const u32 row_bytes = have_strip ? (u32)((shift + (sx1 - sx0) + 15) & ~15) : 0u;
+    if (threadIdx.x == 0) mbar_init(&strip_bar, 1);
+    __syncthreads();
+    if (have_strip && warp == 0) {
+        if (lane == 0) mbar_expect_tx(&strip_bar, row_bytes * (u32)srows);
+        __syncwarp();
         const u8* src = pyr + (size_t)slot * P.pyr_bytes + G.pyr_ofs + (size_t)(iniY + ORB_EDGE) * G.pitch + ax0;
-        for (int i = threadIdx.x; i < nw * srows; i += FAST_WARPS * 32) {
-            const int r = i / nw, c = i - r * nw;
-            *reinterpret_cast<u32*>(strip + r * SP + 4 * c) = *reinterpret_cast<const u32*>(src + (size_t)r * G.pitch + 4 * c);
-        }
+        for (int r = lane; r < srows; r += 32) bulk_g2s(strip + r * SP, src + (size_t)r * G.pitch, row_bytes, &strip_bar);
     }
-    // zero this warp's score tile while the strip loads are in flight (the rim is what "outside the window scores 0" means)
+    // zero this warp's score tile while the copies are in flight (the rim is what "outside the window scores 0" means)
     u8* tile = smem + SP * SR + warp * (TP * TR);
     for (int i = lane; i < (TP * TR) >> 2; i += 32) reinterpret_cast<u32*>(tile)[i] = 0u;
-    __syncthreads();
+    if (have_strip) mbar_wait(&strip_bar, 0);
+    __syncwarp();
 
     const int j = j0 + warp;
     if (j >= G.nCols) return;
