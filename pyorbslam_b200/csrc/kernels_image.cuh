@@ -264,10 +264,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
 // K2: FAST-9/16 per 30-px cell with the iniThFAST -> minThFAST retry (ORBextractor.cpp:788-828) and
 // cv::FAST's cell-confined strict non-max suppression.
 // One CTA = one strip of FAST_WARPS consecutive cells of a cell row: the raw strip (cells + 3-px rim) is
-// staged in shared memory once with 32-bit loads, then one warp per cell computes the threshold-free
-// corner score, suppresses non-maxima inside its own detection window, decides the threshold
-// (post-NMS list empty at iniThFAST -> use minThFAST) and emits the survivors in row-major order with
-// ballot-ranked stores.  Output per cell: count + packed (x | y<<12 | score<<24), x/y relative to (16,16).
+// staged in shared memory once by the copy engine (one cp.async.bulk per row, mbarrier completion), then one
+// warp per cell runs quick reject -> compacted work list -> exact corner strength -> strict NMS inside its own
+// detection window, first at iniThFAST and again at minThFAST only if nothing survived, and emits the
+// survivors in row-major order with ballot-ranked stores.
+// Output per cell: count + packed (x | y<<12 | score<<24), x/y relative to the (16,16) detection origin.
 // ------------------------------------------------------------------------------------------------
 #define FAST_WARPS 8
 
