@@ -186,6 +186,12 @@ int b200orb_vocab_transform(b200orb_vocab* v, const uint8_t* desc, int n, int ni
 int b200orb_vocab_transform_resident(b200orb_vocab* v, b200orb_extractor* e, int nid_level, int32_t* leaf_node,
                                      int32_t* level_node);
 
+/* SURVEY.md 8(f) rank 1, first piece: all-pairs Hamming distances out[i*nB + j] = popcount(A[i] xor B[j]) between two sets of
+ * 32-byte descriptors in host memory -- what ORBMatcher.descriptor_distance (ORBMatcher.py:12-14) computes one pair at a time
+ * inside search_by_BoW_kf_f / search_by_BoW_kf_kf (ORBMatcher.py:21-213).  The greedy matching logic stays on the host
+ * (pyorbslam_b200/matcher.py) and looks distances up in this matrix. */
+int b200orb_hamming_matrix(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, uint16_t* out);
+
 /* pinned host memory helpers for callers without their own allocator */
 int b200orb_host_alloc(void** p, size_t bytes);
 int b200orb_host_free(void* p);

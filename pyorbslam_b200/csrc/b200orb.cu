@@ -993,6 +993,29 @@ int b200orb_vocab_transform_resident(b200orb_vocab* v, b200orb_extractor* e, int
     return vocab_run(v, e->d_desc, e->n, nid_level, leaf_node, level_node, e->st);
 }
 
+// ---------------------------------------------------------------- all-pairs Hamming (first piece)
+int b200orb_hamming_matrix(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, uint16_t* out) {
+    if (nA < 0 || nB < 0) return fail(B200ORB_E_ARG, "negative size");
+    if (nA == 0 || nB == 0) return 0;
+    if (!A || !B || !out) return fail(B200ORB_E_ARG, "NULL argument");
+    CU_TRY(cudaSetDevice(device));
+    u8 *dA = nullptr, *dB = nullptr;
+    unsigned short* dO = nullptr;
+    auto done = [&](int rc) { cudaFree(dA); cudaFree(dB); cudaFree(dO); return rc; };
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&dA, (size_t)nA * 32)) != cudaSuccess || (e = cudaMalloc((void**)&dB, (size_t)nB * 32)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&dO, (size_t)nA * nB * 2)) != cudaSuccess)
+        return done(fail(B200ORB_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)));
+    if ((e = cudaMemcpy(dA, A, (size_t)nA * 32, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dB, B, (size_t)nB * 32, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return done(fail(B200ORB_E_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e)));
+    k_hamming_matrix<<<dim3((nB + 127) / 128, (nA + HM_ROWS - 1) / HM_ROWS), 128>>>(dA, nA, dB, nB, dO);
+    ++g_launches;
+    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpy(out, dO, (size_t)nA * nB * 2, cudaMemcpyDeviceToHost)) != cudaSuccess)
+        return done(fail(B200ORB_E_CUDA, std::string("k_hamming_matrix: ") + cudaGetErrorString(e)));
+    return done(0);
+}
+
 int b200orb_host_alloc(void** p, size_t bytes) {
     if (!p) return fail(B200ORB_E_ARG, "p is NULL");
     CU_TRY(cudaHostAlloc(p, bytes, cudaHostAllocDefault));

@@ -462,3 +462,27 @@ __global__ void __launch_bounds__(VOC_WARPS * 32) k_vocab_descend(const u8* __re
     }
     if (lane == 0) { leaf_node[i] = node; level_node[i] = at_level; }
 }
+
+// ------------------------------------------------------------------------------------------------
+// SURVEY.md 8(f) rank 1 (first piece) -- all-pairs Hamming distances between two descriptor sets, the quantity
+// ORBMatcher.descriptor_distance (ORBMatcher.py:12-14) computes one pair at a time in Python inside the
+// search_by_BoW_* loops.  Thread j holds descriptor B_j in registers and walks HM_ROWS rows of A (warp-uniform
+// loads); distances are written as uint16 (0..256), coalesced along j.
+// ------------------------------------------------------------------------------------------------
+#define HM_ROWS 16
+__global__ void __launch_bounds__(128) k_hamming_matrix(const u8* __restrict__ A, int nA, const u8* __restrict__ B, int nB,
+                                                        unsigned short* __restrict__ out) {
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    const int i0 = blockIdx.y * HM_ROWS;
+    if (j >= nB) return;
+    const uint4* bp = reinterpret_cast<const uint4*>(B + (size_t)j * 32);
+    const uint4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+#pragma unroll 4
+    for (int i = i0; i < min(i0 + HM_ROWS, nA); ++i) {
+        const uint4* ap = reinterpret_cast<const uint4*>(A + (size_t)i * 32);
+        const uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+        const unsigned d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+        out[(size_t)i * nB + j] = (unsigned short)d;
+    }
+}

@@ -77,6 +77,7 @@ def main():
                         desc_sha=sha(d4), per_level=np.bincount(k4[:, 5].astype(int), minlength=12))
     print("hires", len(k4))
     bow_case()
+    matcher_case()
 
 
 def bow_case():
@@ -105,6 +106,24 @@ def bow_case():
     np.savez_compressed(os.path.join(HERE, "bow_small.npz"), vocab_sha=hashlib.sha256(text.encode()).hexdigest(), desc=desc,
                         n_nodes=len(voc.nodes), n_words=len(voc.words), **out)
     print("bow", len(voc.nodes), "nodes", len(voc.words), "words", {k: len(v) for k, v in out.items() if k.startswith("bv_keys")})
+
+
+def matcher_case():
+    """SURVEY.md 8(f) rank 1 (first piece): the reference's own ORBMatcher.search_by_BoW_* on a synthetic two-view case."""
+    from ORBMatcher import ORBMatcher     # the reference's own class
+    from oracle.matcher_py import make_case
+    out = {}
+    for tag, (ratio, ori) in {"a": (0.7, True), "b": (1, True), "c": (0.9, False)}.items():
+        A, B = make_case()
+        m = ORBMatcher(ratio, ori)
+        n1, v1 = m.search_by_BoW_kf_f(A, B)
+        n2, v2 = m.search_by_BoW_kf_kf(A, B)
+        out[f"kf_f_n_{tag}"] = n1
+        out[f"kf_f_{tag}"] = np.array([-1 if p is None else p.uid for p in v1], np.int64)
+        out[f"kf_kf_n_{tag}"] = n2
+        out[f"kf_kf_{tag}"] = np.array([-1 if p is None else p.uid for p in v2], np.int64)
+    np.savez_compressed(os.path.join(HERE, "matcher_small.npz"), **out)
+    print("matcher", {k: int(v) for k, v in out.items() if "_n_" in k})
 
 
 if __name__ == "__main__":
