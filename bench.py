@@ -180,7 +180,7 @@ def run_reference_arm(args):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(pairs, chunk):
@@ -474,9 +474,31 @@ def run_b200_arm(args):
         line["bow_transform_8f_rank2"] = bow_extra
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner at WARN level, nvcc-built
+    helpers, ...) write to file descriptor 1 directly, so fd 1 is pointed at stderr for the whole run and the JSON line
+    goes to a saved duplicate of the original stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -500,6 +522,7 @@ def main():
     args.pairs = args.pairs or wl["pairs"]
     args.chunk = args.chunk or wl["chunk"]
     args.e2e_pairs = min(args.e2e_pairs, args.pairs)
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
