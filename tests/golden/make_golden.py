@@ -122,6 +122,22 @@ def matcher_case():
         out[f"kf_f_{tag}"] = np.array([-1 if p is None else p.uid for p in v1], np.int64)
         out[f"kf_kf_n_{tag}"] = n2
         out[f"kf_kf_{tag}"] = np.array([-1 if p is None else p.uid for p in v2], np.int64)
+    # the two frame projection searches, on top of the reference's own Frame.get_features_in_area / assign_features_to_grid
+    from oracle.matcher_py import make_projection_case
+
+    def ref_assign(f):
+        f.pos_in_grid = lambda kps, _f=f: Frame.pos_in_grid(_f, kps)
+        Frame.assign_features_to_grid(f)
+        return f.mGrid
+    for tag, (ratio, ori, th, motion) in {"p": (0.9, True, 15, (0.05, 0.0, 0.3)), "q": (0.8, False, 7, (0.0, 0.02, -0.9)),
+                                          "r": (1, True, 10, (0.4, 0.0, 0.0))}.items():
+        m = ORBMatcher(ratio, ori)
+        cur, last, local = make_projection_case(get_area=Frame.get_features_in_area, assign=ref_assign, motion=motion)
+        out[f"f_f_n_{tag}"] = m.search_by_projection_f_f(cur, last, th)
+        out[f"f_f_{tag}"] = np.array([-1 if p is None else p.uid for p in cur.mvpMapPoints], np.int64)
+        cur, last, local = make_projection_case(get_area=Frame.get_features_in_area, assign=ref_assign, motion=motion)
+        out[f"f_p_n_{tag}"] = m.search_by_projection_f_p(cur, local, float(th) / 5)
+        out[f"f_p_{tag}"] = np.array([-1 if p is None else p.uid for p in cur.mvpMapPoints], np.int64)
     np.savez_compressed(os.path.join(HERE, "matcher_small.npz"), **out)
     print("matcher", {k: int(v) for k, v in out.items() if "_n_" in k})
 
