@@ -178,8 +178,9 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
     hp.fast_TP = round_up(maxw + 2, 4);
     hp.fast_TR = maxh + 2;
     if (maxw > 63 || maxh > 63) return fail(B200ORB_E_ARG, "FAST cell larger than 63 px (level narrower than 62 px after the border?)");
-    hp.fast_LC = round_up(std::max(maxw * maxh, 2), 2);
-    hp.fast_smem = (size_t)hp.fast_SP * hp.fast_SR + (size_t)FAST_WARPS * hp.fast_TP * hp.fast_TR + (size_t)FAST_WARPS * hp.fast_LC * 2;
+    hp.fast_LC = round_up(std::max(maxw * maxh, 2), 8);            // 16-byte multiple: the row bitmaps behind the lists are read as uint2 / uint4
+    hp.fast_smem = (size_t)hp.fast_SP * hp.fast_SR + (size_t)FAST_WARPS * hp.fast_TP * hp.fast_TR + (size_t)FAST_WARPS * hp.fast_LC * 2 +
+                   (size_t)FAST_WARPS * 1024;
     hp.fast_smem = (hp.fast_smem + 15) & ~(size_t)15;
     if (hp.fast_smem > 200 * 1024) return fail(B200ORB_E_ARG, "cell size too large for the FAST kernel's shared memory");
     hp.oct_capN = round_up(maxcap + 8, 4);
@@ -275,7 +276,8 @@ struct Engine {
             dim3 grid(((G.pitch >> 2) * ((G.rows + 1) / 2) + 255) / 256, n);
             // the word-window fast path needs the 4 columns of a thread to span <= 10 source bytes: scale < 2
             const int fast_ok = (double)P.lv[l - 1].w / G.w < 1.95 ? 1 : 0;
-            k_resize<<<grid, 256, 0, st>>>(P, l, fast_ok, d_pyr, d_xtab, d_ytab);
+            const unsigned wpr = (unsigned)(G.pitch >> 2), wpr_magic = (unsigned)((0x100000000ULL + wpr - 1) / wpr);
+            k_resize<<<grid, 256, 0, st>>>(P, l, fast_ok, wpr_magic, d_pyr, d_xtab, d_ytab);
             ++g_launches;
         }
         if (evs) cudaEventRecord(evs[2], st);

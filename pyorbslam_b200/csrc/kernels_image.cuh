@@ -65,24 +65,31 @@ __global__ void __launch_bounds__(256) k_border0(const __grid_constant__ Plan P,
 // (p[sx], p[sx+1]) byte pair of every column with one PRMT and form the horizontal interpolation with one 2-way dot
 // product (DP2A) against the packed 11-bit coefficients; two consecutive output rows usually share a source row.
 // Border threads (reflected, non-monotonic columns) and scale factors >= 2 take the per-byte path.
-__device__ __forceinline__ u32 rs_vert(int T0, int T1, int b0, int b1) {
-    return (u32)(((((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2) & 0xff);
+// Vertical step of cv::resize's fixed-point bilinear: ((b0 * (T0 >> 4) >> 16) + (b1 * (T1 >> 4) >> 16) + 2) >> 2.
+// b0s / b1s are the 11-bit row weights pre-shifted left by 16, so each ">> 16" product is one multiply-high with
+// accumulate (IMAD.HI, on the FMA pipe -- these kernels are bound by the ALU pipe).  The result is at most 255
+// (b0 + b1 == 2048, T >> 4 <= 32640), so no byte mask is needed.
+__device__ __forceinline__ u32 rs_vert(int T0, int T1, u32 b0s, u32 b1s) {
+    return (__umulhi((u32)T0 >> 4, b0s) + __umulhi((u32)T1 >> 4, b1s) + 2u) >> 2;
 }
 
-__global__ void __launch_bounds__(256, 6) k_resize(const __grid_constant__ Plan P, int l, int fast_ok, u8* __restrict__ pyr,
+__global__ void __launch_bounds__(256, 5) k_resize(const __grid_constant__ Plan P, int l, int fast_ok, u32 wpr_magic, u8* __restrict__ pyr,
                                                 const XTab* __restrict__ xtab, const YTab* __restrict__ ytab) {
     const LevelGeom& G = P.lv[l];
     const LevelGeom& S = P.lv[l - 1];
     const int slot = blockIdx.y;
     const int words_per_row = G.pitch >> 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int rp = idx / words_per_row;                     // row pair
+    int rp = (int)__umulhi((u32)idx, wpr_magic);            // row pair = idx / words_per_row via ceil(2^32 / d); may overshoot by one
+    if (rp * words_per_row > idx) --rp;
     const int by = rp << 1, bx = (idx - rp * words_per_row) << 2;
     if (by >= G.rows) return;
     const bool two = by + 1 < G.rows;
     u8* base = pyr + (size_t)slot * P.pyr_bytes;
     const u8* srcb = base + S.pyr_ofs;                       // bordered buffer of level l-1 (ROI at +19, +19)
     const YTab ya = ytab[G.ytab_ofs + by], yb = ytab[G.ytab_ofs + (two ? by + 1 : by)];
+    const u32 ab0 = (u32)(unsigned short)ya.b0 << 16, ab1 = (u32)(unsigned short)ya.b1 << 16;
+    const u32 bb0 = (u32)(unsigned short)yb.b0 << 16, bb1 = (u32)(unsigned short)yb.b1 << 16;
     const int4* tp = reinterpret_cast<const int4*>(xtab + G.xtab_ofs + bx);
     const int4 t01 = __ldg(tp), t23 = __ldg(tp + 1);
     const int sxs[4] = {t01.x, t01.z, t23.x, t23.z};
@@ -116,17 +123,17 @@ __global__ void __launch_bounds__(256, 6) k_resize(const __grid_constant__ Plan 
         hrow(ya.y0, Ta);
         hrow(ya.y1, Tb);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) va |= rs_vert(Ta[j], Tb[j], ya.b0, ya.b1) << (8 * j);
+        for (int j = 0; j < 4; ++j) va |= rs_vert(Ta[j], Tb[j], ab0, ab1) << (8 * j);
         if (two) {
             if (yb.y0 == ya.y1) {                              // usual case at scale 1.2: the rows overlap by one source row
                 hrow(yb.y1, Ta);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) vb |= rs_vert(Tb[j], Ta[j], yb.b0, yb.b1) << (8 * j);
+                for (int j = 0; j < 4; ++j) vb |= rs_vert(Tb[j], Ta[j], bb0, bb1) << (8 * j);
             } else {
                 if (yb.y0 != ya.y0) hrow(yb.y0, Ta);
                 if (yb.y1 != ya.y1) hrow(yb.y1, Tb);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) vb |= rs_vert(Ta[j], Tb[j], yb.b0, yb.b1) << (8 * j);
+                for (int j = 0; j < 4; ++j) vb |= rs_vert(Ta[j], Tb[j], bb0, bb1) << (8 * j);
             }
         }
     } else {
@@ -138,11 +145,11 @@ __global__ void __launch_bounds__(256, 6) k_resize(const __grid_constant__ Plan 
                 const int sx = sxs[k], a0 = (int)(cf[k] & 0xffff), a1 = (int)(cf[k] >> 16);
                 const u8* r0 = roi + (size_t)ya.y0 * S.pitch + sx;
                 const u8* r1 = roi + (size_t)ya.y1 * S.pitch + sx;
-                va |= rs_vert(r0[0] * a0 + r0[1] * a1, r1[0] * a0 + r1[1] * a1, ya.b0, ya.b1) << (8 * k);
+                va |= rs_vert(r0[0] * a0 + r0[1] * a1, r1[0] * a0 + r1[1] * a1, ab0, ab1) << (8 * k);
                 if (two) {
                     const u8* q0 = roi + (size_t)yb.y0 * S.pitch + sx;
                     const u8* q1 = roi + (size_t)yb.y1 * S.pitch + sx;
-                    vb |= rs_vert(q0[0] * a0 + q0[1] * a1, q1[0] * a0 + q1[1] * a1, yb.b0, yb.b1) << (8 * k);
+                    vb |= rs_vert(q0[0] * a0 + q0[1] * a1, q1[0] * a0 + q1[1] * a1, bb0, bb1) << (8 * k);
                 }
             }
         }
@@ -290,6 +297,93 @@ __device__ __forceinline__ bool fast_quick(const u8* p, int SP, int t) {
     return br | dk;
 }
 
+// The same reject for FOUR consecutive pixels of a row (address o, o & 3 == AL) from aligned 32-bit shared-memory words:
+// the five operands (centre, x-3, x+3, y-3, y+3) are cut out of the words with funnel shifts, spread into 16-bit lanes
+// (pixels 0|2 and 1|3) and tested two pixels per instruction with the packed min / max (VIMNMX.U16x2):
+//   bright <=> min(max(a,b), max(c,d)) > v + t,   dark <=> max(min(a,b), min(c,d)) < v - t
+// and  m + (0x7fff - t) - v  sets bit 15 of a lane  <=>  m - v > t  (lanes stay inside [0x7e01, 0x80fe]: no carry, no borrow).
+// Returns a nibble: bit k = pixel k passes.
+__device__ __forceinline__ u32 fast_quick2(u32 v, u32 a, u32 b, u32 c, u32 d, u32 Kt) {
+    const u32 mn = __vminu2(__vmaxu2(a, b), __vmaxu2(c, d));
+    const u32 mx = __vmaxu2(__vminu2(a, b), __vminu2(c, d));
+    return ((mn + Kt - v) | (v + Kt - mx)) & 0x80008000u;
+}
+template <int OFS>
+__device__ __forceinline__ u32 fast_cut4(const u32* w) {       // bytes OFS .. OFS + 3 of the word array
+    if constexpr ((OFS & 3) == 0) return w[OFS >> 2];
+    else return __funnelshift_r(w[OFS >> 2], w[(OFS >> 2) + 1], 8 * (OFS & 3));
+}
+template <int AL>
+__device__ __forceinline__ u32 fast_quick4(const u8* o, int SP, u32 Kt) {
+    const u32* wc = reinterpret_cast<const u32*>(o - AL - 4);            // centre row: bytes -AL-4 .. of the pixel group
+    const u32* wt = reinterpret_cast<const u32*>(o - AL + 3 * SP);
+    const u32* wb = reinterpret_cast<const u32*>(o - AL - 3 * SP);
+    const u32 L = fast_cut4<AL + 1>(wc), C = fast_cut4<AL + 4>(wc), R = fast_cut4<AL + 7>(wc);
+    const u32 T = fast_cut4<AL>(wt), B = fast_cut4<AL>(wb);
+    const u32 pe = fast_quick2(__byte_perm(C, 0, 0x4240), __byte_perm(T, 0, 0x4240), __byte_perm(B, 0, 0x4240),
+                               __byte_perm(R, 0, 0x4240), __byte_perm(L, 0, 0x4240), Kt);      // pixels 0 | 2
+    const u32 po = fast_quick2(__byte_perm(C, 0, 0x4341), __byte_perm(T, 0, 0x4341), __byte_perm(B, 0, 0x4341),
+                               __byte_perm(R, 0, 0x4341), __byte_perm(L, 0, 0x4341), Kt);      // pixels 1 | 3
+    const u32 x = (pe >> 15) | (po >> 14);
+    return (x | (x >> 14)) & 0xfu;
+}
+
+// Phase 1 of a cell (detection window up to 63 x 63): a lane tests 4 consecutive pixels of a row -- 8 lanes per row and 4 rows
+// per step for windows up to 32 px wide, 16 lanes per row and 2 rows per step beyond -- and drops the nibble into a per-row
+// bitmap; then lane r turns the masks of rows r and r + 32 into list entries at the offsets an exclusive warp scan of the
+// row counts gives: row-major order by construction, no per-pixel ballot.
+template <int AL>
+__device__ __forceinline__ int fast_phase1_quads(const u8* s0, int SP, int cw, int ch, int T, u8* rowbits, unsigned short* list, int lane) {
+    const bool wide = cw > 32;
+    const int sh = wide ? 4 : 3, r = lane >> sh, q = lane & ((1 << sh) - 1), rstep = 32 >> sh;
+    const u32 Kt = (u32)(0x7fff - T) * 0x00010001u;
+    if (4 * q < cw) {
+        const u8* o = s0 + r * SP + 4 * q;
+        u8* rb = rowbits + (r << sh) + q;
+#pragma unroll 2
+        for (int y = r; y < ch; y += rstep, o += rstep * SP, rb += 32) *rb = (u8)fast_quick4<AL>(o, SP, Kt);
+    }
+    __syncwarp();
+    // nibble bytes -> 64-bit row masks of rows lane and lane + 32
+    auto squeeze = [](u32 w) { u32 a = (w | (w >> 4)) & 0x00ff00ffu; return (a | (a >> 8)) & 0xffffu; };
+    const unsigned long long colmask = (1ull << cw) - 1ull;
+    unsigned long long m[2] = {0ull, 0ull};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int row = lane + 32 * h;
+        if (row < ch) {
+            if (wide) {
+                const uint4 w = *reinterpret_cast<const uint4*>(rowbits + row * 16);
+                m[h] = (unsigned long long)(squeeze(w.x) | (squeeze(w.y) << 16)) | ((unsigned long long)(squeeze(w.z) | (squeeze(w.w) << 16)) << 32);
+            } else {
+                const uint2 w = *reinterpret_cast<const uint2*>(rowbits + row * 8);
+                m[h] = squeeze(w.x) | (squeeze(w.y) << 16);
+            }
+            m[h] &= colmask;
+        }
+    }
+    int base = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (h == 1 && ch <= 32) break;
+        const int c = __popcll(m[h]);
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        unsigned short* w = list + base + (incl - c);
+        const int ybits = (lane + 32 * h) << 6;
+        u32 lo = (u32)m[h], hi = (u32)(m[h] >> 32);
+        while (lo) { *w++ = (unsigned short)(ybits | (__ffs(lo) - 1)); lo &= lo - 1; }
+        while (hi) { *w++ = (unsigned short)(ybits | (__ffs(hi) + 31)); hi &= hi - 1; }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    return base;
+}
+
 // 9-of-16 segment test (strictly brighter than v+t or strictly darker than v-t on 9 contiguous ring pixels).
 // The 32 comparisons are done two ring pixels at a time in 16-bit lanes (SWAR): with pair = p_k | p_{k+8} << 16,
 //   pair + (0x7fff - hi) per lane sets bit 15 of a lane  <=>  p > hi        (no carry: p + 0x7fff - hi < 0x10000)
@@ -416,6 +510,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_con
         return;
     }
     unsigned short* list = reinterpret_cast<unsigned short*>(smem + SP * SR + FAST_WARPS * (TP * TR)) + warp * LC;
+    u8* rowbits = smem + SP * SR + FAST_WARPS * (TP * TR) + FAST_WARPS * LC * 2 + warp * 1024;  // 64 rows x 16 nibble bytes
     const u8* s0 = strip + 3 * SP + (iniX - sx0) + shift + 3;
 
     // Threshold schedule = the reference's own (ORBextractor.cpp:808-815): detect at iniThFAST; only if nothing survives
@@ -427,27 +522,11 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_con
     for (int attempt = 0; attempt < 2; ++attempt) {
         // ---- phase 1 ----
         int nA = 0;
-        if (cw <= 32) {             // the usual case (30-px cells): one row per step, pointer walks down the strip
-            const bool inx = lane < cw;
-            const u8* pr = s0 + lane;
-            unsigned short* lw = list;
-#pragma unroll 4
-            for (int y = 0; y < ch; ++y, pr += SP) {
-                const bool pass = inx && fast_quick(pr, SP, T);
-                const u32 m = __ballot_sync(0xffffffffu, pass);
-                if (pass) lw[__popc(m & lt)] = (unsigned short)((y << 6) | lane);
-                lw += __popc(m);
-            }
-            nA = (int)(lw - list);
-        } else {
-            for (int y = 0; y < ch; ++y)
-                for (int xb = 0; xb < cw; xb += 32) {
-                    const int x = xb + lane;
-                    const bool pass = x < cw && fast_quick(s0 + y * SP + x, SP, T);
-                    const u32 m = __ballot_sync(0xffffffffu, pass);
-                    if (pass) list[nA + __popc(m & lt)] = (unsigned short)((y << 6) | x);
-                    nA += __popc(m);
-                }
+        switch ((int)(reinterpret_cast<size_t>(s0) & 3)) {     // four pixels per lane, see fast_phase1_quads
+            case 0: nA = fast_phase1_quads<0>(s0, SP, cw, ch, T, rowbits, list, lane); break;
+            case 1: nA = fast_phase1_quads<1>(s0, SP, cw, ch, T, rowbits, list, lane); break;
+            case 2: nA = fast_phase1_quads<2>(s0, SP, cw, ch, T, rowbits, list, lane); break;
+            default: nA = fast_phase1_quads<3>(s0, SP, cw, ch, T, rowbits, list, lane); break;
         }
         __syncwarp();
         // ---- phases 2 + 3: exact corner strength of every quick-test survivor; corner at T <=> best > T <=> score >= T
