@@ -87,6 +87,7 @@ int make_params(int nfeatures, float scaleFactor, int nlevels, int iniTh, int mi
 struct HostPlan {
     Plan P;
     std::vector<XTab> xtab;
+    std::vector<XGroup> xgrp;
     std::vector<YTab> ytab;
     int fast_SP = 0, fast_SR = 0, fast_TP = 0, fast_TR = 0, fast_LC = 0;
     size_t fast_smem = 0;
@@ -104,7 +105,7 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
     memset(&P, 0, sizeof(P));
     P.nlevels = prm.nlevels; P.H = H; P.W = W; P.iniTh = prm.iniTh; P.minTh = prm.minTh;
     for (int v = 0; v < 16; ++v) P.umax[v] = prm.umax[v];
-    hp.xtab.clear(); hp.ytab.clear();
+    hp.xtab.clear(); hp.ytab.clear(); hp.xgrp.clear();
     int pyr = 0, blr = 0, cells = 0, cand = 0, kpt = 0, fctas = 0, bctas = 0, maxw = 0, maxh = 0, maxcap = 0, maxcells = 0;
     for (int l = 0; l < prm.nlevels; ++l) {
         LevelGeom& G = P.lv[l];
@@ -169,6 +170,26 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
             const int bw = G.w + 2 * ORB_EDGE;
             for (int bx = 0; bx < G.pitch; ++bx) hp.xtab.push_back(xr[refl(std::min(bx, bw - 1) - ORB_EDGE, G.w)]);
             for (int by = 0; by < G.rows; ++by) hp.ytab.push_back(yr[refl(by - ORB_EDGE, G.h)]);
+            // per-thread (4-column) entries of the word-window path; index = xtab_ofs / 4 + group
+            hp.xgrp.resize(hp.xtab.size() / 4);
+            for (int g = 0; g < G.pitch / 4; ++g) {
+                XGroup e{0, 0xffffffffu, 0u, 0u, {0u, 0u, 0u, 0u}};
+                const int xi = 4 * g - ORB_EDGE;
+                bool ok = xi >= 0 && xi + 3 < G.w;
+                for (int j = 0; ok && j < 4; ++j) { const int rel = xr[xi + j].sx - xr[xi].sx; ok = rel >= 0 && rel <= 6; }
+                if (ok) {
+                    const int c0 = xr[xi].sx + ORB_EDGE;
+                    unsigned sel[4];
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned rel = (unsigned)(xr[xi + j].sx - xr[xi].sx);
+                        sel[j] = rel | ((rel + 1) << 4) | (rel << 8) | (rel << 12);      // bytes 0 / 1 of the PRMT result = p[sx], p[sx + 1]
+                        e.cf[j] = (unsigned)(unsigned short)xr[xi + j].a0 | ((unsigned)(unsigned short)xr[xi + j].a1 << 16);
+                    }
+                    e.wofs = c0 >> 2; e.shift8 = 8u * (unsigned)(c0 & 3);
+                    e.sel01 = sel[0] | (sel[1] << 16); e.sel23 = sel[2] | (sel[3] << 16);
+                }
+                hp.xgrp[G.xtab_ofs / 4 + g] = e;
+            }
         }
     }
     P.pyr_bytes = pyr; P.blur_bytes = blr; P.ncells = std::max(cells, 1); P.cand_entries = std::max(cand, 4);
@@ -212,12 +233,13 @@ struct Engine {
     int2* d_rmeta = nullptr;
     unsigned char* d_octnodes = nullptr;     // node arrays of k_octree when they do not fit in shared memory
     XTab* d_xtab = nullptr;
+    XGroup* d_xgrp = nullptr;
     YTab* d_ytab = nullptr;
     long long bytes = 0;
 
     void release() {
         cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_cand); cudaFree(d_scratch); cudaFree(d_lvlkp);
-        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_sorted); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr;
+        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_xgrp); d_xgrp = nullptr; cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_sorted); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr;
         d_pyr = d_blur = nullptr; d_cand = d_scratch = d_lvlkp = nullptr; d_cellcnt = d_lvlcnt = d_status = d_rowstart = d_sorted = nullptr;
         d_xtab = nullptr; d_ytab = nullptr; planned = false; bytes = 0;
     }
@@ -246,11 +268,13 @@ struct Engine {
         TRY(alloc(&d_rmeta, (size_t)S * P.kp_total));
         if (hp.oct_global_nodes) TRY(alloc(&d_octnodes, (size_t)S * P.nlevels * hp.oct_node_stride));
         TRY(alloc(&d_xtab, hp.xtab.size()));
+        TRY(alloc(&d_xgrp, hp.xgrp.size()));
         TRY(alloc(&d_ytab, hp.ytab.size()));
         CU_TRY(cudaMemset(d_pyr, 0, (size_t)S * P.pyr_bytes));
         CU_TRY(cudaMemset(d_blur, 0, (size_t)S * P.blur_bytes));
         CU_TRY(cudaMemset(d_status, 0, sizeof(int)));
         if (!hp.xtab.empty()) CU_TRY(cudaMemcpy(d_xtab, hp.xtab.data(), hp.xtab.size() * sizeof(XTab), cudaMemcpyHostToDevice));
+        if (!hp.xgrp.empty()) CU_TRY(cudaMemcpy(d_xgrp, hp.xgrp.data(), hp.xgrp.size() * sizeof(XGroup), cudaMemcpyHostToDevice));
         if (!hp.ytab.empty()) CU_TRY(cudaMemcpy(d_ytab, hp.ytab.data(), hp.ytab.size() * sizeof(YTab), cudaMemcpyHostToDevice));
         CU_TRY(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.fast_smem));
         CU_TRY(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.oct_smem));
@@ -273,11 +297,11 @@ struct Engine {
         }
         for (int l = 1; l < P.nlevels; ++l) {
             const LevelGeom& G = P.lv[l];
-            dim3 grid(((G.pitch >> 2) * ((G.rows + 1) / 2) + 255) / 256, n);
+            dim3 grid(((G.pitch >> 2) * ((G.rows + RS_ROWS - 1) / RS_ROWS) + 255) / 256, n);
             // the word-window fast path needs the 4 columns of a thread to span <= 10 source bytes: scale < 2
             const int fast_ok = (double)P.lv[l - 1].w / G.w < 1.95 ? 1 : 0;
             const unsigned wpr = (unsigned)(G.pitch >> 2), wpr_magic = (unsigned)((0x100000000ULL + wpr - 1) / wpr);
-            k_resize<<<grid, 256, 0, st>>>(P, l, fast_ok, wpr_magic, d_pyr, d_xtab, d_ytab);
+            k_resize<<<grid, 256, 0, st>>>(P, l, fast_ok, wpr_magic, d_pyr, d_xtab, d_xgrp, d_ytab);
             ++g_launches;
         }
         if (evs) cudaEventRecord(evs[2], st);

@@ -59,104 +59,118 @@ __global__ void __launch_bounds__(256) k_border0(const __grid_constant__ Plan P,
 // dst = (((b0*(T0>>4))>>16) + ((b1*(T1>>4))>>16) + 2) >> 2   (SURVEY.md App. A2).
 // ------------------------------------------------------------------------------------------------
 // The tables are indexed by BORDERED coordinates (the host applied the reflect-101 map and padded each row of
-// entries to the buffer pitch), so a thread's four column entries are one aligned 32-byte read (2 x LDG.128).
-// One thread = 4 columns x 2 rows of the bordered output.  Interior threads (the vast majority) read each source row
-// they need as three aligned 32-bit words (the 4 columns span <= 10 source bytes for scale factors < 2), pick the
-// (p[sx], p[sx+1]) byte pair of every column with one PRMT and form the horizontal interpolation with one 2-way dot
-// product (DP2A) against the packed 11-bit coefficients; two consecutive output rows usually share a source row.
-// Border threads (reflected, non-monotonic columns) and scale factors >= 2 take the per-byte path.
+// entries to the buffer pitch).  One thread = 4 columns x RS_ROWS rows of the bordered output; its XGroup entry (one
+// aligned 32-byte read) says where the 12-byte source window of the 4 columns starts, and each source row it needs is
+// three aligned 32-bit words -> two funnel shifts (8 bytes from column 0's left sample on) -> per column one PRMT that
+// picks (p[sx], p[sx+1]) and one 2-way dot product (DP2A) against the packed 11-bit coefficients.  Horizontally filtered
+// source rows are kept for the next output row (at scale 1.2 consecutive output rows share one), so a thread filters
+// ~1.4 source rows per output row.  Groups the host marked (reflected border columns, scale factors >= 2) take the
+// per-byte path through XTab.
 // Vertical step of cv::resize's fixed-point bilinear: ((b0 * (T0 >> 4) >> 16) + (b1 * (T1 >> 4) >> 16) + 2) >> 2.
 // b0s / b1s are the 11-bit row weights pre-shifted left by 16, so each ">> 16" product is one multiply-high with
 // accumulate (IMAD.HI, on the FMA pipe -- these kernels are bound by the ALU pipe).  The result is at most 255
-// (b0 + b1 == 2048, T >> 4 <= 32640), so no byte mask is needed.
+// (b0 + b1 <= 2049, T >> 4 <= 32655), so no byte mask is needed.
+// ------------------------------------------------------------------------------------------------
+#define RS_ROWS 4
 __device__ __forceinline__ u32 rs_vert(int T0, int T1, u32 b0s, u32 b1s) {
     return (__umulhi((u32)T0 >> 4, b0s) + __umulhi((u32)T1 >> 4, b1s) + 2u) >> 2;
 }
+__device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel) {       // raw PRMT: the selector's upper bits are ignored by the hardware
+    u32 d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
 
 __global__ void __launch_bounds__(256, 5) k_resize(const __grid_constant__ Plan P, int l, int fast_ok, u32 wpr_magic, u8* __restrict__ pyr,
-                                                const XTab* __restrict__ xtab, const YTab* __restrict__ ytab) {
+                                                const XTab* __restrict__ xtab, const XGroup* __restrict__ xgrp,
+                                                const YTab* __restrict__ ytab) {
     const LevelGeom& G = P.lv[l];
     const LevelGeom& S = P.lv[l - 1];
     const int slot = blockIdx.y;
     const int words_per_row = G.pitch >> 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    int rp = (int)__umulhi((u32)idx, wpr_magic);            // row pair = idx / words_per_row via ceil(2^32 / d); may overshoot by one
-    if (rp * words_per_row > idx) --rp;
-    const int by = rp << 1, bx = (idx - rp * words_per_row) << 2;
-    if (by >= G.rows) return;
-    const bool two = by + 1 < G.rows;
+    int rq = (int)__umulhi((u32)idx, wpr_magic);            // row group = idx / words_per_row via ceil(2^32 / d); may overshoot by one
+    if (rq * words_per_row > idx) --rq;
+    const int by0 = rq * RS_ROWS, gx = idx - rq * words_per_row, bx = gx << 2;
+    if (by0 >= G.rows) return;
     u8* base = pyr + (size_t)slot * P.pyr_bytes;
     const u8* srcb = base + S.pyr_ofs;                       // bordered buffer of level l-1 (ROI at +19, +19)
-    const YTab ya = ytab[G.ytab_ofs + by], yb = ytab[G.ytab_ofs + (two ? by + 1 : by)];
-    const u32 ab0 = (u32)(unsigned short)ya.b0 << 16, ab1 = (u32)(unsigned short)ya.b1 << 16;
-    const u32 bb0 = (u32)(unsigned short)yb.b0 << 16, bb1 = (u32)(unsigned short)yb.b1 << 16;
-    const int4* tp = reinterpret_cast<const int4*>(xtab + G.xtab_ofs + bx);
-    const int4 t01 = __ldg(tp), t23 = __ldg(tp + 1);
-    const int sxs[4] = {t01.x, t01.z, t23.x, t23.z};
-    const u32 cf[4] = {(u32)t01.y, (u32)t01.w, (u32)t23.y, (u32)t23.w};       // a0 | a1 << 16 (both in [0, 2048])
-    const int bw = G.w + 2 * ORB_EDGE;
-    u32 va = 0, vb = 0;
-    const int xi = bx - ORB_EDGE;
-    if (fast_ok && xi >= 0 && xi + 3 < G.w) {
-        // byte offset of column j's left sample inside the 12-byte window that starts at the aligned word of column 0
-        const int c0 = sxs[0] + ORB_EDGE, wb = c0 >> 2;
-        int o[4]; u32 sel[4]; bool hi[4];
+    const uint2* yt = reinterpret_cast<const uint2*>(ytab + G.ytab_ofs + by0);      // {y0 | y1 << 16, b0 | b1 << 16}
+    const int4* gp = reinterpret_cast<const int4*>(xgrp + (G.xtab_ofs >> 2) + gx);
+    const int4 g0 = __ldg(gp), g1 = __ldg(gp + 1);           // {wofs, shift8, sel01, sel23}, {cf0..cf3}
+    u8* dst = base + G.pyr_ofs + (size_t)by0 * G.pitch + bx;
+    const int nr = min(RS_ROWS, G.rows - by0);
+    if (fast_ok && (u32)g0.y != 0xffffffffu) {
+        const u32 sh = (u32)g0.y, s0 = (u32)g0.z, s1 = (u32)g0.z >> 16, s2 = (u32)g0.w, s3 = (u32)g0.w >> 16;
+        const u32 spw = (u32)S.pitch >> 2;
+        const u32* wsrc = reinterpret_cast<const u32*>(srcb) + g0.x + ORB_EDGE * spw;
+        // all loads first (the table rows, then every source row the RS_ROWS outputs need), arithmetic afterwards: the
+        // kernel is latency-bound otherwise.  Row r's upper source row is usually row r-1's lower one (scale 1.2) and is
+        // only fetched when it is not.
+        uint2 yv[RS_ROWS];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            o[j] = sxs[j] + ORB_EDGE - (wb << 2);            // 0 .. 10
-            hi[j] = o[j] > 6;                                 // pair comes from words (1, 2) instead of (0, 1)
-            const int k = hi[j] ? o[j] - 4 : o[j];
-            sel[j] = (u32)k | ((u32)(k + 1) << 4);            // PRMT selector: result byte 0 = window byte k, byte 1 = k + 1
+        for (int r = 0; r < RS_ROWS; ++r) yv[r] = __ldg(yt + min(r, nr - 1));
+        u32 wb[RS_ROWS][3], wa[RS_ROWS][3];
+        bool la[RS_ROWS];
+#pragma unroll
+        for (int r = 0; r < RS_ROWS; ++r) {
+            const u32* q = wsrc + (yv[r].x >> 16) * spw;           // y1: clamped source rows are never negative
+            wb[r][0] = q[0]; wb[r][1] = q[1]; wb[r][2] = q[2];
         }
-        const int spw = S.pitch >> 2;
-        const u32* wsrc = reinterpret_cast<const u32*>(srcb) + wb;
-        int Ta[4], Tb[4];                                      // horizontal results of the two source rows in flight
-        auto hrow = [&](int sy, int (&T)[4]) {
-            const u32* r = wsrc + (size_t)(sy + ORB_EDGE) * spw;
-            const u32 w0 = r[0], w1 = r[1], w2 = r[2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const u32 pr = __byte_perm(hi[j] ? w1 : w0, hi[j] ? w2 : w1, sel[j]);
-                T[j] = (int)__dp2a_lo(cf[j], pr, 0u);         // p[sx] * a0 + p[sx+1] * a1
+        for (int r = 0; r < RS_ROWS; ++r) {
+            la[r] = r == 0 || (yv[r].x & 0xffffu) != (yv[r - 1].x >> 16);
+            wa[r][0] = wa[r][1] = wa[r][2] = 0u;
+            if (la[r]) {
+                const u32* q = wsrc + (yv[r].x & 0xffffu) * spw;   // y0
+                wa[r][0] = q[0]; wa[r][1] = q[1]; wa[r][2] = q[2];
             }
+        }
+        auto hrow = [&](const u32 (&w)[3], int (&T)[4]) {
+            const u32 lo = __funnelshift_r(w[0], w[1], sh), hi = __funnelshift_r(w[1], w[2], sh);   // 8 bytes from column 0's left sample on
+            T[0] = (int)__dp2a_lo((u32)g1.x, prmt(lo, hi, s0), 0u);                                  // p[sx] * a0 + p[sx+1] * a1
+            T[1] = (int)__dp2a_lo((u32)g1.y, prmt(lo, hi, s1), 0u);
+            T[2] = (int)__dp2a_lo((u32)g1.z, prmt(lo, hi, s2), 0u);
+            T[3] = (int)__dp2a_lo((u32)g1.w, prmt(lo, hi, s3), 0u);
         };
-        hrow(ya.y0, Ta);
-        hrow(ya.y1, Tb);
+        int A[4], B[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) va |= rs_vert(Ta[j], Tb[j], ab0, ab1) << (8 * j);
-        if (two) {
-            if (yb.y0 == ya.y1) {                              // usual case at scale 1.2: the rows overlap by one source row
-                hrow(yb.y1, Ta);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) vb |= rs_vert(Tb[j], Ta[j], bb0, bb1) << (8 * j);
+        for (int r = 0; r < RS_ROWS; ++r) {
+            if (la[r]) {
+                hrow(wa[r], A);
             } else {
-                if (yb.y0 != ya.y0) hrow(yb.y0, Ta);
-                if (yb.y1 != ya.y1) hrow(yb.y1, Tb);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) vb |= rs_vert(Ta[j], Tb[j], bb0, bb1) << (8 * j);
+                for (int j = 0; j < 4; ++j) A[j] = B[j];
             }
+            hrow(wb[r], B);
+            const u32 b0s = yv[r].y << 16, b1s = yv[r].y & 0xffff0000u;
+            u32 v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v |= rs_vert(A[j], B[j], b0s, b1s) << (8 * j);
+            if (r < nr) *reinterpret_cast<u32*>(dst + (size_t)r * G.pitch) = v;
         }
     } else {
         const u8* roi = srcb + (size_t)ORB_EDGE * S.pitch + ORB_EDGE;
+        const XTab* xt = xtab + G.xtab_ofs + bx;
+        const int bw = G.w + 2 * ORB_EDGE;
+        for (int r = 0; r < nr; ++r) {
+            const uint2 y = __ldg(yt + r);
+            const int y0 = (int)(y.x & 0xffffu), y1 = (int)(y.x >> 16);
+            const u32 b0s = y.y << 16, b1s = y.y & 0xffff0000u;
+            u32 v = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (bx + k < bw) {
-                // when sx is the last column a1 == 0 and sx+1 reads the (valid) border pixel
-                const int sx = sxs[k], a0 = (int)(cf[k] & 0xffff), a1 = (int)(cf[k] >> 16);
-                const u8* r0 = roi + (size_t)ya.y0 * S.pitch + sx;
-                const u8* r1 = roi + (size_t)ya.y1 * S.pitch + sx;
-                va |= rs_vert(r0[0] * a0 + r0[1] * a1, r1[0] * a0 + r1[1] * a1, ab0, ab1) << (8 * k);
-                if (two) {
-                    const u8* q0 = roi + (size_t)yb.y0 * S.pitch + sx;
-                    const u8* q1 = roi + (size_t)yb.y1 * S.pitch + sx;
-                    vb |= rs_vert(q0[0] * a0 + q0[1] * a1, q1[0] * a0 + q1[1] * a1, bb0, bb1) << (8 * k);
+            for (int k = 0; k < 4; ++k) {
+                if (bx + k < bw) {
+                    // when sx is the last column a1 == 0 and sx+1 reads the (valid) border pixel
+                    const int sx = xt[k].sx, a0 = xt[k].a0, a1 = xt[k].a1;
+                    const u8* r0 = roi + (size_t)y0 * S.pitch + sx;
+                    const u8* r1 = roi + (size_t)y1 * S.pitch + sx;
+                    v |= rs_vert(r0[0] * a0 + r0[1] * a1, r1[0] * a0 + r1[1] * a1, b0s, b1s) << (8 * k);
                 }
             }
+            *reinterpret_cast<u32*>(dst + (size_t)r * G.pitch) = v;
         }
     }
-    u8* dst = base + G.pyr_ofs + (size_t)by * G.pitch + bx;
-    *reinterpret_cast<u32*>(dst) = va;
-    if (two) *reinterpret_cast<u32*>(dst + G.pitch) = vb;
 }
 
 // ------------------------------------------------------------------------------------------------

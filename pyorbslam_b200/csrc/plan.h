@@ -42,6 +42,11 @@ struct Plan {
 // resize lookup tables (built on the host with the exact OpenCV float arithmetic)
 struct XTab { int sx; short a0, a1; };            // source column + horizontal 11-bit coefficients
 struct YTab { short y0, y1, b0, b1; };            // clamped source rows + vertical coefficients
+// One entry per group of 4 consecutive bordered output columns (= one k_resize thread): where its 12-byte source window starts
+// (word index in a bordered source row), how far column 0's left sample sits inside it, the byte-pair selectors of the 4
+// columns relative to column 0 and their packed coefficients.  shift8 == 0xffffffff: the group is not an interior one
+// (reflected border columns, or columns more than 6 source bytes apart) and takes the per-byte path through XTab.
+struct XGroup { int wofs; unsigned shift8, sel01, sel23, cf[4]; };
 
 // pyramid addressing for the stereo SAD stage (device-resident pyramids or uploaded GetImagePyramid() views)
 struct StereoGeom {
