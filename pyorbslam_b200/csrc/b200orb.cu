@@ -88,6 +88,7 @@ struct HostPlan {
     Plan P;
     std::vector<XTab> xtab;
     std::vector<XGroup> xgrp;
+    std::vector<uint2> mtab;      // IC_Angle coefficient table, see k_describe
     std::vector<YTab> ytab;
     int fast_SP = 0, fast_SR = 0, fast_TP = 0, fast_TR = 0, fast_LC = 0;
     size_t fast_smem = 0;
@@ -192,6 +193,22 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
             }
         }
     }
+    // IC_Angle (ORBextractor.cpp:77-106) as dot products: the 31 x 31 disc is read as aligned 32-bit words, 3 rows x 9 words per
+    // step (lane = (row % 3) * 9 + word), 11 steps; entry [al][step][lane] holds the 4 signed u coefficients and the 4 signed v
+    // coefficients of that word's bytes (0 outside the disc), al = alignment of the patch's left edge.
+    hp.mtab.assign(4 * MOM_STEPS * 32, make_uint2(0u, 0u));
+    for (int al = 0; al < 4; ++al)
+        for (int i = 0; i < MOM_STEPS; ++i)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int k = lane % 9, row = 3 * i + lane / 9, v = row - 15;
+                if (lane >= 27 || row > 30) continue;
+                unsigned cu = 0, cv = 0;
+                for (int j = 0; j < 4; ++j) {
+                    const int u = 4 * k + j - al - 15;
+                    if (std::abs(u) <= prm.umax[std::abs(v)]) { cu |= (unsigned)(u & 0xff) << (8 * j); cv |= (unsigned)(v & 0xff) << (8 * j); }
+                }
+                hp.mtab[(al * MOM_STEPS + i) * 32 + lane] = make_uint2(cu, cv);
+            }
     P.pyr_bytes = pyr; P.blur_bytes = blr; P.ncells = std::max(cells, 1); P.cand_entries = std::max(cand, 4);
     P.kp_total = std::max(kpt, 1); P.fast_ctas = fctas; P.blur_ctas = bctas; P.max_cells_level = maxcells;
     hp.fast_SP = round_up(15 + FAST_WARPS * maxw + 6 + 16, 16);   // rows are bulk-copied in 16-byte units from a 16-byte aligned start
@@ -234,12 +251,13 @@ struct Engine {
     unsigned char* d_octnodes = nullptr;     // node arrays of k_octree when they do not fit in shared memory
     XTab* d_xtab = nullptr;
     XGroup* d_xgrp = nullptr;
+    uint2* d_mtab = nullptr;
     YTab* d_ytab = nullptr;
     long long bytes = 0;
 
     void release() {
         cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_cand); cudaFree(d_scratch); cudaFree(d_lvlkp);
-        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_xgrp); d_xgrp = nullptr; cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_sorted); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr;
+        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_xgrp); d_xgrp = nullptr; cudaFree(d_mtab); d_mtab = nullptr; cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_sorted); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr;
         d_pyr = d_blur = nullptr; d_cand = d_scratch = d_lvlkp = nullptr; d_cellcnt = d_lvlcnt = d_status = d_rowstart = d_sorted = nullptr;
         d_xtab = nullptr; d_ytab = nullptr; planned = false; bytes = 0;
     }
@@ -269,12 +287,14 @@ struct Engine {
         if (hp.oct_global_nodes) TRY(alloc(&d_octnodes, (size_t)S * P.nlevels * hp.oct_node_stride));
         TRY(alloc(&d_xtab, hp.xtab.size()));
         TRY(alloc(&d_xgrp, hp.xgrp.size()));
+        TRY(alloc(&d_mtab, hp.mtab.size()));
         TRY(alloc(&d_ytab, hp.ytab.size()));
         CU_TRY(cudaMemset(d_pyr, 0, (size_t)S * P.pyr_bytes));
         CU_TRY(cudaMemset(d_blur, 0, (size_t)S * P.blur_bytes));
         CU_TRY(cudaMemset(d_status, 0, sizeof(int)));
         if (!hp.xtab.empty()) CU_TRY(cudaMemcpy(d_xtab, hp.xtab.data(), hp.xtab.size() * sizeof(XTab), cudaMemcpyHostToDevice));
         if (!hp.xgrp.empty()) CU_TRY(cudaMemcpy(d_xgrp, hp.xgrp.data(), hp.xgrp.size() * sizeof(XGroup), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(d_mtab, hp.mtab.data(), hp.mtab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
         if (!hp.ytab.empty()) CU_TRY(cudaMemcpy(d_ytab, hp.ytab.data(), hp.ytab.size() * sizeof(YTab), cudaMemcpyHostToDevice));
         CU_TRY(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.fast_smem));
         CU_TRY(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.oct_smem));
@@ -318,8 +338,8 @@ struct Engine {
                                                                       hp.oct_capK, hp.oct_capC, d_octnodes, hp.oct_node_stride);
         ++g_launches;
         if (evs) cudaEventRecord(evs[5], st);
-        k_describe<<<dim3((P.kp_total + DESC_WARPS - 1) / DESC_WARPS, n), DESC_WARPS * 32, 0, st>>>(P, d_pyr, d_blur, d_lvlkp, d_lvlcnt, d_kps,
-                                                                                                    d_desc, d_nkp);
+        k_describe<<<dim3((P.kp_total + DESC_WARPS - 1) / DESC_WARPS, n), DESC_WARPS * 32, 0, st>>>(P, d_pyr, d_blur, d_lvlkp, d_lvlcnt, d_mtab,
+                                                                                                    d_kps, d_desc, d_nkp);
         ++g_launches;
         if (evs) cudaEventRecord(evs[6], st);
         CU_TRY(cudaGetLastError());

@@ -76,10 +76,15 @@ __device__ __forceinline__ void glibc_sincosf(float y, float* sp, float* cp) {
 //   * the output row: (x, y) * mvScaleFactor[level] for level > 0 (:1094-1100), size, angle, response, octave.
 // ------------------------------------------------------------------------------------------------
 #define DESC_WARPS 8
+__device__ __forceinline__ int dp4a_us(u32 a_u8x4, u32 b_s8x4, int c) {     // unsigned bytes x signed bytes
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
                                                               const u8* __restrict__ blur, const u32* __restrict__ lvl_kp,
-                                                              const int* __restrict__ lvl_cnt, float* __restrict__ kps,
-                                                              u8* __restrict__ desc, int* __restrict__ nkp) {
+                                                              const int* __restrict__ lvl_cnt, const uint2* __restrict__ mtab,
+                                                              float* __restrict__ kps, u8* __restrict__ desc, int* __restrict__ nkp) {
     const int slot = blockIdx.y, lane = threadIdx.x & 31;
     const int i = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
     const int* cnt = lvl_cnt + (size_t)slot * P.nlevels;
@@ -98,17 +103,24 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
 
     // ---- orientation ----
     const u8* c = pyr + (size_t)slot * P.pyr_bytes + G.pyr_ofs + (size_t)(y + ORB_EDGE) * G.pitch + (x + ORB_EDGE);
-    const int u = lane - 15;
+    // m10 = sum u * I, m01 = sum v * I over the radius-15 disc (exact integers, any order): the disc is read as aligned words,
+    // 3 rows x 9 words per step, and each word is two 4-way dot products against the step's coefficient words (host table:
+    // signed u and signed v of the word's 4 bytes, 0 outside the disc).  Lanes 27..31 read in-bounds pixels against zeros.
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int au = u < 0 ? -u : u;
+    {
+        const u8* c0 = c - 15;                               // u = -15 on the centre row
+        const int al = (int)(reinterpret_cast<size_t>(c0) & 3);
+        const int rsub = (lane * 57) >> 9, k = lane - 9 * rsub;   // lane / 9, lane % 9
+        const int wpr = G.pitch >> 2;
+        const u32* p = reinterpret_cast<const u32*>(c0 - al) + (ptrdiff_t)((rsub - 15) * wpr + k);
+        const uint2* tb = mtab + al * (MOM_STEPS * 32) + lane;
+        const ptrdiff_t step = 3 * wpr;
 #pragma unroll
-        for (int v = -15; v <= 15; ++v) {   // fully unrolled: 31 independent loads in flight per lane
-            if (au <= P.umax[v < 0 ? -v : v]) {
-                const int val = c[v * G.pitch + u];
-                m10 += u * val;
-                m01 += v * val;
-            }
+        for (int i = 0; i < MOM_STEPS; ++i, p += step) {
+            const u32 w = *p;
+            const uint2 cf = __ldg(tb + i * 32);
+            m10 = dp4a_us(w, cf.x, m10);
+            m01 = dp4a_us(w, cf.y, m01);
         }
     }
 #pragma unroll

@@ -46,6 +46,7 @@ struct YTab { short y0, y1, b0, b1; };            // clamped source rows + verti
 // (word index in a bordered source row), how far column 0's left sample sits inside it, the byte-pair selectors of the 4
 // columns relative to column 0 and their packed coefficients.  shift8 == 0xffffffff: the group is not an interior one
 // (reflected border columns, or columns more than 6 source bytes apart) and takes the per-byte path through XTab.
+#define MOM_STEPS 11   // IC_Angle: 31 disc rows, 3 per step
 struct XGroup { int wofs; unsigned shift8, sel01, sel23, cf[4]; };
 
 // pyramid addressing for the stereo SAD stage (device-resident pyramids or uploaded GetImagePyramid() views)
