@@ -252,12 +252,13 @@ struct Engine {
     XTab* d_xtab = nullptr;
     XGroup* d_xgrp = nullptr;
     uint2* d_mtab = nullptr;
+    float4* d_fpat = nullptr;
     YTab* d_ytab = nullptr;
     long long bytes = 0;
 
     void release() {
         cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_cand); cudaFree(d_scratch); cudaFree(d_lvlkp);
-        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_xgrp); d_xgrp = nullptr; cudaFree(d_mtab); d_mtab = nullptr; cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_sorted); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr;
+        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_xgrp); d_xgrp = nullptr; cudaFree(d_mtab); d_mtab = nullptr; cudaFree(d_fpat); d_fpat = nullptr; cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_sorted); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr;
         d_pyr = d_blur = nullptr; d_cand = d_scratch = d_lvlkp = nullptr; d_cellcnt = d_lvlcnt = d_status = d_rowstart = d_sorted = nullptr;
         d_xtab = nullptr; d_ytab = nullptr; planned = false; bytes = 0;
     }
@@ -288,6 +289,7 @@ struct Engine {
         TRY(alloc(&d_xtab, hp.xtab.size()));
         TRY(alloc(&d_xgrp, hp.xgrp.size()));
         TRY(alloc(&d_mtab, hp.mtab.size()));
+        TRY(alloc(&d_fpat, 256));
         TRY(alloc(&d_ytab, hp.ytab.size()));
         CU_TRY(cudaMemset(d_pyr, 0, (size_t)S * P.pyr_bytes));
         CU_TRY(cudaMemset(d_blur, 0, (size_t)S * P.blur_bytes));
@@ -295,6 +297,16 @@ struct Engine {
         if (!hp.xtab.empty()) CU_TRY(cudaMemcpy(d_xtab, hp.xtab.data(), hp.xtab.size() * sizeof(XTab), cudaMemcpyHostToDevice));
         if (!hp.xgrp.empty()) CU_TRY(cudaMemcpy(d_xgrp, hp.xgrp.data(), hp.xgrp.size() * sizeof(XGroup), cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(d_mtab, hp.mtab.data(), hp.mtab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        {
+            static const signed char pat[1024] = {B200ORB_PATTERN_VALUES};
+            std::vector<float4> fp(256);
+            for (int lane = 0; lane < 32; ++lane)
+                for (int k = 0; k < 8; ++k) {
+                    const signed char* q = pat + 4 * (8 * lane + k);
+                    fp[k * 32 + lane] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
+                }
+            CU_TRY(cudaMemcpy(d_fpat, fp.data(), fp.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        }
         if (!hp.ytab.empty()) CU_TRY(cudaMemcpy(d_ytab, hp.ytab.data(), hp.ytab.size() * sizeof(YTab), cudaMemcpyHostToDevice));
         CU_TRY(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.fast_smem));
         CU_TRY(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.oct_smem));
@@ -338,8 +350,8 @@ struct Engine {
                                                                       hp.oct_capK, hp.oct_capC, d_octnodes, hp.oct_node_stride);
         ++g_launches;
         if (evs) cudaEventRecord(evs[5], st);
-        k_describe<<<dim3((P.kp_total + DESC_WARPS - 1) / DESC_WARPS, n), DESC_WARPS * 32, 0, st>>>(P, d_pyr, d_blur, d_lvlkp, d_lvlcnt, d_mtab,
-                                                                                                    d_kps, d_desc, d_nkp);
+        k_describe<<<dim3((P.kp_total + DESC_WARPS * DESC_KPW - 1) / (DESC_WARPS * DESC_KPW), n), DESC_WARPS * 32, 0, st>>>(P, d_pyr, d_blur, d_lvlkp, d_lvlcnt, d_mtab,
+                                                                                                    d_fpat, d_kps, d_desc, d_nkp);
         ++g_launches;
         if (evs) cudaEventRecord(evs[6], st);
         CU_TRY(cudaGetLastError());

@@ -9,6 +9,8 @@
 // 8 consecutive 32-bit words; it reads them straight from this (L1/L2-resident) global array.  Constant memory
 // would serialise the 32 distinct addresses of a warp.
 __device__ __align__(16) const signed char g_pattern[1024] = {B200ORB_PATTERN_VALUES};
+// The descriptor kernel reads the same values as floats from a host-built table, transposed so that a warp's read of "pair k of
+// every lane" is one contiguous 512-byte line: fpat[k * 32 + lane] = (x0, y0, x1, y1) of test pair 8 * lane + k.
 
 // cv::fastAtan2 (degrees), scalar polynomial path
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
@@ -76,6 +78,7 @@ __device__ __forceinline__ void glibc_sincosf(float y, float* sp, float* cp) {
 //   * the output row: (x, y) * mvScaleFactor[level] for level > 0 (:1094-1100), size, angle, response, octave.
 // ------------------------------------------------------------------------------------------------
 #define DESC_WARPS 8
+#define DESC_KPW 8     // keypoints per warp
 __device__ __forceinline__ int dp4a_us(u32 a_u8x4, u32 b_s8x4, int c) {     // unsigned bytes x signed bytes
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
@@ -84,19 +87,30 @@ __device__ __forceinline__ int dp4a_us(u32 a_u8x4, u32 b_s8x4, int c) {     // u
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
                                                               const u8* __restrict__ blur, const u32* __restrict__ lvl_kp,
                                                               const int* __restrict__ lvl_cnt, const uint2* __restrict__ mtab,
-                                                              float* __restrict__ kps, u8* __restrict__ desc, int* __restrict__ nkp) {
+                                                              const float4* __restrict__ fpat, float* __restrict__ kps,
+                                                              u8* __restrict__ desc, int* __restrict__ nkp) {
     const int slot = blockIdx.y, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
-    const int* cnt = lvl_cnt + (size_t)slot * P.nlevels;
-    int l = 0, off = 0, total = 0;
-    bool found = false;
-    for (int k = 0; k < P.nlevels; ++k) {
-        const int c = cnt[k];
-        if (!found && i < total + c) { l = k; off = total; found = true; }
-        total += c;
+    // the moment table goes to shared memory once per CTA, the float pattern into registers once per warp; every warp then
+    // walks DESC_KPW consecutive keypoints
+    __shared__ uint2 s_mtab[4 * MOM_STEPS * 32];
+    for (int k = threadIdx.x; k < 4 * MOM_STEPS * 32; k += DESC_WARPS * 32) s_mtab[k] = __ldg(mtab + k);
+    float4 pq[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pq[k] = __ldg(fpat + k * 32 + lane);
+    // level of keypoint i: lanes hold the running ends of the per-level counts
+    int lend = lane < P.nlevels ? lvl_cnt[(size_t)slot * P.nlevels + lane] : 0;
+#pragma unroll
+    for (int d = 1; d < ORB_MAX_LEVELS; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, lend, d);
+        if (lane >= d) lend += up;
     }
-    if (i == 0 && lane == 0) nkp[slot] = total;
-    if (!found) return;
+    const int total = __shfl_sync(0xffffffffu, lend, ORB_MAX_LEVELS - 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) nkp[slot] = total;
+    __syncthreads();
+    const int i0 = (blockIdx.x * DESC_WARPS + (threadIdx.x >> 5)) * DESC_KPW;
+    for (int i = i0; i < min(i0 + DESC_KPW, total); ++i) {
+    const int l = __popc(__ballot_sync(0xffffffffu, lane < P.nlevels && i >= lend));
+    const int off = __shfl_sync(0xffffffffu, lend, max(l - 1, 0)) & (l ? -1 : 0);
     const LevelGeom& G = P.lv[l];
     const u32 packed = lvl_kp[(size_t)slot * P.kp_total + G.kp_ofs + (i - off)];
     const int x = packed & 0xfff, y = (packed >> 12) & 0xfff, resp = packed >> 24;
@@ -113,12 +127,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
         const int rsub = (lane * 57) >> 9, k = lane - 9 * rsub;   // lane / 9, lane % 9
         const int wpr = G.pitch >> 2;
         const u32* p = reinterpret_cast<const u32*>(c0 - al) + (ptrdiff_t)((rsub - 15) * wpr + k);
-        const uint2* tb = mtab + al * (MOM_STEPS * 32) + lane;
+        const uint2* tb = s_mtab + al * (MOM_STEPS * 32) + lane;
         const ptrdiff_t step = 3 * wpr;
 #pragma unroll
-        for (int i = 0; i < MOM_STEPS; ++i, p += step) {
+        for (int s = 0; s < MOM_STEPS; ++s, p += step) {
             const u32 w = *p;
-            const uint2 cf = __ldg(tb + i * 32);
+            const uint2 cf = tb[s * 32];
             m10 = dp4a_us(w, cf.x, m10);
             m01 = dp4a_us(w, cf.y, m01);
         }
@@ -134,18 +148,24 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
     float a, b;
     glibc_sincosf(angle * factorPI, &b, &a);
+    // Sample coordinates: cvRound(x * b + y * a) rows, cvRound(x * a - y * b) columns (ORBextractor.cpp:117-120, products and sums
+    // rounded separately: --fmad=false).  Rounding to nearest-even is done by adding 1.5 * 2^23 (FADD, exact for |v| < 2^22) instead
+    // of a float->int conversion: the integer then sits in the low mantissa bits, biased by K = 0x4B400000.  The byte offset
+    // rbits * pitch + cbits is formed in 32-bit wrap-around arithmetic and equals trueoffset + KC (mod 2^32) with
+    // KC = K * (pitch + 1); KC is a non-zero multiple of 2^22 (pitch is a multiple of 64, so pitch + 1 is odd) and |trueoffset| < 2^22,
+    // so the sum never wraps and (bc - KC)[u32 offset] is the sample.  Everything but the load runs on the FMA pipe.
     const u8* bc = blur + (size_t)slot * P.blur_bytes + G.blur_ofs + (size_t)y * G.blur_pitch + x;
-    const int4* pw = reinterpret_cast<const int4*>(g_pattern + lane * 32);
-    const int4 w0 = __ldg(pw), w1 = __ldg(pw + 1);
-    const int pwords[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float RN = 12582912.f;
+    const u32 bp = (u32)G.blur_pitch;
+    const u8* bk = bc - (size_t)(0x4B400000u * (bp + 1u));
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int pk = pwords[k];
-        const float x0 = (float)(signed char)(pk & 0xff), y0 = (float)(signed char)((pk >> 8) & 0xff),
-                    x1 = (float)(signed char)((pk >> 16) & 0xff), y1 = (float)(signed char)(pk >> 24);
-        const int t0 = bc[__float2int_rn(x0 * b + y0 * a) * G.blur_pitch + __float2int_rn(x0 * a - y0 * b)];
-        const int t1 = bc[__float2int_rn(x1 * b + y1 * a) * G.blur_pitch + __float2int_rn(x1 * a - y1 * b)];
+        const float4 q = pq[k];
+        const float r0 = (q.x * b + q.y * a) + RN, c0 = (q.x * a - q.y * b) + RN;
+        const float r1 = (q.z * b + q.w * a) + RN, c1 = (q.z * a - q.w * b) + RN;
+        const int t0 = bk[__float_as_uint(r0) * bp + __float_as_uint(c0)];
+        const int t1 = bk[__float_as_uint(r1) * bp + __float_as_uint(c1)];
         val |= (t0 < t1) << k;
     }
     desc[((size_t)slot * P.kp_total + i) * 32 + lane] = (u8)val;
@@ -161,6 +181,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
             default: o = (float)l; break;
         }
         kps[((size_t)slot * P.kp_total + i) * 6 + lane] = o;
+    }
     }
 }
 
