@@ -117,7 +117,11 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
         G.rows = G.h + 2 * ORB_EDGE;
         G.pyr_ofs = pyr; pyr += round_up(G.pitch * G.rows, 256);
         G.blur_pitch = round_up(G.w, 64);
+        // guard band in front of the first and behind the last level: the descriptor kernel stages the full 37 x 37 sample window
+        // of every keypoint, which overhangs the level image by up to 2 rows for keypoints 16 px from its edge
+        if (l == 0) blr = round_up(19 * G.blur_pitch + 64, 256);
         G.blur_ofs = blr; blr += round_up(G.blur_pitch * G.h, 256);
+        if (l == P.nlevels - 1) blr += round_up(19 * G.blur_pitch + 64, 256);
         G.maxBX = G.w - ORB_EDGE + 3; G.maxBY = G.h - ORB_EDGE + 3;
         const float width = (float)(G.maxBX - ORB_DET_ORIGIN), height = (float)(G.maxBY - ORB_DET_ORIGIN);
         int nCols = (int)(width / 30.f), nRows = (int)(height / 30.f);    // ORBextractor.cpp:783-784

@@ -79,12 +79,13 @@ __device__ __forceinline__ void glibc_sincosf(float y, float* sp, float* cp) {
 // ------------------------------------------------------------------------------------------------
 #define DESC_WARPS 8
 #define DESC_KPW 8     // keypoints per warp
+#define DESC_PP 40     // pitch of the staged descriptor window (37 columns + alignment slack)
 __device__ __forceinline__ int dp4a_us(u32 a_u8x4, u32 b_s8x4, int c) {     // unsigned bytes x signed bytes
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
     return d;
 }
-__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
+__global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
                                                               const u8* __restrict__ blur, const u32* __restrict__ lvl_kp,
                                                               const int* __restrict__ lvl_cnt, const uint2* __restrict__ mtab,
                                                               const float4* __restrict__ fpat, float* __restrict__ kps,
@@ -93,10 +94,10 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
     // the moment table goes to shared memory once per CTA, the float pattern into registers once per warp; every warp then
     // walks DESC_KPW consecutive keypoints
     __shared__ uint2 s_mtab[4 * MOM_STEPS * 32];
+    __shared__ u32 s_patch[DESC_WARPS * 37 * (DESC_PP / 4)];    // per warp: 37 rows x DESC_PP bytes of the blurred level
     for (int k = threadIdx.x; k < 4 * MOM_STEPS * 32; k += DESC_WARPS * 32) s_mtab[k] = __ldg(mtab + k);
-    float4 pq[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) pq[k] = __ldg(fpat + k * 32 + lane);
+    __shared__ float4 s_fpat[256];
+    for (int k = threadIdx.x; k < 256; k += DESC_WARPS * 32) s_fpat[k] = __ldg(fpat + k);
     // level of keypoint i: lanes hold the running ends of the per-level counts
     int lend = lane < P.nlevels ? lvl_cnt[(size_t)slot * P.nlevels + lane] : 0;
 #pragma unroll
@@ -115,6 +116,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
     const u32 packed = lvl_kp[(size_t)slot * P.kp_total + G.kp_ofs + (i - off)];
     const int x = packed & 0xfff, y = (packed >> 12) & 0xfff, resp = packed >> 24;
 
+    // the descriptor stage below reads a 37-row window of the blurred level: ask for its lines now, the orientation work hides the latency
+    {
+        const u8* w0 = blur + (size_t)slot * P.blur_bytes + G.blur_ofs + ((ptrdiff_t)y - 18) * G.blur_pitch + (x - 18);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(w0 + (ptrdiff_t)lane * G.blur_pitch + 18));
+        if (lane < 5) asm volatile("prefetch.global.L1 [%0];" ::"l"(w0 + (ptrdiff_t)(lane + 32) * G.blur_pitch + 18));
+    }
     // ---- orientation ----
     const u8* c = pyr + (size_t)slot * P.pyr_bytes + G.pyr_ofs + (size_t)(y + ORB_EDGE) * G.pitch + (x + ORB_EDGE);
     // m10 = sum u * I, m01 = sum v * I over the radius-15 disc (exact integers, any order): the disc is read as aligned words,
@@ -149,23 +156,39 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
     float a, b;
     glibc_sincosf(angle * factorPI, &b, &a);
     // Sample coordinates: cvRound(x * b + y * a) rows, cvRound(x * a - y * b) columns (ORBextractor.cpp:117-120, products and sums
-    // rounded separately: --fmad=false).  Rounding to nearest-even is done by adding 1.5 * 2^23 (FADD, exact for |v| < 2^22) instead
-    // of a float->int conversion: the integer then sits in the low mantissa bits, biased by K = 0x4B400000.  The byte offset
-    // rbits * pitch + cbits is formed in 32-bit wrap-around arithmetic and equals trueoffset + KC (mod 2^32) with
-    // KC = K * (pitch + 1); KC is a non-zero multiple of 2^22 (pitch is a multiple of 64, so pitch + 1 is odd) and |trueoffset| < 2^22,
-    // so the sum never wraps and (bc - KC)[u32 offset] is the sample.  Everything but the load runs on the FMA pipe.
+    // rounded separately: --fmad=false); |coordinate| <= 18 (the pattern's largest radius is 18.38).
+    // The 37 x 37 window of the blurred level around the keypoint is staged in shared memory first (aligned words, 3 rows x 10
+    // words per step): read straight from global memory the 16 samples of a lane hit ~25 different cache lines per warp
+    // instruction and the L1 tag stage becomes the bound of the kernel.
+    // Rounding to nearest-even is done by adding 1.5 * 2^23 (FADD, exact for |v| < 2^22) instead of a float->int conversion: the
+    // integer then sits in the low mantissa bits, biased by K = 0x4B400000, and the shared-memory byte address
+    // rbits * DESC_PP + cbits + D (mod 2^32) absorbs the bias in the per-keypoint constant D.
     const u8* bc = blur + (size_t)slot * P.blur_bytes + G.blur_ofs + (size_t)y * G.blur_pitch + x;
+    u32 D;
+    {
+        const u8* a0 = bc - 18 * (ptrdiff_t)G.blur_pitch - 18;                 // window corner (-18, -18)
+        const int al2 = (int)(reinterpret_cast<size_t>(a0) & 3);
+        const int rs = (lane * 205) >> 11, wi = lane - 10 * rs;                 // lane / 10, lane % 10
+        const u32* src = reinterpret_cast<const u32*>(a0 - al2) + (ptrdiff_t)rs * (G.blur_pitch >> 2) + wi;
+        const ptrdiff_t step = 3 * (G.blur_pitch >> 2);
+        u32* dstw = s_patch + (threadIdx.x >> 5) * (37 * (DESC_PP / 4)) + rs * (DESC_PP / 4) + wi;
+        __syncwarp();                                                           // the previous keypoint's samples are done
+#pragma unroll
+        for (int s = 0; s < 13; ++s, src += step, dstw += 3 * (DESC_PP / 4))
+            if (lane < 30 && 3 * s + rs < 37) *dstw = *src;
+        __syncwarp();
+        D = (u32)(18 * DESC_PP + 18 + al2) - 0x4B400000u * (u32)(DESC_PP + 1);
+    }
     const float RN = 12582912.f;
-    const u32 bp = (u32)G.blur_pitch;
-    const u8* bk = bc - (size_t)(0x4B400000u * (bp + 1u));
+    const u8* sp = reinterpret_cast<const u8*>(s_patch + (threadIdx.x >> 5) * (37 * (DESC_PP / 4)));
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float4 q = pq[k];
+        const float4 q = s_fpat[k * 32 + lane];
         const float r0 = (q.x * b + q.y * a) + RN, c0 = (q.x * a - q.y * b) + RN;
         const float r1 = (q.z * b + q.w * a) + RN, c1 = (q.z * a - q.w * b) + RN;
-        const int t0 = bk[__float_as_uint(r0) * bp + __float_as_uint(c0)];
-        const int t1 = bk[__float_as_uint(r1) * bp + __float_as_uint(c1)];
+        const u32 t0 = sp[__float_as_uint(r0) * (u32)DESC_PP + (__float_as_uint(c0) + D)];
+        const u32 t1 = sp[__float_as_uint(r1) * (u32)DESC_PP + (__float_as_uint(c1) + D)];
         val |= (t0 < t1) << k;
     }
     desc[((size_t)slot * P.kp_total + i) * 32 + lane] = (u8)val;
