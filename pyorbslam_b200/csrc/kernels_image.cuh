@@ -203,6 +203,12 @@ __global__ void __launch_bounds__(BLUR_WARPS * 32) k_blur(const __grid_constant_
     const int w0 = min((x0 + 16) >> 2, wpr - 1);
     const int wx = min(((tx * BLUR_TW + 16) >> 2) + 32 + (lane & 1), wpr - 1);   // lanes 0/1 fetch the two words past the strip
     u8* dst = blur + (size_t)slot * P.blur_bytes + G.blur_ofs;
+    // ask for all BLUR_RB + 6 input rows of the strip at once (one line per row): the unrolled loop below then runs on L1 hits
+    // instead of serialising on DRAM latency a few rows at a time
+    for (int r = lane; r < BLUR_RB + 6; r += 32) {
+        const int by = min(y0 + r - 3 + ORB_EDGE, G.rows - 1);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(src + (size_t)by * wpr + min(((tx * BLUR_TW + 16) >> 2) + 16, wpr - 1)));
+    }
     // Horizontal pass: the 7 taps of one output are two 4-byte dot products (DP4A) on byte windows cut out of the three
     // source words with funnel shifts.  Vertical pass: consecutive filtered rows (16-bit values) are kept packed in pairs
     // P[k] = (h[k], h[k+1]) so that 6 of the 7 taps are three 2-way dot products (DP2A) and the 7th one multiply-add.
