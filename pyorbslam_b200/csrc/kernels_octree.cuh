@@ -43,14 +43,12 @@ __device__ __forceinline__ int block_excl_scan(int v, int* tmp, int* total) {
     __syncthreads();                      // tmp may still be read from a previous call
     if (lane == 31) tmp[warp] = incl;
     __syncthreads();
-    int base = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < OCT_WARPS; ++w) {
-        const int t = tmp[w];
-        if (w < warp) base += t;
-        tot += t;
-    }
-    *total = tot;
+    // cross-warp combine: lanes 0..OCT_WARPS-1 of every warp scan the OCT_WARPS warp sums with shuffles
+    static_assert(OCT_WARPS <= 32, "one lane per warp sum");
+    const int ws = lane < OCT_WARPS ? tmp[lane] : 0;
+    const int wincl = warp_incl_scan(ws, lane);
+    *total = __shfl_sync(0xffffffffu, wincl, OCT_WARPS - 1);
+    const int base = __shfl_sync(0xffffffffu, wincl - ws, warp);
     return base + incl - v;
 }
 
