@@ -128,7 +128,8 @@ def test_drop_in_compute_stereo_matches_resident_and_host_paths(golden_dir):
     assert Cls.compute_stereo_matches is compute_stereo_matches and orig is not None
 
 
-@pytest.mark.parametrize("case", ["noise", "smooth", "odd_params", "right_view", "three_levels", "scale_1.5"])
+@pytest.mark.parametrize("case", ["noise", "smooth", "odd_params", "right_view", "three_levels", "scale_1.5", "scale_2.0", "scale_2.6",
+                                  "one_wide_cell", "two_wide_cells", "tall_cells", "single_level"])
 def test_extractor_vs_oracle_seeded(case):
     rng = np.random.default_rng(11)
     params = KITTI
@@ -142,6 +143,24 @@ def test_extractor_vs_oracle_seeded(case):
         params = (500, 1.3, 5, 15, 5)
     elif case == "right_view":
         img = make_stereo_pair(3)[1]
+    elif case == "scale_2.0":             # resize: 4 output columns span more than one 12-byte window -> per-byte path
+        img = make_stereo_pair(21, 400, 700)[0]
+        params = (600, 2.0, 3, 20, 7)
+    elif case == "scale_2.6":
+        img = make_stereo_pair(22, 480, 900)[0]
+        params = (500, 2.6, 3, 18, 6)
+    elif case == "one_wide_cell":         # detection width 59 px: a single cell column 59 px wide (16 lanes per row in FAST phase 1)
+        img = rng.integers(0, 256, (120, 85), dtype=np.uint8)
+        params = (200, 1.2, 1, 20, 7)
+    elif case == "two_wide_cells":        # cells 45 px wide and 59 px tall
+        img = rng.integers(0, 256, (85, 115), dtype=np.uint8)
+        params = (200, 1.2, 2, 20, 7)
+    elif case == "tall_cells":            # 59-px-tall cells: both halves of the 64-row bitmap expansion
+        img = make_stereo_pair(23, 85, 640)[0]
+        params = (300, 1.2, 2, 12, 5)
+    elif case == "single_level":
+        img = make_stereo_pair(24, 376, 1241)[0]
+        params = (1000, 1.2, 1, 20, 7)
     elif case == "three_levels":
         img = make_stereo_pair(8, 200, 333)[0]
         params = (60, 1.2, 3, 20, 7)       # tiny quota: the octree stops after its first passes
