@@ -350,7 +350,7 @@ struct Engine {
             ++g_launches;
         }
         if (evs) cudaEventRecord(evs[4], st);
-        k_octree<<<dim3(P.nlevels, n), OCT_THREADS, hp.oct_smem, st>>>(P, d_cand, d_cellcnt, d_scratch, d_lvlkp, d_lvlcnt, hp.oct_capN,
+        k_octree<<<dim3(n, P.nlevels), OCT_THREADS, hp.oct_smem, st>>>(P, d_cand, d_cellcnt, d_scratch, d_lvlkp, d_lvlcnt, hp.oct_capN,
                                                                       hp.oct_capK, hp.oct_capC, d_octnodes, hp.oct_node_stride);
         ++g_launches;
         if (evs) cudaEventRecord(evs[5], st);
