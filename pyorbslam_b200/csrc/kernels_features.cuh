@@ -308,7 +308,7 @@ __device__ __forceinline__ const u8* view_ptr(const u8* base, const StereoGeom& 
     return base + SG.base[o] + (size_t)pr * SG.pitch[o] + (lin - pr * SG.plog[o]);
 }
 
-__global__ void __launch_bounds__(ST_WARPS * 32) k_stereo(const __grid_constant__ StereoGeom SG, const StereoArgs A) {
+__global__ void __launch_bounds__(ST_WARPS * 32, 8) k_stereo(const __grid_constant__ StereoGeom SG, const StereoArgs A) {
     __shared__ unsigned char s_win[ST_WARPS][11 * 11 + 11 * 21 + 4];
     const int pair = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nL = A.nL[(size_t)pair * A.n_stride];
