@@ -251,7 +251,7 @@ struct Engine {
     u8 *d_pyr = nullptr, *d_blur = nullptr;
     u32 *d_cand = nullptr, *d_scratch = nullptr, *d_lvlkp = nullptr;
     int *d_cellcnt = nullptr, *d_lvlcnt = nullptr, *d_status = nullptr, *d_rowstart = nullptr, *d_sorted = nullptr;
-    int2* d_rmeta = nullptr;
+    int4* d_rmeta = nullptr;
     unsigned char* d_octnodes = nullptr;     // node arrays of k_octree when they do not fit in shared memory
     XTab* d_xtab = nullptr;
     XGroup* d_xgrp = nullptr;
@@ -396,7 +396,7 @@ int launch_stereo(const StereoGeom& SG, StereoArgs A, int max_left, int pairs, c
     A.reach = (int)ceil(2.0 * smax) + 2;
     const size_t smem = (size_t)(2 * SG.nRows + 1) * sizeof(int);
     k_rowindex<<<pairs, RI_THREADS, smem, st>>>(A.kpsR, A.nR, A.kp_stride, A.n_stride, A.kp_row, A.oct_idx, SG, (int*)A.rowStart,
-                                                (int*)A.sorted, (int2*)A.rmeta, A.idx_stride, A.status);
+                                                (int*)A.sorted, (int4*)A.rmeta, A.idx_stride, A.status);
     ++g_launches;
     dim3 grid((max_left + ST_WARPS - 1) / ST_WARPS, pairs);
     k_stereo<<<grid, ST_WARPS * 32, 0, st>>>(SG, A);
@@ -729,7 +729,7 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     u8 *d_blob = nullptr, *d_dL = nullptr, *d_dR = nullptr;
     float *d_kL = nullptr, *d_kR = nullptr, *d_u = nullptr, *d_d = nullptr;
     int *d_m = nullptr, *d_n = nullptr, *d_rs = nullptr, *d_so = nullptr;
-    int2* d_rm = nullptr;
+    int4* d_rm = nullptr;
     int rc = 0;
     auto cleanup = [&]() { cudaFree(d_blob); cudaFree(d_dL); cudaFree(d_dR); cudaFree(d_kL); cudaFree(d_kR); cudaFree(d_u); cudaFree(d_d); cudaFree(d_m); cudaFree(d_n); cudaFree(d_rs); cudaFree(d_so); cudaFree(d_rm); };
 #define CU_TRY2(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(B200ORB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
@@ -744,7 +744,7 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     CU_TRY2(cudaMalloc((void**)&d_n, 12));
     CU_TRY2(cudaMalloc((void**)&d_rs, (size_t)(lh[0] + 1) * 4));
     CU_TRY2(cudaMalloc((void**)&d_so, (size_t)std::max(nRight, 1) * 4));
-    CU_TRY2(cudaMalloc((void**)&d_rm, (size_t)std::max(nRight, 1) * 8));
+    CU_TRY2(cudaMalloc((void**)&d_rm, (size_t)std::max(nRight, 1) * 16));
     for (int l = 0; l < nlevels; ++l) {
         CU_TRY2(cudaMemcpy(d_blob + SG.base[l], pyrL[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice));
         CU_TRY2(cudaMemcpy(d_blob + total + SG.base[l], pyrR[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice));

@@ -217,11 +217,11 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_co
 // One CTA per right image.
 // ------------------------------------------------------------------------------------------------
 #define RI_THREADS 256
-// It also writes, per right keypoint, the 8 bytes the matcher needs: uR and minr | maxr << 12 | octave << 24, where
+// It also writes, per SORTED position, the 16 bytes the matcher needs: uR, minr | maxr << 12 | octave << 24 and the keypoint index, where
 // minr = floor(y - 2s), maxr = ceil(y + 2s) are evaluated in double exactly like Frame.py:173-176.
 __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict__ kpsR, const int* __restrict__ nR, long long kp_stride,
                                                          int n_stride, int kp_row, int oct_idx, const __grid_constant__ StereoGeom SG,
-                                                         int* __restrict__ rowStart, int* __restrict__ sorted, int2* __restrict__ rmeta,
+                                                         int* __restrict__ rowStart, int* __restrict__ sorted, int4* __restrict__ rmeta,
                                                          int idx_stride, int* __restrict__ status) {
     const int nRows = SG.nRows;
     extern __shared__ int ri_hist[];     // nRows + 1 counters, then nRows cursors
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict
     const float* k = kpsR + (size_t)pair * kp_stride;
     int* rs = rowStart + (size_t)pair * (nRows + 1);
     int* so = sorted + (size_t)pair * idx_stride;
-    int2* rm = rmeta + (size_t)pair * idx_stride;
+    int4* rm = rmeta + (size_t)pair * idx_stride;
     int* cursor = ri_hist + nRows + 1;
     for (int i = threadIdx.x; i <= nRows; i += RI_THREADS) ri_hist[i] = 0;
     __syncthreads();
@@ -266,9 +266,10 @@ __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict
         const int o = min(max((int)r[oct_idx], 0), SG.nlevels - 1);
         const double y = (double)r[1], reach = 2.0 * (double)SG.sf[o];
         const int minr = min(max((int)floor(y - reach), 0), 4095), maxr = min(max((int)ceil(y + reach), 0), 4095);
-        rm[j] = make_int2(__float_as_int(r[0]), minr | (maxr << 12) | (o << 24));
         if (row < 0 || row >= nRows) continue;
-        so[atomicAdd(&cursor[row], 1)] = j;
+        const int pos = atomicAdd(&cursor[row], 1);
+        so[pos] = j;
+        rm[pos] = make_int4(__float_as_int(r[0]), minr | (maxr << 12) | (o << 24), j, 0);   // stored in SORTED order: one load per candidate
     }
 }
 
@@ -293,7 +294,7 @@ struct StereoArgs {
     int n_stride;                                           // stride of nL / nR between pairs (ints)
     int kp_row, oct_idx;                                    // floats per keypoint row, index of the octave
     int out_stride;                                         // rows per pair in the outputs
-    const int* rowStart; const int* sorted; const int2* rmeta; int idx_stride; // row index + metadata of the right keypoints (k_rowindex)
+    const int* rowStart; const int* sorted; const int4* rmeta; int idx_stride; // row index + metadata of the right keypoints (k_rowindex)
     int reach;                                              // bins to visit on each side of the left keypoint's row
     float mbf32, mb, maxD;
     double mbf;
@@ -319,7 +320,6 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 8) k_stereo(const __grid_consta
     const u8* dL = A.descL + (size_t)pair * A.desc_stride;
     const u8* dR = A.descR + (size_t)pair * A.desc_stride;
     const int* rs = A.rowStart + (size_t)pair * (SG.nRows + 1);
-    const int* so = A.sorted + (size_t)pair * A.idx_stride;
 
     const float* p = kL + (size_t)iL * A.kp_row;
     const float uL = p[0], vL = p[1];
@@ -333,10 +333,10 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 8) k_stereo(const __grid_consta
         const uint4* dl = reinterpret_cast<const uint4*>(dL + (size_t)iL * 32);
         const uint4 l0 = dl[0], l1 = dl[1];
         const int c0 = rs[max(row - A.reach, 0)], c1 = rs[min(row + A.reach + 1, SG.nRows)];
-        const int2* rm = A.rmeta + (size_t)pair * A.idx_stride;
+        const int4* rm = A.rmeta + (size_t)pair * A.idx_stride;
         for (int c = c0 + lane; c < c1; c += 32) {
-            const int j = so[c];
-            const int2 m = rm[j];
+            const int4 m = rm[c];
+            const int j = m.z;
             const float uR = __int_as_float(m.x);
             const int oR = m.y >> 24, minr = m.y & 0xfff, maxr = (m.y >> 12) & 0xfff;
             if (row < minr || row > maxr || oR < oL - 1 || oR > oL + 1 || !(minU <= uR) || !(uR <= uL)) continue;
