@@ -286,6 +286,7 @@ struct Engine {
         CU_TRY(cudaSetDevice(device));
         release();
         if (!aux) {
+            if (const char* s = getenv("B200ORB_SERIAL_LEVELS")) overlap_levels = !(s[0] && s[0] != '0');   // one launch per stage, e.g. under ncu
             CU_TRY(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
             for (int l = 0; l < ORB_MAX_LEVELS; ++l) CU_TRY(cudaEventCreateWithFlags(&ev_lvl[l], cudaEventDisableTiming));
             CU_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
@@ -339,6 +340,8 @@ struct Engine {
                 cudaEvent_t* evs = nullptr) {
         if (n < 1 || n > S) return fail(B200ORB_E_ARG, "slot count out of range");
         const Plan& P = hp.P;
+        // a handful of images cannot fill the GPU either way: keep the short serial launch sequence for the one-frame API
+        const bool overlap_levels = this->overlap_levels && n >= 16;
         {
             const LevelGeom& G = P.lv[0];
             dim3 grid(((G.pitch >> 4) * G.rows + 255) / 256, n);
