@@ -514,7 +514,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=None, help="stereo pairs per GPU per step (kitti: 4096 = BASELINE.json configs[2])")
     ap.add_argument("--chunk", type=int, default=None, help="pairs per kernel-sequence launch (kitti: 128)")
     ap.add_argument("--base-pairs", type=int, default=16, help="distinct synthetic scenes per rank")
-    ap.add_argument("--e2e-pairs", type=int, default=2048, help="pairs per end-to-end step (pinned host memory: 0.93 MB in + 0.25 MB out per pair)")
+    ap.add_argument("--e2e-pairs", type=int, default=4096, help="pairs per end-to-end step, capped at --pairs (pinned host memory: 0.93 MB in + 0.25 MB out per pair)")
     ap.add_argument("--streams", type=int, default=1, help="front-ends running consecutive chunks concurrently (own workspace + stream each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
