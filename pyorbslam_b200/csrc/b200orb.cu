@@ -218,7 +218,7 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
     hp.fast_SP = round_up(15 + FAST_WARPS * maxw + 6 + 16, 16);   // rows are bulk-copied in 16-byte units from a 16-byte aligned start
     hp.fast_SR = maxh + 6;
     hp.fast_TP = round_up(maxw + 2, 4);
-    hp.fast_TR = maxh + 2;
+    hp.fast_TR = round_up(maxh + 2, 4);       // TP * TR is a multiple of 16: the tiles are cleared with 128-bit stores
     if (maxw > 63 || maxh > 63) return fail(B200ORB_E_ARG, "FAST cell larger than 63 px (level narrower than 62 px after the border?)");
     hp.fast_LC = round_up(std::max(maxw * maxh, 2), 8);            // 16-byte multiple: the row bitmaps behind the lists are read as uint2 / uint4
     hp.fast_smem = (size_t)hp.fast_SP * hp.fast_SR + (size_t)FAST_WARPS * hp.fast_TP * hp.fast_TR + (size_t)FAST_WARPS * hp.fast_LC * 2 +
@@ -367,7 +367,7 @@ struct Engine {
             if (evs) cudaEventRecord(evs[3], st);
             if (P.fast_ctas > 0) {
                 k_fast_cells<<<dim3(P.fast_ctas, n), FAST_WARPS * 32, hp.fast_smem, st>>>(P, d_pyr, d_cand, d_cellcnt, hp.fast_SP, hp.fast_SR,
-                                                                                       hp.fast_TP, hp.fast_TR, hp.fast_LC, 0);
+                                                                                       hp.fast_TP, hp.fast_TR, hp.fast_LC, 0, -1);
                 ++g_launches;
             }
             if (evs) cudaEventRecord(evs[4], st);
@@ -381,7 +381,7 @@ struct Engine {
                 const int f0 = G.fast_cta_ofs, f1 = l + 1 < P.nlevels ? P.lv[l + 1].fast_cta_ofs : P.fast_ctas;
                 if (f1 > f0) {
                     k_fast_cells<<<dim3(f1 - f0, n), FAST_WARPS * 32, hp.fast_smem, aux>>>(P, d_pyr, d_cand, d_cellcnt, hp.fast_SP, hp.fast_SR,
-                                                                                        hp.fast_TP, hp.fast_TR, hp.fast_LC, f0);
+                                                                                        hp.fast_TP, hp.fast_TR, hp.fast_LC, f0, l);
                     ++g_launches;
                 }
                 const int b0 = G.blur_cta_ofs, b1 = l + 1 < P.nlevels ? P.lv[l + 1].blur_cta_ofs : P.blur_ctas;

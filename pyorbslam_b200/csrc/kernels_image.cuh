@@ -480,13 +480,15 @@ __device__ __forceinline__ int fast_score(const u8* p, int SP, int t) {
 __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
                                                                 u32* __restrict__ cand, int* __restrict__ cellcnt,
                                                                 int SP /*strip pitch*/, int SR /*strip rows*/, int TP /*tile pitch*/, int TR /*tile rows*/,
-                                                                int LC /*list capacity per warp*/, int cta_base /*first CTA of this launch*/) {
+                                                                int LC /*list capacity per warp*/, int cta_base /*first CTA of this launch*/,
+                                                                int level /*all CTAs of this launch belong to it; -1: search*/) {
     extern __shared__ __align__(16) u8 smem[];
     u8* strip = smem;
     const int slot = blockIdx.y;
     int l = 0;
     const int bid = (int)blockIdx.x + cta_base;
-    while (l + 1 < P.nlevels && bid >= P.lv[l + 1].fast_cta_ofs) ++l;
+    if (level >= 0) l = level;
+    else while (l + 1 < P.nlevels && bid >= P.lv[l + 1].fast_cta_ofs) ++l;
     const LevelGeom& G = P.lv[l];
     const int local = bid - G.fast_cta_ofs;
     const int ci = local / G.fast_groups, g = local - ci * G.fast_groups;
@@ -516,7 +518,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_con
     }
     // zero this warp's score tile while the copies are in flight (the rim is what "outside the window scores 0" means)
     u8* tile = smem + SP * SR + warp * (TP * TR);
-    for (int i = lane; i < (TP * TR) >> 2; i += 32) reinterpret_cast<u32*>(tile)[i] = 0u;
+    for (int i = lane; i < (TP * TR) >> 4; i += 32) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);   // TP, TR multiples of 4
     if (have_strip) mbar_wait(&strip_bar, 0);
     __syncwarp();
 
