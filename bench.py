@@ -514,7 +514,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=None, help="stereo pairs per GPU per step (kitti: 4096 = BASELINE.json configs[2])")
     ap.add_argument("--chunk", type=int, default=None, help="pairs per kernel-sequence launch (kitti: 128)")
     ap.add_argument("--base-pairs", type=int, default=16, help="distinct synthetic scenes per rank")
-    ap.add_argument("--e2e-pairs", type=int, default=4096, help="pairs per end-to-end step, capped at --pairs (pinned host memory: 0.93 MB in + 0.25 MB out per pair)")
+    ap.add_argument("--e2e-pairs", type=int, default=None, help="pairs per end-to-end step, capped at --pairs; default 4096, 2048 when more than 4 ranks "
+                    "share the host (pinned host memory: 0.93 MB in + 0.25 MB out per pair and rank)")
     ap.add_argument("--streams", type=int, default=1, help="front-ends running consecutive chunks concurrently (own workspace + stream each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -524,6 +525,8 @@ def main():
     H, W, ORB, WORKLOAD_NAME = wl["H"], wl["W"], wl["orb"], wl["name"]
     args.pairs = args.pairs or wl["pairs"]
     args.chunk = args.chunk or wl["chunk"]
+    if args.e2e_pairs is None:
+        args.e2e_pairs = 4096 if int(os.environ.get("WORLD_SIZE", "1")) <= 4 else 2048
     args.e2e_pairs = min(args.e2e_pairs, args.pairs)
     claim_stdout()
     if args.impl == "reference":
