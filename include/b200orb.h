@@ -192,6 +192,33 @@ int b200orb_vocab_transform_resident(b200orb_vocab* v, b200orb_extractor* e, int
  * (pyorbslam_b200/matcher.py) and looks distances up in this matrix. */
 int b200orb_hamming_matrix(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, uint16_t* out);
 
+/* SURVEY.md 8(f) rank 1, projection searches (ORBMatcher.search_by_projection_f_p, ORBMatcher.py:215-283, and
+ * search_by_projection_f_f, ORBMatcher.py:291-393): Frame.get_features_in_area (Frame.py:373-416) for M queries at once, fused with
+ * the Hamming distance from each query's descriptor to every feature it returns (ORBMatcher.descriptor_distance, ORBMatcher.py:12-14).
+ *   kxy / koct / kdesc   the frame's N undistorted keypoints (x, y), octaves and 32-byte descriptors (mvKeysUn, mDescriptors)
+ *   cell_start / cell_idx the frame's mGrid (Frame.assign_features_to_grid, Frame.py:153-159) as CSR over cell ix * rows + iy,
+ *                         features of a cell in the order they were appended
+ *   qxyr[M][3]           x, y, r of each query as the reference passes them; f32_mode != 0 when its scalar arithmetic ran in float32
+ *                         (a NumPy float32 coordinate with Python-float radius, NumPy >= 2 promotion), 0 for float64
+ *   qlvl[M][2]           min_level, max_level;   qcell[M][4]   n_min_cell_x, n_max_cell_x, n_min_cell_y, n_max_cell_y as evaluated by
+ *                         the caller with the reference's own expressions (Frame.py:376-390; min > max = no cell)
+ *   qdesc[M][32]         the query descriptors (MapPoint.get_descriptor())
+ * Output (CSR over the queries): cand_start[M + 1], cand_idx / cand_dist[cap] in the order get_features_in_area returns them.
+ * *total = number of candidates; B200ORB_E_RANGE with *total set when cap is too small (call again with larger buffers). */
+int b200orb_area_hamming(int device, int f32_mode, int N, const float* kxy, const int32_t* koct, const uint8_t* kdesc, int cols, int rows,
+                         const int32_t* cell_start, const int32_t* cell_idx, int M, const double* qxyr, const int32_t* qlvl,
+                         const int32_t* qcell, const uint8_t* qdesc, int32_t* cand_start, int32_t* cand_idx, int32_t* cand_dist, int cap,
+                         int32_t* total);
+/* The order-dependent selection of the two searches on those candidate lists (host side: each decision depends on the matches made for
+ * the earlier map points).  ok[c] = 0 marks candidates failing the right-image check (ORBMatcher.py:246-249, 345-349), occupied[j] != 0
+ * features that hold a map point with observations() > 0 (updated in place), marks[q] != 0 map points with observations() > 0.
+ * best[q] = matched feature or -1.  _ff: best distance <= th_high (ORBMatcher.py:335-366); _fp: best / second best with the octave
+ * and ratio test (ORBMatcher.py:236-281). */
+int b200orb_greedy_project_ff(int M, const int32_t* start, const int32_t* idx, const int32_t* dist, const uint8_t* ok, int N,
+                              uint8_t* occupied, const uint8_t* marks, int th_high, int32_t* best);
+int b200orb_greedy_project_fp(int M, const int32_t* start, const int32_t* idx, const int32_t* dist, const uint8_t* ok, int N,
+                              uint8_t* occupied, const uint8_t* marks, const int32_t* koct, int th_high, double nnratio, int32_t* best);
+
 /* pinned host memory helpers for callers without their own allocator */
 int b200orb_host_alloc(void** p, size_t bytes);
 int b200orb_host_free(void* p);

@@ -250,7 +250,7 @@ struct Engine {
     bool planned = false;
     u8 *d_pyr = nullptr, *d_blur = nullptr;
     u32 *d_cand = nullptr, *d_scratch = nullptr, *d_lvlkp = nullptr;
-    int *d_cellcnt = nullptr, *d_lvlcnt = nullptr, *d_status = nullptr, *d_rowstart = nullptr, *d_sorted = nullptr;
+    int *d_cellcnt = nullptr, *d_lvlcnt = nullptr, *d_status = nullptr, *d_rowstart = nullptr;
     int4* d_rmeta = nullptr;
     bool overlap_levels = true;              // per-level FAST / blur on `aux` underneath the resize chain (see extract())
     cudaStream_t aux = nullptr;
@@ -265,8 +265,8 @@ struct Engine {
 
     void release() {
         cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_cand); cudaFree(d_scratch); cudaFree(d_lvlkp);
-        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_xgrp); d_xgrp = nullptr; cudaFree(d_mtab); d_mtab = nullptr; cudaFree(d_fpat); d_fpat = nullptr; cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_sorted); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr;
-        d_pyr = d_blur = nullptr; d_cand = d_scratch = d_lvlkp = nullptr; d_cellcnt = d_lvlcnt = d_status = d_rowstart = d_sorted = nullptr;
+        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_xgrp); d_xgrp = nullptr; cudaFree(d_mtab); d_mtab = nullptr; cudaFree(d_fpat); d_fpat = nullptr; cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr;
+        d_pyr = d_blur = nullptr; d_cand = d_scratch = d_lvlkp = nullptr; d_cellcnt = d_lvlcnt = d_status = d_rowstart = nullptr;
         d_xtab = nullptr; d_ytab = nullptr; planned = false; bytes = 0;
     }
     void release_streams() {
@@ -303,7 +303,6 @@ struct Engine {
         TRY(alloc(&d_lvlcnt, (size_t)S * P.nlevels));
         TRY(alloc(&d_status, 1));
         TRY(alloc(&d_rowstart, (size_t)S * (P.lv[0].h + 1)));
-        TRY(alloc(&d_sorted, (size_t)S * P.kp_total));
         TRY(alloc(&d_rmeta, (size_t)S * P.kp_total));
         if (hp.oct_global_nodes) TRY(alloc(&d_octnodes, (size_t)S * P.nlevels * hp.oct_node_stride));
         TRY(alloc(&d_xtab, hp.xtab.size()));
@@ -430,7 +429,7 @@ void fill_stereo_consts(StereoArgs& A, double mbf, float fx) {
     A.maxD = A.mbf32 / A.mb;         // Frame.py:183
 }
 
-// row index of the right keypoints, then the matcher.  A.rowStart / A.sorted / A.idx_stride must point at
+// row index of the right keypoints, then the matcher.  A.rowStart / A.rmeta / A.idx_stride must point at
 // (nRows + 1) and idx_stride ints per pair of scratch.
 int launch_stereo(const StereoGeom& SG, StereoArgs A, int max_left, int pairs, cudaStream_t st, int flags = 0) {
     if (pairs < 1 || max_left < 1) return 0;
@@ -439,7 +438,7 @@ int launch_stereo(const StereoGeom& SG, StereoArgs A, int max_left, int pairs, c
     A.reach = (int)ceil(2.0 * smax) + 2;
     const size_t smem = (size_t)(2 * SG.nRows + 1) * sizeof(int);
     k_rowindex<<<pairs, RI_THREADS, smem, st>>>(A.kpsR, A.nR, A.kp_stride, A.n_stride, A.kp_row, A.oct_idx, SG, (int*)A.rowStart,
-                                                (int*)A.sorted, (int4*)A.rmeta, A.idx_stride, A.status);
+                                                (int4*)A.rmeta, A.idx_stride, A.status);
     ++g_launches;
     dim3 grid((max_left + ST_WARPS - 1) / ST_WARPS, pairs);
     k_stereo<<<grid, ST_WARPS * 32, 0, st>>>(SG, A);
@@ -723,7 +722,7 @@ int b200orb_stereo_ex(b200orb_extractor* L, b200orb_extractor* R, double mbf, fl
     A.pyrL = L->eng.d_pyr; A.pyrR = R->eng.d_pyr;
     A.kp_row = 6; A.oct_idx = 5; A.out_stride = PL.kp_total;
     A.uRight = L->d_uR; A.depth = L->d_depth; A.matchIdx = L->d_match; A.status = L->eng.d_status; A.sadDist = L->d_sad;
-    A.rowStart = L->eng.d_rowstart; A.sorted = L->eng.d_sorted; A.rmeta = L->eng.d_rmeta; A.idx_stride = PL.kp_total;
+    A.rowStart = L->eng.d_rowstart; A.rmeta = L->eng.d_rmeta; A.idx_stride = PL.kp_total;
     fill_stereo_consts(A, mbf, fx);
     CU_TRY(cudaMemsetAsync(L->eng.d_status, 0, 4, L->st));
     TRY(launch_stereo(SG, A, L->n, 1, L->st, flags));
@@ -771,10 +770,10 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     }
     u8 *d_blob = nullptr, *d_dL = nullptr, *d_dR = nullptr;
     float *d_kL = nullptr, *d_kR = nullptr, *d_u = nullptr, *d_d = nullptr;
-    int *d_m = nullptr, *d_n = nullptr, *d_rs = nullptr, *d_so = nullptr;
+    int *d_m = nullptr, *d_n = nullptr, *d_rs = nullptr;
     int4* d_rm = nullptr;
     int rc = 0;
-    auto cleanup = [&]() { cudaFree(d_blob); cudaFree(d_dL); cudaFree(d_dR); cudaFree(d_kL); cudaFree(d_kR); cudaFree(d_u); cudaFree(d_d); cudaFree(d_m); cudaFree(d_n); cudaFree(d_rs); cudaFree(d_so); cudaFree(d_rm); };
+    auto cleanup = [&]() { cudaFree(d_blob); cudaFree(d_dL); cudaFree(d_dR); cudaFree(d_kL); cudaFree(d_kR); cudaFree(d_u); cudaFree(d_d); cudaFree(d_m); cudaFree(d_n); cudaFree(d_rs); cudaFree(d_rm); };
 #define CU_TRY2(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(B200ORB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
     CU_TRY2(cudaMalloc((void**)&d_blob, (size_t)total * 2));
     CU_TRY2(cudaMalloc((void**)&d_kL, (size_t)nLeft * 12));
@@ -786,7 +785,6 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     CU_TRY2(cudaMalloc((void**)&d_m, (size_t)nLeft * 4));
     CU_TRY2(cudaMalloc((void**)&d_n, 12));
     CU_TRY2(cudaMalloc((void**)&d_rs, (size_t)(lh[0] + 1) * 4));
-    CU_TRY2(cudaMalloc((void**)&d_so, (size_t)std::max(nRight, 1) * 4));
     CU_TRY2(cudaMalloc((void**)&d_rm, (size_t)std::max(nRight, 1) * 16));
     for (int l = 0; l < nlevels; ++l) {
         CU_TRY2(cudaMemcpy(d_blob + SG.base[l], pyrL[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice));
@@ -806,7 +804,7 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     A.pyrL = d_blob; A.pyrR = d_blob + total;
     A.kp_row = 3; A.oct_idx = 2; A.out_stride = nLeft;
     A.uRight = d_u; A.depth = d_d; A.matchIdx = d_m; A.status = d_n + 2;
-    A.rowStart = d_rs; A.sorted = d_so; A.rmeta = d_rm; A.idx_stride = std::max(nRight, 1);
+    A.rowStart = d_rs; A.rmeta = d_rm; A.idx_stride = std::max(nRight, 1);
     fill_stereo_consts(A, mbf, fx);
     rc = launch_stereo(SG, A, nLeft, 1, nullptr);
     if (rc) { cleanup(); return rc; }
@@ -885,7 +883,7 @@ int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint
     A.kp_stride = (long long)C * 6; A.desc_stride = (long long)C * 32; A.pyr_stride = P.pyr_bytes;
     A.kp_row = 6; A.oct_idx = 5; A.out_stride = (int)C;
     A.uRight = d_uRight; A.depth = d_depth; A.matchIdx = d_matchIdx; A.status = b->eng.d_status;
-    A.rowStart = b->eng.d_rowstart; A.sorted = b->eng.d_sorted; A.rmeta = b->eng.d_rmeta; A.idx_stride = (int)C;
+    A.rowStart = b->eng.d_rowstart; A.rmeta = b->eng.d_rmeta; A.idx_stride = (int)C;
     fill_stereo_consts(A, mbf, fx);
     if (b->stereo_flags & B200ORB_STEREO_MEDIAN_CULL) {
         if (!b->d_sad) CU_TRY(cudaMalloc((void**)&b->d_sad, (size_t)b->P * C * 4));
@@ -1119,6 +1117,120 @@ int b200orb_hamming_matrix(int device, const uint8_t* A, int nA, const uint8_t* 
     if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpy(out, dO, (size_t)nA * nB * 2, cudaMemcpyDeviceToHost)) != cudaSuccess)
         return done(fail(B200ORB_E_CUDA, std::string("k_hamming_matrix: ") + cudaGetErrorString(e)));
     return done(0);
+}
+
+// ---------------------------------------------------------------- projection searches
+int b200orb_area_hamming(int device, int f32_mode, int N, const float* kxy, const int32_t* koct, const uint8_t* kdesc, int cols, int rows,
+                         const int32_t* cell_start, const int32_t* cell_idx, int M, const double* qxyr, const int32_t* qlvl,
+                         const int32_t* qcell, const uint8_t* qdesc, int32_t* cand_start, int32_t* cand_idx, int32_t* cand_dist, int cap,
+                         int32_t* total) {
+    if (N < 0 || M < 0 || cols < 1 || rows < 1 || cap < 0) return fail(B200ORB_E_ARG, "bad sizes");
+    if (!cand_start || !total) return fail(B200ORB_E_ARG, "NULL argument");
+    *total = 0;
+    for (int q = 0; q <= M; ++q) cand_start[q] = 0;
+    if (M == 0) return 0;
+    if (!cell_start || !qxyr || !qlvl || !qcell || !qdesc || (N > 0 && (!kxy || !koct || !kdesc))) return fail(B200ORB_E_ARG, "NULL argument");
+    const int ncell = cols * rows, nidx = cell_start[ncell];
+    if (cell_start[0] != 0 || nidx < 0 || nidx > N || (nidx > 0 && !cell_idx)) return fail(B200ORB_E_ARG, "bad grid CSR");
+    for (int c = 0; c < ncell; ++c) if (cell_start[c + 1] < cell_start[c]) return fail(B200ORB_E_ARG, "bad grid CSR");
+    for (int i = 0; i < nidx; ++i) if (cell_idx[i] < 0 || cell_idx[i] >= N) return fail(B200ORB_E_RANGE, "grid entry is not a feature index");
+    std::vector<int> qc((size_t)M * 4);
+    for (int q = 0; q < M; ++q) {
+        const int c0 = qcell[4 * q], c1 = qcell[4 * q + 1], r0 = qcell[4 * q + 2], r1 = qcell[4 * q + 3];
+        const bool empty = c0 > c1 || r0 > r1;
+        if (!empty && (c0 < 0 || c1 >= cols || r0 < 0 || r1 >= rows)) return fail(B200ORB_E_RANGE, "query cell range leaves the grid");
+        qc[4 * q] = empty ? 1 : c0; qc[4 * q + 1] = empty ? 0 : c1; qc[4 * q + 2] = empty ? 0 : r0; qc[4 * q + 3] = empty ? 0 : r1;
+    }
+    CU_TRY(cudaSetDevice(device));
+    double* d_q = nullptr; int *d_lvl = nullptr, *d_cell = nullptr, *d_cs = nullptr, *d_ci = nullptr, *d_oct = nullptr, *d_cnt = nullptr, *d_oi = nullptr, *d_od = nullptr;
+    u8 *d_qd = nullptr, *d_kd = nullptr; float* d_xy = nullptr;
+    auto done = [&](int rc) {
+        cudaFree(d_q); cudaFree(d_lvl); cudaFree(d_cell); cudaFree(d_cs); cudaFree(d_ci); cudaFree(d_oct); cudaFree(d_cnt); cudaFree(d_oi);
+        cudaFree(d_od); cudaFree(d_qd); cudaFree(d_kd); cudaFree(d_xy);
+        return rc;
+    };
+    cudaError_t e = cudaSuccess;
+    auto up = [&](auto** dp, const void* src, size_t bytes) {
+        if (e != cudaSuccess) return;
+        if ((e = cudaMalloc((void**)dp, std::max<size_t>(bytes, 16))) != cudaSuccess) return;
+        if (bytes && src) e = cudaMemcpy(*dp, src, bytes, cudaMemcpyHostToDevice);
+    };
+    up(&d_q, qxyr, (size_t)M * 24); up(&d_lvl, qlvl, (size_t)M * 8); up(&d_cell, qc.data(), (size_t)M * 16); up(&d_qd, qdesc, (size_t)M * 32);
+    up(&d_cs, cell_start, (size_t)(ncell + 1) * 4); up(&d_ci, cell_idx, (size_t)nidx * 4); up(&d_xy, kxy, (size_t)N * 8);
+    up(&d_oct, koct, (size_t)N * 4); up(&d_kd, kdesc, (size_t)N * 32); up(&d_cnt, nullptr, (size_t)(M + 1) * 4);
+    if (e != cudaSuccess) return done(fail(B200ORB_E_CUDA, std::string("area_hamming upload: ") + cudaGetErrorString(e)));
+    const dim3 grid((M + AQ_WARPS - 1) / AQ_WARPS);
+    auto launch = [&](int count_only, const int* d_start, int* oi, int* od) {
+        if (f32_mode) k_area_hamming<float><<<grid, AQ_WARPS * 32>>>(M, d_q, d_lvl, d_cell, d_qd, rows, d_cs, d_ci, d_xy, d_oct, d_kd, count_only, d_cnt, d_start, oi, od);
+        else k_area_hamming<double><<<grid, AQ_WARPS * 32>>>(M, d_q, d_lvl, d_cell, d_qd, rows, d_cs, d_ci, d_xy, d_oct, d_kd, count_only, d_cnt, d_start, oi, od);
+        ++g_launches;
+    };
+    launch(1, nullptr, nullptr, nullptr);
+    std::vector<int> cnt(M);
+    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpy(cnt.data(), d_cnt, (size_t)M * 4, cudaMemcpyDeviceToHost)) != cudaSuccess)
+        return done(fail(B200ORB_E_CUDA, std::string("k_area_hamming: ") + cudaGetErrorString(e)));
+    long long sum = 0;
+    for (int q = 0; q < M; ++q) { cand_start[q] = (int32_t)sum; sum += cnt[q]; }
+    if (sum > 0x7fffffffLL) return done(fail(B200ORB_E_RANGE, "too many candidates"));
+    cand_start[M] = (int32_t)sum; *total = (int32_t)sum;
+    if (sum > cap) return done(fail(B200ORB_E_RANGE, "candidate buffers too small (*total holds the size needed)"));
+    if (sum == 0) return done(0);
+    if (!cand_idx || !cand_dist) return done(fail(B200ORB_E_ARG, "NULL argument"));
+    if ((e = cudaMemcpy(d_cnt, cand_start, (size_t)(M + 1) * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&d_oi, (size_t)sum * 4)) != cudaSuccess || (e = cudaMalloc((void**)&d_od, (size_t)sum * 4)) != cudaSuccess)
+        return done(fail(B200ORB_E_CUDA, std::string("area_hamming buffers: ") + cudaGetErrorString(e)));
+    launch(0, d_cnt, d_oi, d_od);
+    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpy(cand_idx, d_oi, (size_t)sum * 4, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+        (e = cudaMemcpy(cand_dist, d_od, (size_t)sum * 4, cudaMemcpyDeviceToHost)) != cudaSuccess)
+        return done(fail(B200ORB_E_CUDA, std::string("k_area_hamming: ") + cudaGetErrorString(e)));
+    return done(0);
+}
+
+// The order-dependent part of the two projection searches, on the candidate lists b200orb_area_hamming produced (host code: every
+// decision depends on the assignments made for the earlier map points, exactly as in the reference's loops).
+//   ok[c]       0 = candidate c fails the caller-evaluated right-image check (ORBMatcher.py:246-249 / 345-349)
+//   occupied[j] feature j already holds a map point with observations() > 0 (ORBMatcher.py:242-244 / 341-343); updated as matches are made
+//   marks[q]    map point q has observations() > 0 (what occupied[] becomes for the feature it is assigned to)
+int b200orb_greedy_project_ff(int M, const int32_t* start, const int32_t* idx, const int32_t* dist, const uint8_t* ok, int N,
+                              uint8_t* occupied, const uint8_t* marks, int th_high, int32_t* best) {
+    if (M < 0 || N < 0) return fail(B200ORB_E_ARG, "bad sizes");
+    if (M == 0) return 0;
+    if (!start || !occupied || !marks || !best || (start[M] > 0 && (!idx || !dist || !ok))) return fail(B200ORB_E_ARG, "NULL argument");
+    for (int q = 0; q < M; ++q) {            // ORBMatcher.py:335-366
+        int bestDist = 256, bestIdx = -1;
+        for (int c = start[q]; c < start[q + 1]; ++c) {
+            const int j = idx[c];
+            if (j < 0 || j >= N) return fail(B200ORB_E_RANGE, "candidate index out of range");
+            if (occupied[j] || !ok[c]) continue;
+            if (dist[c] < bestDist) { bestDist = dist[c]; bestIdx = j; }
+        }
+        best[q] = -1;
+        if (bestDist <= th_high && bestIdx >= 0) { best[q] = bestIdx; occupied[bestIdx] = marks[q]; }
+    }
+    return 0;
+}
+int b200orb_greedy_project_fp(int M, const int32_t* start, const int32_t* idx, const int32_t* dist, const uint8_t* ok, int N,
+                              uint8_t* occupied, const uint8_t* marks, const int32_t* koct, int th_high, double nnratio, int32_t* best) {
+    if (M < 0 || N < 0) return fail(B200ORB_E_ARG, "bad sizes");
+    if (M == 0) return 0;
+    if (!start || !occupied || !marks || !best || !koct || (start[M] > 0 && (!idx || !dist || !ok))) return fail(B200ORB_E_ARG, "NULL argument");
+    for (int q = 0; q < M; ++q) {            // ORBMatcher.py:236-281
+        int b1 = 256, l1 = -1, b2 = 256, l2 = -1, bi = -1;
+        for (int c = start[q]; c < start[q + 1]; ++c) {
+            const int j = idx[c];
+            if (j < 0 || j >= N) return fail(B200ORB_E_RANGE, "candidate index out of range");
+            if (occupied[j] || !ok[c]) continue;
+            const int d = dist[c];
+            if (d < b1) { b2 = b1; b1 = d; l2 = l1; l1 = koct[j]; bi = j; }
+            else if (d < b2) { l2 = koct[j]; b2 = d; }
+        }
+        best[q] = -1;
+        if (b1 <= th_high && bi >= 0) {
+            if (l1 == l2 && (double)b1 > nnratio * (double)b2) continue;
+            best[q] = bi; occupied[bi] = marks[q];
+        }
+    }
+    return 0;
 }
 
 int b200orb_host_alloc(void** p, size_t bytes) {

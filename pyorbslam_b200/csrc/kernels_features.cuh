@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_co
 
 // ------------------------------------------------------------------------------------------------
 // K7a: row index of the RIGHT keypoints (the GPU form of vRowIndices, Frame.py:170-179): counting sort of the
-// right keypoints by integer row into rowStart[nRows + 1] / sorted[nR].  A left keypoint at row v then only
+// right keypoints by integer row into rowStart[nRows + 1] / rmeta[nR] (sorted order).  A left keypoint at row v then only
 // visits the bins v - R .. v + R (R = ceil(2 * max scale) + 2 covers every band) and applies the exact
 // floor(y - 2s) <= v <= ceil(y + 2s) test per candidate.  Order inside a bin is irrelevant: the winner is the
 // minimum of (dist << 20 | right index), which equals the reference's first strict minimum in ascending index.
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_co
 // minr = floor(y - 2s), maxr = ceil(y + 2s) are evaluated in double exactly like Frame.py:173-176.
 __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict__ kpsR, const int* __restrict__ nR, long long kp_stride,
                                                          int n_stride, int kp_row, int oct_idx, const __grid_constant__ StereoGeom SG,
-                                                         int* __restrict__ rowStart, int* __restrict__ sorted, int4* __restrict__ rmeta,
+                                                         int* __restrict__ rowStart, int4* __restrict__ rmeta,
                                                          int idx_stride, int* __restrict__ status) {
     const int nRows = SG.nRows;
     extern __shared__ int ri_hist[];     // nRows + 1 counters, then nRows cursors
@@ -230,7 +230,6 @@ __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict
     const int n = nR[(size_t)pair * n_stride];
     const float* k = kpsR + (size_t)pair * kp_stride;
     int* rs = rowStart + (size_t)pair * (nRows + 1);
-    int* so = sorted + (size_t)pair * idx_stride;
     int4* rm = rmeta + (size_t)pair * idx_stride;
     int* cursor = ri_hist + nRows + 1;
     for (int i = threadIdx.x; i <= nRows; i += RI_THREADS) ri_hist[i] = 0;
@@ -268,7 +267,6 @@ __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict
         const int minr = min(max((int)floor(y - reach), 0), 4095), maxr = min(max((int)ceil(y + reach), 0), 4095);
         if (row < 0 || row >= nRows) continue;
         const int pos = atomicAdd(&cursor[row], 1);
-        so[pos] = j;
         rm[pos] = make_int4(__float_as_int(r[0]), minr | (maxr << 12) | (o << 24), j, 0);   // stored in SORTED order: one load per candidate
     }
 }
@@ -294,7 +292,7 @@ struct StereoArgs {
     int n_stride;                                           // stride of nL / nR between pairs (ints)
     int kp_row, oct_idx;                                    // floats per keypoint row, index of the octave
     int out_stride;                                         // rows per pair in the outputs
-    const int* rowStart; const int* sorted; const int4* rmeta; int idx_stride; // row index + metadata of the right keypoints (k_rowindex)
+    const int* rowStart; const int4* rmeta; int idx_stride;   // row index + sorted metadata of the right keypoints (k_rowindex)
     int reach;                                              // bins to visit on each side of the left keypoint's row
     float mbf32, mb, maxD;
     double mbf;
@@ -541,4 +539,67 @@ __global__ void __launch_bounds__(128) k_hamming_matrix(const u8* __restrict__ A
                            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
         out[(size_t)i * nB + j] = (unsigned short)d;
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Frame.get_features_in_area (Frame.py:373-416) for a batch of queries, fused with the Hamming distance
+// the projection searches take to each feature it returns (ORBMatcher.py:255, 355).  One warp per query walks the query's grid
+// cells in the reference's order (ix outer, iy inner, features of a cell in ascending index = the order
+// assign_features_to_grid appended them, Frame.py:153-159), applies the octave window and the |dx| < r, |dy| < r test, and
+// emits (feature index, distance) in that order with ballot-ranked stores.  The caller evaluates the cell range with the
+// reference's own scalar arithmetic; F is the floating type that arithmetic ran in (NumPy >= 2 keeps float32 when the query
+// coordinate is a float32 scalar and the other operands are Python floats, otherwise it is float64).
+// count_only: pass 1 writes the per-query counts, pass 2 (after a host prefix sum) the entries.
+// ------------------------------------------------------------------------------------------------
+#define AQ_WARPS 8
+template <typename F>
+__global__ void __launch_bounds__(AQ_WARPS * 32) k_area_hamming(int M, const double* __restrict__ qxyr, const int* __restrict__ qlvl,
+                                                                const int* __restrict__ qcell, const u8* __restrict__ qdesc, int rows,
+                                                                const int* __restrict__ cellStart, const int* __restrict__ cellIdx,
+                                                                const float* __restrict__ kxy, const int* __restrict__ koct,
+                                                                const u8* __restrict__ kdesc, int count_only, int* __restrict__ qcount,
+                                                                const int* __restrict__ qstart, int* __restrict__ outIdx,
+                                                                int* __restrict__ outDist) {
+    const int q = blockIdx.x * AQ_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= M) return;
+    const F x = (F)qxyr[3 * q], y = (F)qxyr[3 * q + 1], r = (F)qxyr[3 * q + 2];
+    const int minL = qlvl[2 * q], maxL = qlvl[2 * q + 1];
+    const bool checkLevels = minL > 0 || maxL >= 0;
+    const int c0 = qcell[4 * q], c1 = qcell[4 * q + 1], r0 = qcell[4 * q + 2], r1 = qcell[4 * q + 3];
+    uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+    if (!count_only) {
+        const uint4* dq = reinterpret_cast<const uint4*>(qdesc + (size_t)q * 32);
+        d0 = __ldg(dq); d1 = __ldg(dq + 1);
+    }
+    const u32 lt = (1u << lane) - 1;
+    int n = 0;
+    const int base = count_only ? 0 : qstart[q];
+    for (int ix = c0; ix <= c1; ++ix) {
+        // the cells (ix, r0..r1) are consecutive in the CSR: one contiguous run of feature slots per grid column
+        const int beg = cellStart[ix * rows + r0], end = cellStart[ix * rows + r1 + 1];
+        for (int k = beg; k < end; k += 32) {
+            const int i = k + lane;
+            bool in = false;
+            int g = 0;
+            if (i < end) {
+                g = cellIdx[i];
+                const int o = koct[g];
+                in = !(checkLevels && (o < minL || (maxL >= 0 && o > maxL)));
+                const F dx = (F)kxy[2 * g] - x, dy = (F)kxy[2 * g + 1] - y;
+                in = in && (dx < 0 ? -dx : dx) < r && (dy < 0 ? -dy : dy) < r;
+            }
+            const u32 m = __ballot_sync(0xffffffffu, in);
+            if (in && !count_only) {
+                const uint4* dk = reinterpret_cast<const uint4*>(kdesc + (size_t)g * 32);
+                const uint4 a = __ldg(dk), b = __ldg(dk + 1);
+                const int pos = base + n + __popc(m & lt);
+                outIdx[pos] = g;
+                outDist[pos] = __popc(a.x ^ d0.x) + __popc(a.y ^ d0.y) + __popc(a.z ^ d0.z) + __popc(a.w ^ d0.w) +
+                               __popc(b.x ^ d1.x) + __popc(b.y ^ d1.y) + __popc(b.z ^ d1.z) + __popc(b.w ^ d1.w);
+            }
+            n += __popc(m);
+        }
+    }
+    if (count_only && lane == 0) qcount[q] = n;
 }

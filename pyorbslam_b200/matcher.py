@@ -1,7 +1,9 @@
 """the tracking-side searches of the reference's ORBMatcher -- `search_by_BoW_kf_f`,
 `search_by_BoW_kf_kf` (ORBMatcher.py:21-213), `search_by_projection_f_p` (ORBMatcher.py:215-283) and
-`search_by_projection_f_f` (ORBMatcher.py:291-393) -- with the Hamming distances taken from one GPU all-pairs matrix
-(`b200orb_hamming_matrix`) instead of one Python `bin().count` call per candidate pair (ORBMatcher.py:12-14).
+`search_by_projection_f_f` (ORBMatcher.py:291-393) -- with the Hamming distances taken from the GPU instead of one Python
+`bin().count` call per candidate pair (ORBMatcher.py:12-14): an all-pairs matrix (`b200orb_hamming_matrix`) for the BoW searches,
+and for the projection searches one call that also answers every `Frame.get_features_in_area` query (`b200orb_area_hamming`)
+followed by the order-dependent selection behind the same C ABI (`b200orb_greedy_project_ff / _fp`).
 
 The greedy, order-dependent matching logic (skip already matched features, best / second-best ratio test, rotation
 histogram with its np.argsort tie behaviour, python round()) is restated unchanged on the host -- only the distance
@@ -148,19 +150,117 @@ def search_by_BoW_kf_kf(self, kf1, kf2):
     return n_matches, matches12
 
 
-def _descriptor_rows(map_points, wanted):
-    """uint8[n, 32]: row i = map_points[i].get_descriptor() where wanted[i], zeros elsewhere."""
-    out = np.zeros((len(map_points), 32), np.uint8)
-    for i, (mp, w) in enumerate(zip(map_points, wanted)):
-        if w:
-            out[i] = mp.get_descriptor()
+# ---------------------------------------------------------------- projection searches
+def _elem_float_dtype(values):
+    """dtype of the NumPy floating scalars in `values` (None when there are only Python numbers, which NumPy >= 2 treats as weak)."""
+    dt = None
+    for v in values:
+        if isinstance(v, np.floating):
+            dt = v.dtype if dt is None else np.result_type(dt, v.dtype)
+    return dt
+
+
+def _grid_csr(frame):
+    """frame.mGrid (Frame.assign_features_to_grid, Frame.py:153-159) as CSR over cell ix * rows + iy."""
+    cols, rows = frame.FRAME_GRID_COLS, frame.FRAME_GRID_ROWS
+    start = np.zeros(cols * rows + 1, np.int32)
+    flat = []
+    k = 0
+    for ix in range(cols):
+        col = frame.mGrid[ix]
+        for iy in range(rows):
+            cell = col[iy]
+            if cell:
+                flat.extend(cell)
+            k += 1
+            start[k] = len(flat)
+    return start, np.asarray(flat, np.int32).reshape(-1)
+
+
+def _cell_ranges(frame, x, y, r):
+    """n_min_cell_x .. n_max_cell_y of Frame.get_features_in_area (Frame.py:376-390) for arrays of queries, in the arithmetic the
+    reference's scalar expressions run in: x / y keep their dtype, the frame's Python floats and the radius are cast to it."""
+    dt = x.dtype
+    r = r.astype(dt)
+    minx, miny = dt.type(frame.mnMinX), dt.type(frame.mnMinY)
+    iw, ih = dt.type(frame.mfGridElementWidthInv), dt.type(frame.mfGridElementHeightInv)
+    cols, rows = frame.FRAME_GRID_COLS, frame.FRAME_GRID_ROWS
+    with np.errstate(invalid="ignore", over="ignore"):
+        c0 = np.maximum(0, np.trunc((x - minx - r) * iw)).astype(np.int64)
+        c1 = np.minimum(cols - 1, np.trunc((x - minx + r) * iw)).astype(np.int64)
+        r0 = np.maximum(0, np.trunc((y - miny - r) * ih)).astype(np.int64)
+        r1 = np.minimum(rows - 1, np.trunc((y - miny + r) * ih)).astype(np.int64)
+    empty = (c0 >= cols) | (c1 < 0) | (r0 >= rows) | (r1 < 0)          # the four early returns
+    out = np.stack([c0, c1, r0, r1], 1).astype(np.int32)
+    out[empty] = (1, 0, 0, 0)
     return out
 
 
+def _area_hamming(frame, qx, qy, qr, qlvl, qdesc, device=0):
+    """Candidate lists of Frame.get_features_in_area for every query + Hamming distance to each candidate (one GPU call)."""
+    M = len(qx)
+    start = np.zeros(M + 1, np.int32)
+    if M == 0 or frame.N == 0:
+        return start, np.zeros(0, np.int32), np.zeros(0, np.int32)
+    kxy = np.array([k.pt for k in frame.mvKeysUn], np.float32).reshape(-1, 2)
+    koct = np.array([k.octave for k in frame.mvKeysUn], np.int32)
+    kdesc = np.ascontiguousarray(frame.mDescriptors, np.uint8).reshape(-1, 32)
+    cs, ci = _grid_csr(frame)
+    f32 = qx.dtype == np.float32
+    qcell = _cell_ranges(frame, qx, qy, qr)
+    qxyr = np.ascontiguousarray(np.stack([qx.astype(np.float64), qy.astype(np.float64),
+                                          qr.astype(qx.dtype).astype(np.float64)], 1))
+    qlvl = np.ascontiguousarray(qlvl, np.int32)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    l = _lib.lib()
+    l.b200orb_area_hamming.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 2 + \
+                                      [C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
+    cap = max(64 * M, 1024)
+    total = C.c_int32(0)
+    while True:
+        idx = np.empty(cap, np.int32)
+        dist = np.empty(cap, np.int32)
+        rc = l.b200orb_area_hamming(int(device), int(f32), int(frame.N), kxy.ctypes.data, koct.ctypes.data, kdesc.ctypes.data,
+                                    int(frame.FRAME_GRID_COLS), int(frame.FRAME_GRID_ROWS), cs.ctypes.data, ci.ctypes.data, M,
+                                    qxyr.ctypes.data, qlvl.ctypes.data, qcell.ctypes.data, qdesc.ctypes.data, start.ctypes.data,
+                                    idx.ctypes.data, dist.ctypes.data, cap, C.byref(total))
+        if rc != 0 and total.value > cap:
+            cap = total.value
+            continue
+        _lib.check(rc)
+        return start, idx[:total.value], dist[:total.value]
+
+
+def _right_ok(frame, start, idx, q_xr, q_rad):
+    """Per candidate: False when the right-image check rejects it (ORBMatcher.py:246-249 / 345-349), evaluated in the dtype the
+    reference's scalar expression `abs(xr - mvuRight[i]) > radius` runs in."""
+    n = len(idx)
+    if n == 0:
+        return np.ones(0, np.uint8)
+    ur_list = frame.mvuRight
+    el = _elem_float_dtype(ur_list)
+    dt = q_xr.dtype if el is None else np.result_type(q_xr.dtype, el)
+    ur = np.array([float(v) for v in ur_list], np.float64)
+    has_r = ur[idx] > 0
+    per_q = np.repeat(np.arange(len(start) - 1), np.diff(start))
+    er = np.abs(q_xr.astype(dt)[per_q] - ur.astype(dt)[idx])
+    bad = has_r & (er > q_rad.astype(dt)[per_q])
+    return (~bad).astype(np.uint8)
+
+
+def _occupied(frame):
+    return np.array([1 if (mp and mp.observations() > 0) else 0 for mp in frame.mvpMapPoints], np.uint8)
+
+
+def _homogeneous(vals):
+    kinds = {type(v) for v in vals}
+    return len(kinds) <= 1 or all(not isinstance(v, np.floating) for v in vals)
+
+
 def search_by_projection_f_f(self, current_frame, last_frame, th):
-    """ORBMatcher.search_by_projection_f_f, ORBMatcher.py:291-393 (TrackWithMotionModel)."""
-    n_matches = 0
-    rot_hist = [[] for _ in range(HISTO_LENGTH)]
+    """ORBMatcher.search_by_projection_f_f, ORBMatcher.py:291-393 (TrackWithMotionModel).
+    The projections run exactly as in the reference (same scalar NumPy expressions); all window queries and descriptor distances
+    are one GPU call (b200orb_area_hamming), the order-dependent selection one host call (b200orb_greedy_project_ff)."""
     Rcw = current_frame.mTcw[:3, :3]
     tcw = current_frame.mTcw[:3, 3:4]
     twc = -Rcw.T @ tcw
@@ -169,100 +269,111 @@ def search_by_projection_f_f(self, current_frame, last_frame, th):
     tlc = Rlw @ twc + tlw
     b_forward = tlc[2] > current_frame.mb
     b_backward = -tlc[2] > current_frame.mb
-    usable = [bool(last_frame.mvpMapPoints[i]) and not last_frame.mvbOutlier[i] for i in range(last_frame.N)]
-    D = hamming_matrix(_descriptor_rows(last_frame.mvpMapPoints, usable), current_frame.mDescriptors) if any(usable) and current_frame.N else None
-    cur_mps, cur_ur = current_frame.mvpMapPoints, current_frame.mvuRight
+    qi, qu, qv, qrad, qlvl, qxr, qmp = [], [], [], [], [], [], []
+    fx, fy, cx, cy, mbf = current_frame.fx, current_frame.fy, current_frame.cx, current_frame.cy, current_frame.mbf
+    x0, x1, y0, y1 = current_frame.mnMinX, current_frame.mnMaxX, current_frame.mnMinY, current_frame.mnMaxY
+    sf = current_frame.mvScaleFactors
     for i in range(last_frame.N):
-        if not usable[i]:
-            continue
         pMP = last_frame.mvpMapPoints[i]
+        if not pMP or last_frame.mvbOutlier[i]:
+            continue
         x3Dc = Rcw @ pMP.get_world_pos() + tcw
         xc, yc, zc = x3Dc[0][0], x3Dc[1][0], x3Dc[2][0]
         invzc = 1.0 / zc
         if invzc < 0:
             continue
-        u = current_frame.fx * xc * invzc + current_frame.cx
-        v = current_frame.fy * yc * invzc + current_frame.cy
-        if u < current_frame.mnMinX or u > current_frame.mnMaxX:
+        u = fx * xc * invzc + cx
+        v = fy * yc * invzc + cy
+        if u < x0 or u > x1:
             continue
-        if v < current_frame.mnMinY or v > current_frame.mnMaxY:
+        if v < y0 or v > y1:
             continue
         octave = last_frame.mvKeys[i].octave
-        radius = th * current_frame.mvScaleFactors[octave]
-        if b_forward:
-            cand = current_frame.get_features_in_area(u, v, radius, octave, -1)
-        elif b_backward:
-            cand = current_frame.get_features_in_area(u, v, radius, 0, octave)
-        else:
-            cand = current_frame.get_features_in_area(u, v, radius, octave - 1, octave + 1)
-        if not cand:
-            continue
-        dists = D[i, np.asarray(cand, np.intp)].tolist()
-        best_dist, best_idx2 = 256, -1
-        for i2, dist in zip(cand, dists):
-            if cur_mps[i2]:
-                if cur_mps[i2].observations() > 0:
-                    continue
-            if cur_ur[i2] > 0:
-                ur = u - current_frame.mbf * invzc
-                if abs(ur - cur_ur[i2]) > radius:
-                    continue
-            if dist < best_dist:
-                best_dist, best_idx2 = dist, i2
-        if best_dist <= TH_HIGH:
-            cur_mps[best_idx2] = pMP
-            n_matches += 1
-            if self.mbCheckOrientation:
-                b = _rot_bin(last_frame.mvKeysUn[i].angle - current_frame.mvKeysUn[best_idx2].angle)
-                assert 0 <= b < HISTO_LENGTH
-                rot_hist[b].append(best_idx2)
+        qi.append(i); qu.append(u); qv.append(v); qrad.append(th * sf[octave]); qmp.append(pMP)
+        qlvl.append((octave, -1) if b_forward else ((0, octave) if b_backward else (octave - 1, octave + 1)))
+        qxr.append(u - mbf * invzc)
+    M = len(qi)
+    if M == 0 or current_frame.N == 0:
+        return 0
+    if not (_homogeneous(qu) and _homogeneous(qv) and _homogeneous(qxr)):
+        raise TypeError("projected coordinates of mixed scalar types")
+    qu, qv, qxr = np.array(qu), np.array(qv), np.array(qxr)
+    if qu.dtype != qv.dtype or qu.dtype not in (np.float32, np.float64):
+        raise TypeError("projected coordinates must be float32 or float64 scalars")
+    qrad = np.array(qrad, np.float64)
+    qdesc = np.stack([np.asarray(mp.get_descriptor(), np.uint8).reshape(32) for mp in qmp])
+    start, idx, dist = _area_hamming(current_frame, qu, qv, qrad, np.array(qlvl, np.int32), qdesc)
+    ok = _right_ok(current_frame, start, idx, qxr, qrad)
+    occ = _occupied(current_frame)
+    marks = np.array([1 if mp.observations() > 0 else 0 for mp in qmp], np.uint8)
+    best = np.empty(M, np.int32)
+    l = _lib.lib()
+    l.b200orb_greedy_project_ff.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    _lib.check(l.b200orb_greedy_project_ff(M, start.ctypes.data, idx.ctypes.data, dist.ctypes.data, ok.ctypes.data, int(current_frame.N),
+                                           occ.ctypes.data, marks.ctypes.data, TH_HIGH, best.ctypes.data))
+    n_matches = 0
+    rot_hist = [[] for _ in range(HISTO_LENGTH)]
+    cur_mps = current_frame.mvpMapPoints
+    for q in np.nonzero(best >= 0)[0].tolist():
+        b2 = int(best[q])
+        cur_mps[b2] = qmp[q]
+        n_matches += 1
+        if self.mbCheckOrientation:
+            b = _rot_bin(last_frame.mvKeysUn[qi[q]].angle - current_frame.mvKeysUn[b2].angle)
+            assert 0 <= b < HISTO_LENGTH
+            rot_hist[b].append(b2)
     if self.mbCheckOrientation:
         keep = _three_maxima(rot_hist)
         for i in range(HISTO_LENGTH):
             if i not in keep:
-                for idx in rot_hist[i]:
-                    cur_mps[idx] = None
+                for k in rot_hist[i]:
+                    cur_mps[k] = None
                     n_matches -= 1
     return n_matches
 
 
 def search_by_projection_f_p(self, frame, vp_map_points, th):
-    """ORBMatcher.search_by_projection_f_p, ORBMatcher.py:215-283 (SearchLocalPoints)."""
-    n_matches = 0
+    """ORBMatcher.search_by_projection_f_p, ORBMatcher.py:215-283 (SearchLocalPoints); same split as search_by_projection_f_f."""
     b_factor = th != 1.0
-    usable = [bool(mp.mbTrackInView) and not mp.is_bad() for mp in vp_map_points]
-    D = hamming_matrix(_descriptor_rows(vp_map_points, usable), frame.mDescriptors) if any(usable) and frame.N else None
-    for k, pMP in enumerate(vp_map_points):
-        if not usable[k]:
+    qmp, qx, qy, qxr, qrad, qlvl = [], [], [], [], [], []
+    sf = frame.mvScaleFactors
+    for pMP in vp_map_points:
+        if not pMP.mbTrackInView:
+            continue
+        if pMP.is_bad():
             continue
         level = pMP.mnTrackScaleLevel
         r = 2.5 if pMP.mTrackViewCos > 0.998 else 4.0          # radius_by_viewing_cos, ORBMatcher.py:285-289
         if b_factor:
             r *= th
-        cand = frame.get_features_in_area(pMP.mTrackProjX, pMP.mTrackProjY, r * frame.mvScaleFactors[level], level - 1, level)
-        if not cand:
-            continue
-        dists = D[k, np.asarray(cand, np.intp)].tolist()
-        best_dist, best_level, best_dist2, best_level2, best_idx = 256, -1, 256, -1, -1
-        for idx, dist in zip(cand, dists):
-            if frame.mvpMapPoints[idx]:
-                if frame.mvpMapPoints[idx].observations() > 0:
-                    continue
-            if frame.mvuRight[idx] > 0:
-                if abs(pMP.mTrackProjXR - frame.mvuRight[idx]) > r * frame.mvScaleFactors[level]:
-                    continue
-            if dist < best_dist:
-                best_dist2, best_dist = best_dist, dist
-                best_level2, best_level = best_level, frame.mvKeysUn[idx].octave
-                best_idx = idx
-            elif dist < best_dist2:
-                best_level2 = frame.mvKeysUn[idx].octave
-                best_dist2 = dist
-        if best_dist <= TH_HIGH:
-            if best_level == best_level2 and best_dist > self.mfNNratio * best_dist2:
-                continue
-            frame.mvpMapPoints[best_idx] = pMP
-            n_matches += 1
+        qmp.append(pMP); qx.append(pMP.mTrackProjX); qy.append(pMP.mTrackProjY); qxr.append(pMP.mTrackProjXR)
+        qrad.append(r * sf[level]); qlvl.append((level - 1, level))
+    M = len(qmp)
+    if M == 0 or frame.N == 0:
+        return 0
+    if not (_homogeneous(qx) and _homogeneous(qy) and _homogeneous(qxr)):
+        raise TypeError("projected coordinates of mixed scalar types")
+    qx, qy, qxr = np.array(qx), np.array(qy), np.array(qxr)
+    if qx.dtype != qy.dtype or qx.dtype not in (np.float32, np.float64):
+        raise TypeError("projected coordinates must be float32 or float64 scalars")
+    qrad = np.array(qrad, np.float64)
+    qdesc = np.stack([np.asarray(mp.get_descriptor(), np.uint8).reshape(32) for mp in qmp])
+    start, idx, dist = _area_hamming(frame, qx, qy, qrad, np.array(qlvl, np.int32), qdesc)
+    ok = _right_ok(frame, start, idx, qxr, qrad)
+    occ = _occupied(frame)
+    marks = np.array([1 if mp.observations() > 0 else 0 for mp in qmp], np.uint8)
+    koct = np.array([k.octave for k in frame.mvKeysUn], np.int32)
+    best = np.empty(M, np.int32)
+    l = _lib.lib()
+    l.b200orb_greedy_project_fp.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                                                            C.c_void_p]
+    _lib.check(l.b200orb_greedy_project_fp(M, start.ctypes.data, idx.ctypes.data, dist.ctypes.data, ok.ctypes.data, int(frame.N),
+                                           occ.ctypes.data, marks.ctypes.data, koct.ctypes.data, TH_HIGH, float(self.mfNNratio),
+                                           best.ctypes.data))
+    n_matches = 0
+    for q in np.nonzero(best >= 0)[0].tolist():
+        frame.mvpMapPoints[int(best[q])] = qmp[q]
+        n_matches += 1
     return n_matches
 
 

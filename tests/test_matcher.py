@@ -124,3 +124,92 @@ def test_gpu_projection_vs_reference_orbmatcher(golden_dir, tag):
     for p in local:
         p.mbTrackInView = False
     assert m.search_by_projection_f_p(cur, local, 1.0) == 0
+
+
+# ---------------------------------------------------------------- the pieces behind the projection searches
+def _greedy_py(start, idx, dist, ok, occ, marks, koct=None, th=100, ratio=None):
+    """Pure-Python statement of ORBMatcher.py:236-281 (ratio given) / :335-366 (ratio None) on candidate lists."""
+    occ = occ.copy()
+    best = np.full(len(start) - 1, -1, np.int32)
+    for q in range(len(start) - 1):
+        b1, l1, b2, l2, bi = 256, -1, 256, -1, -1
+        for c in range(start[q], start[q + 1]):
+            j = idx[c]
+            if occ[j] or not ok[c]:
+                continue
+            d = dist[c]
+            if d < b1:
+                b2, b1, l2, l1, bi = b1, d, l1, (koct[j] if koct is not None else 0), j
+            elif d < b2:
+                l2, b2 = (koct[j] if koct is not None else 0), d
+        if b1 <= th and bi >= 0:
+            if ratio is not None and l1 == l2 and b1 > ratio * b2:
+                continue
+            best[q] = bi
+            occ[bi] = marks[q]
+    return best, occ
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_greedy_selection_host_functions_vs_python(seed):
+    """b200orb_greedy_project_ff / _fp are host code behind the C ABI: checked here without a GPU."""
+    import ctypes as C
+    from pyorbslam_b200 import _lib
+    rng = np.random.default_rng(seed)
+    N, Mq = 300, 400
+    cnt = rng.integers(0, 12, Mq)
+    start = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    idx = rng.integers(0, N, start[-1]).astype(np.int32)
+    dist = rng.choice([5, 30, 60, 99, 100, 101, 140], start[-1]).astype(np.int32)       # many ties, values around TH_HIGH
+    ok = (rng.random(start[-1]) < 0.85).astype(np.uint8)
+    occ0 = (rng.random(N) < 0.2).astype(np.uint8)
+    marks = (rng.random(Mq) < 0.6).astype(np.uint8)
+    koct = rng.integers(0, 3, N).astype(np.int32)
+    l = _lib.lib()
+    l.b200orb_greedy_project_ff.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    l.b200orb_greedy_project_fp.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                                                            C.c_void_p]
+    occ, best = occ0.copy(), np.empty(Mq, np.int32)
+    _lib.check(l.b200orb_greedy_project_ff(Mq, start.ctypes.data, idx.ctypes.data, dist.ctypes.data, ok.ctypes.data, N, occ.ctypes.data,
+                                           marks.ctypes.data, 100, best.ctypes.data))
+    eb, eo = _greedy_py(start, idx, dist, ok, occ0, marks)
+    assert np.array_equal(best, eb) and np.array_equal(occ, eo)
+    for ratio in (0.6, 0.9, 1.0):
+        occ, best = occ0.copy(), np.empty(Mq, np.int32)
+        _lib.check(l.b200orb_greedy_project_fp(Mq, start.ctypes.data, idx.ctypes.data, dist.ctypes.data, ok.ctypes.data, N, occ.ctypes.data,
+                                               marks.ctypes.data, koct.ctypes.data, 100, ratio, best.ctypes.data))
+        eb, eo = _greedy_py(start, idx, dist, ok, occ0, marks, koct, 100, ratio)
+        assert np.array_equal(best, eb) and np.array_equal(occ, eo)
+    bad = idx.copy(); bad[0] = N                                  # a candidate that is not a feature index
+    if start[-1] > 0 and cnt[0] > 0:
+        with pytest.raises(IndexError):
+            _lib.check(l.b200orb_greedy_project_ff(Mq, start.ctypes.data, bad.ctypes.data, dist.ctypes.data, ok.ctypes.data, N,
+                                                   occ0.copy().ctypes.data, marks.ctypes.data, 100, best.ctypes.data))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_gpu_area_query_and_distances_vs_get_features_in_area(dtype):
+    """b200orb_area_hamming against the restated Frame.get_features_in_area (itself pinned to the reference's by the golden
+    vectors above), query by query, in both arithmetic modes; includes windows that leave the grid and empty ones."""
+    from pyorbslam_b200.matcher import _area_hamming
+    cur, last, local = M.make_projection_case(seed=21, n=900)
+    rng = np.random.default_rng(5)
+    Mq = 700
+    qx = rng.uniform(-80, 1320, Mq).astype(dtype)
+    qy = rng.uniform(-60, 440, Mq).astype(dtype)
+    qr = rng.choice([0.0, 3.5, 10.0, 24.9, 64.5, 300.0], Mq)
+    lv = rng.integers(-1, 8, (Mq, 2)).astype(np.int32)
+    lv[::7] = (0, -1)                                             # "no level check" combination
+    qd = rng.integers(0, 256, (Mq, 32), dtype=np.uint8)
+    start, idx, dist = _area_hamming(cur, qx, qy, qr, lv, qd)
+    assert start[0] == 0 and start[-1] == len(idx) == len(dist)
+    for q in range(Mq):
+        x, y = (qx[q], qy[q]) if dtype is np.float32 else (float(qx[q]), float(qy[q]))      # np.float32 scalar / Python float
+        ref = M.features_in_area(cur, x, y, float(qr[q]), int(lv[q, 0]), int(lv[q, 1]))
+        got = idx[start[q]:start[q + 1]].tolist()
+        assert got == ref, (q, got[:5], ref[:5])
+        if ref:
+            d = np.unpackbits(cur.mDescriptors[ref] ^ qd[q], axis=1).sum(1)
+            assert np.array_equal(dist[start[q]:start[q + 1]], d)
+    assert len(idx) > 1000
