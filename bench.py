@@ -431,6 +431,38 @@ def run_b200_arm(args):
                      "cpu_python_ms_per_frame_extrapolated": cpu_ms, "cpu_sample_features": ns,
                      "identical_on_sample": list(obv.items()) == list(sbv.items()) and list(ofv.items()) == list(sfv.items())}
 
+    # ---- the two projection searches (TrackWithMotionModel / SearchLocalPoints), GPU path vs the Python restatement ----
+    proj_extra = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import matcher_py as MP                              # scene generator + checker / CPU baseline leg only
+        from pyorbslam_b200.matcher import install_matcher
+
+        class _Matcher:
+            def __init__(self, r, o):
+                self.mfNNratio, self.mbCheckOrientation = r, o
+        install_matcher(_Matcher)
+        mt = _Matcher(0.9, True)
+        npts = 2000
+
+        def uid(fr):
+            return [-1 if p is None else p.uid for p in fr.mvpMapPoints]
+        res = {}
+        for name in ("f_f", "f_p"):
+            def run(gpu):
+                cur, last, loc = MP.make_projection_case(seed=5, n=npts)
+                t0 = time.perf_counter()
+                if name == "f_f":
+                    n = mt.search_by_projection_f_f(cur, last, 15) if gpu else MP.projection_f_f(cur, last, 15, True)
+                else:
+                    n = mt.search_by_projection_f_p(cur, loc, 3.0) if gpu else MP.projection_f_p(cur, loc, 3.0, 0.9)
+                return 1e3 * (time.perf_counter() - t0), n, uid(cur)
+            run(True)
+            g = min(run(True) for _ in range(3))
+            c = run(False)
+            res[name] = {"gpu_ms": g[0], "cpu_python_ms": c[0], "matches": int(g[1]), "identical": g[1] == c[1] and g[2] == c[2]}
+        proj_extra = {"map_points": npts, "features": npts, "what": "one call of ORBMatcher.search_by_projection_f_f / _f_p on a synthetic "
+                      "two-frame scene; CPU = Python restatement with a table popcount (the reference's bin().count distance is slower)", **res}
+
     if rank == 0:
         per_image, stereo_pp, B_frame = algorithmic_bytes(ORB["nfeatures"])
         per_image["octree"] = 4 * ncand + 4 * nkp
@@ -475,6 +507,7 @@ def run_b200_arm(args):
         }
         line["dropin_single_frame_latency"] = dropin
         line["bow_transform_8f_rank2"] = bow_extra
+        line["projection_search_8f_rank1"] = proj_extra
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         emit(line)
