@@ -5,12 +5,9 @@
 #include "plan.h"
 #include "../../include/b200orb_pattern31.h"
 
-// 256 test pairs x (x0, y0, x1, y1) as int8.  Lane i of a warp needs bytes 32*i .. 32*i+31 (descriptor byte i), i.e.
-// 8 consecutive 32-bit words; it reads them straight from this (L1/L2-resident) global array.  Constant memory
-// would serialise the 32 distinct addresses of a warp.
-__device__ __align__(16) const signed char g_pattern[1024] = {B200ORB_PATTERN_VALUES};
-// The descriptor kernel reads the same values as floats from a host-built table, transposed so that a warp's read of "pair k of
-// every lane" is one contiguous 512-byte line: fpat[k * 32 + lane] = (x0, y0, x1, y1) of test pair 8 * lane + k.
+// The 256 test pairs (x0, y0, x1, y1; include/b200orb_pattern31.h) reach the descriptor kernel as floats in a host-built table
+// (b200orb.cu), transposed so that a warp's read of "pair k of every lane" is one contiguous 512-byte line:
+// fpat[k * 32 + lane] = pair 8 * lane + k.  Lane i produces descriptor byte i.
 
 // cv::fastAtan2 (degrees), scalar polynomial path
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
