@@ -213,3 +213,42 @@ def test_gpu_area_query_and_distances_vs_get_features_in_area(dtype):
             d = np.unpackbits(cur.mDescriptors[ref] ^ qd[q], axis=1).sum(1)
             assert np.array_equal(dist[start[q]:start[q + 1]], d)
     assert len(idx) > 1000
+
+
+@pytest.mark.gpu
+def test_gpu_area_query_error_paths():
+    """Too-small output buffers report the size needed; cell ranges outside the grid and broken grids are refused."""
+    import ctypes as C
+    from pyorbslam_b200 import _lib
+    from pyorbslam_b200.matcher import _grid_csr
+    cur, _, _ = M.make_projection_case(seed=3, n=200)
+    kxy = np.array([k.pt for k in cur.mvKeysUn], np.float32)
+    koct = np.array([k.octave for k in cur.mvKeysUn], np.int32)
+    kd = np.ascontiguousarray(cur.mDescriptors)
+    cs, ci = _grid_csr(cur)
+    Mq = 4
+    qxyr = np.array([[600.0, 180.0, 5000.0]] * Mq)
+    qlvl = np.array([[0, -1]] * Mq, np.int32)
+    qcell = np.array([[0, 63, 0, 47]] * Mq, np.int32)
+    qd = np.zeros((Mq, 32), np.uint8)
+    start = np.zeros(Mq + 1, np.int32)
+    total = C.c_int32(0)
+    l = _lib.lib()
+    l.b200orb_area_hamming.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 2 + \
+                                      [C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
+
+    def call(cell_start=cs, cells=qcell, cap=0, idx=None, dist=None):
+        return l.b200orb_area_hamming(0, 0, 200, kxy.ctypes.data, koct.ctypes.data, kd.ctypes.data, 64, 48, cell_start.ctypes.data,
+                                      ci.ctypes.data, Mq, qxyr.ctypes.data, qlvl.ctypes.data, cells.ctypes.data, qd.ctypes.data,
+                                      start.ctypes.data, idx, dist, cap, C.byref(total))
+    assert call() != 0 and total.value > 0                      # every feature of the frame, four times: does not fit in cap = 0
+    need = total.value
+    idx, dist = np.empty(need, np.int32), np.empty(need, np.int32)
+    assert call(cap=need, idx=idx.ctypes.data, dist=dist.ctypes.data) == 0 and start[-1] == need
+    assert sorted(idx[:start[1]].tolist()) == sorted(ci.tolist())
+    bad = qcell.copy(); bad[1] = (0, 64, 0, 47)
+    with pytest.raises(IndexError):
+        _lib.check(call(cells=bad))
+    broken = cs.copy(); broken[5] = broken[4] - 1
+    with pytest.raises(ValueError):
+        _lib.check(call(cell_start=broken))
