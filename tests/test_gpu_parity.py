@@ -512,3 +512,13 @@ def test_bench_shaped_batch_chunking_invariance_and_idempotence():
     # frames that are pure horizontal rolls of each other are different inputs: the batch really has many distinct frames
     n0 = outs[0]["nkp"][0].cpu().numpy()
     assert len(set(n0.tolist())) > 1 or not bool((outs[0]["kps"][0, 0] == outs[0]["kps"][0, nb]).all())
+
+
+def test_randomised_sizes_contents_and_parameters_vs_oracle():
+    """A small batch of tests/gpu_fuzz.py (extractor + stereo, bit-exact); larger runs are done by hand with that script."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gpu_fuzz", os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu_fuzz.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    n, bad, refused = fz.run(seed=123, ncase=24, verbose=False)
+    assert bad == 0 and refused < n // 2
