@@ -72,6 +72,56 @@ def run(seed=0, ncase=100, verbose=True):
     return ncase, bad, refused
 
 
+def run_batch(seed=0, ncase=10, pairs=9, verbose=True):
+    """The batched engine (>= 16 images per call: FAST / blur per level on the second stream) against the one-image API on random
+    geometries: keypoints, descriptors, uRight, depth, match index of every pair identical."""
+    import torch
+    from pyorbslam_b200 import StereoFrontend
+    rng = np.random.default_rng(seed)
+    bad = done = 0
+    for c in range(ncase):
+        H = int(rng.integers(120, 500)); W = int(rng.integers(H, 1300))
+        nlev = int(rng.integers(2, 9)); sf = float(rng.choice([1.15, 1.2, 1.3, 1.5, 2.0]))
+        while min(H, W) / sf ** (nlev - 1) < 70: nlev -= 1
+        params = (int(rng.choice([300, 1000, 2000])), sf, nlev, int(rng.choice([20, 12])), int(rng.choice([7, 5])))
+        try:
+            fe = StereoFrontend(*params, H, W, pairs)
+            eL, eR = ORBextractor(*params, reuse_identical_input=False), ORBextractor(*params, reuse_identical_input=False)
+        except ValueError:
+            continue
+        ps = [make_stereo_pair(int(rng.integers(0, 10 ** 6)), H, W) for _ in range(pairs)]
+        out = fe.run(torch.from_numpy(np.stack([p[0] for p in ps])).cuda(), torch.from_numpy(np.stack([p[1] for p in ps])).cuda(), 386.1448, 718.856)
+        torch.cuda.synchronize()
+        nk = out["nkp"].cpu().numpy()
+        ok = True
+        for i, (L, R) in enumerate(ps):
+            kL, dL = eL.extract_arrays(L); kR, dR = eR.extract_arrays(R)
+            try:
+                u, d, m = stereo_resident(eL, eR, 386.1448, 718.856)
+            except IndexError:
+                continue                        # the batch engine flags these pairs instead of raising; not compared here
+            nl, nr = int(nk[0, i]), int(nk[1, i])
+            ok = ok and (nl, nr) == (len(kL), len(kR))
+            if not ok:
+                break
+            ok = ok and np.array_equal(out["kps"][0, i, :nl].cpu().numpy().view(np.uint32), kL.view(np.uint32))
+            ok = ok and np.array_equal(out["kps"][1, i, :nr].cpu().numpy().view(np.uint32), kR.view(np.uint32))
+            ok = ok and np.array_equal(out["desc"][0, i, :nl].cpu().numpy(), dL) and np.array_equal(out["desc"][1, i, :nr].cpu().numpy(), dR)
+            ok = ok and np.array_equal(out["uRight"][i, :nl].cpu().numpy().view(np.uint32), u.view(np.uint32))
+            ok = ok and np.array_equal(out["depth"][i, :nl].cpu().numpy().view(np.uint32), d.view(np.uint32))
+            ok = ok and np.array_equal(out["matchIdx"][i, :nl].cpu().numpy(), m)
+        done += 1
+        if not ok:
+            bad += 1
+            print("BATCH MISMATCH case", c, (H, W), params)
+        del fe
+    if verbose:
+        print("batch fuzz done:", done, "cases,", bad, "mismatches")
+    return done, bad
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 3 and sys.argv[3] == "batch":
+        sys.exit(1 if run_batch(int(sys.argv[1]), int(sys.argv[2]))[1] else 0)
     _, nbad, _ = run(int(sys.argv[1]) if len(sys.argv) > 1 else 0, int(sys.argv[2]) if len(sys.argv) > 2 else 100)
     sys.exit(1 if nbad else 0)
