@@ -252,9 +252,6 @@ struct Engine {
     u32 *d_cand = nullptr, *d_scratch = nullptr, *d_lvlkp = nullptr;
     int *d_cellcnt = nullptr, *d_lvlcnt = nullptr, *d_status = nullptr, *d_rowstart = nullptr;
     int4* d_rmeta = nullptr;
-    bool overlap_levels = true;              // per-level FAST / blur on `aux` underneath the resize chain (see extract())
-    cudaStream_t aux = nullptr;
-    cudaEvent_t ev_lvl[ORB_MAX_LEVELS] = {}, ev_join = nullptr;
     unsigned char* d_octnodes = nullptr;     // node arrays of k_octree when they do not fit in shared memory
     XTab* d_xtab = nullptr;
     XGroup* d_xgrp = nullptr;
@@ -269,13 +266,6 @@ struct Engine {
         d_pyr = d_blur = nullptr; d_cand = d_scratch = d_lvlkp = nullptr; d_cellcnt = d_lvlcnt = d_status = d_rowstart = nullptr;
         d_xtab = nullptr; d_ytab = nullptr; planned = false; bytes = 0;
     }
-    void release_streams() {
-        if (aux) {
-            cudaStreamDestroy(aux); aux = nullptr;
-            for (int l = 0; l < ORB_MAX_LEVELS; ++l) { cudaEventDestroy(ev_lvl[l]); ev_lvl[l] = nullptr; }
-            cudaEventDestroy(ev_join); ev_join = nullptr;
-        }
-    }
     template <typename T> int alloc(T** p, size_t n) {
         CU_TRY(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
         bytes += (long long)(n * sizeof(T));
@@ -285,12 +275,6 @@ struct Engine {
         if (planned && hp.P.H == H && hp.P.W == W && S == slots) return 0;
         CU_TRY(cudaSetDevice(device));
         release();
-        if (!aux) {
-            if (const char* s = getenv("B200ORB_SERIAL_LEVELS")) overlap_levels = !(s[0] && s[0] != '0');   // one launch per stage, e.g. under ncu
-            CU_TRY(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
-            for (int l = 0; l < ORB_MAX_LEVELS; ++l) CU_TRY(cudaEventCreateWithFlags(&ev_lvl[l], cudaEventDisableTiming));
-            CU_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-        }
         TRY(build_plan(prm, H, W, hp));
         S = slots;
         const Plan& P = hp.P;
@@ -339,15 +323,12 @@ struct Engine {
                 cudaEvent_t* evs = nullptr) {
         if (n < 1 || n > S) return fail(B200ORB_E_ARG, "slot count out of range");
         const Plan& P = hp.P;
-        // a handful of images cannot fill the GPU either way: keep the short serial launch sequence for the one-frame API
-        const bool overlap_levels = this->overlap_levels && n >= 16;
         {
             const LevelGeom& G = P.lv[0];
             dim3 grid(((G.pitch >> 4) * G.rows + 255) / 256, n);
             k_border0<<<grid, 256, 0, st>>>(P, imgA, imgB, splitA, d_pyr);
             ++g_launches;
             if (evs) cudaEventRecord(evs[1], st);
-            else if (overlap_levels) CU_TRY(cudaEventRecord(ev_lvl[0], st));
         }
         for (int l = 1; l < P.nlevels; ++l) {
             const LevelGeom& G = P.lv[l];
@@ -357,41 +338,17 @@ struct Engine {
             const unsigned wpr = (unsigned)(G.pitch >> 2), wpr_magic = (unsigned)((0x100000000ULL + wpr - 1) / wpr);
             k_resize<<<grid, 256, 0, st>>>(P, l, fast_ok, wpr_magic, d_pyr, d_xtab, d_xgrp, d_ytab);
             ++g_launches;
-            if (!evs && overlap_levels) CU_TRY(cudaEventRecord(ev_lvl[l], st));
         }
         if (evs) cudaEventRecord(evs[2], st);
-        if (evs || !overlap_levels) {
-            k_blur<<<dim3(P.blur_ctas, n), BLUR_WARPS * 32, 0, st>>>(P, d_pyr, d_blur, 0);
+        k_blur<<<dim3(P.blur_ctas, n), BLUR_WARPS * 32, 0, st>>>(P, d_pyr, d_blur);
+        ++g_launches;
+        if (evs) cudaEventRecord(evs[3], st);
+        if (P.fast_ctas > 0) {
+            k_fast_cells<<<dim3(P.fast_ctas, n), FAST_WARPS * 32, hp.fast_smem, st>>>(P, d_pyr, d_cand, d_cellcnt, hp.fast_SP, hp.fast_SR,
+                                                                                   hp.fast_TP, hp.fast_TR, hp.fast_LC);
             ++g_launches;
-            if (evs) cudaEventRecord(evs[3], st);
-            if (P.fast_ctas > 0) {
-                k_fast_cells<<<dim3(P.fast_ctas, n), FAST_WARPS * 32, hp.fast_smem, st>>>(P, d_pyr, d_cand, d_cellcnt, hp.fast_SP, hp.fast_SR,
-                                                                                       hp.fast_TP, hp.fast_TR, hp.fast_LC, 0, -1);
-                ++g_launches;
-            }
-            if (evs) cudaEventRecord(evs[4], st);
-        } else {
-            // FAST and blur of level l only need level l: they run per level on a second stream behind the event recorded
-            // after that level's resize, underneath the (latency-bound) rest of the resize chain; the main stream joins before
-            // the octree.  (The profiling pass above keeps the serial order so that every stage can be timed on its own.)
-            for (int l = 0; l < P.nlevels; ++l) {
-                const LevelGeom& G = P.lv[l];
-                CU_TRY(cudaStreamWaitEvent(aux, ev_lvl[l], 0));
-                const int f0 = G.fast_cta_ofs, f1 = l + 1 < P.nlevels ? P.lv[l + 1].fast_cta_ofs : P.fast_ctas;
-                if (f1 > f0) {
-                    k_fast_cells<<<dim3(f1 - f0, n), FAST_WARPS * 32, hp.fast_smem, aux>>>(P, d_pyr, d_cand, d_cellcnt, hp.fast_SP, hp.fast_SR,
-                                                                                        hp.fast_TP, hp.fast_TR, hp.fast_LC, f0, l);
-                    ++g_launches;
-                }
-                const int b0 = G.blur_cta_ofs, b1 = l + 1 < P.nlevels ? P.lv[l + 1].blur_cta_ofs : P.blur_ctas;
-                if (b1 > b0) {
-                    k_blur<<<dim3(b1 - b0, n), BLUR_WARPS * 32, 0, aux>>>(P, d_pyr, d_blur, b0);
-                    ++g_launches;
-                }
-            }
-            CU_TRY(cudaEventRecord(ev_join, aux));
-            CU_TRY(cudaStreamWaitEvent(st, ev_join, 0));
         }
+        if (evs) cudaEventRecord(evs[4], st);
         k_octree<<<dim3(n, P.nlevels), OCT_THREADS, hp.oct_smem, st>>>(P, d_cand, d_cellcnt, d_scratch, d_lvlkp, d_lvlcnt, hp.oct_capN,
                                                                       hp.oct_capK, hp.oct_capC, d_octnodes, hp.oct_node_stride);
         ++g_launches;
@@ -524,7 +481,7 @@ void b200orb_extractor_destroy(b200orb_extractor* e) {
     if (!e) return;
     if (e->st || e->d_img || e->eng.planned) {
         cudaSetDevice(e->eng.device);
-        e->eng.release(); e->eng.release_streams();
+        e->eng.release();
         cudaFree(e->d_img); cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_nkp);
         cudaFree(e->d_uR); cudaFree(e->d_depth); cudaFree(e->d_match); cudaFree(e->d_sad);
         if (e->st) cudaStreamDestroy(e->st);
@@ -835,7 +792,7 @@ int b200orb_batch_create(int nfeatures, float scaleFactor, int nlevels, int iniT
 void b200orb_batch_destroy(b200orb_batch* b) {
     if (!b) return;
     cudaSetDevice(b->eng.device);
-    b->eng.release(); b->eng.release_streams();
+    b->eng.release();
     for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
     cudaFree(b->d_sad);
     for (int i = 0; i < 2; ++i) {

@@ -186,9 +186,8 @@ __global__ void __launch_bounds__(256, 5) k_resize(const __grid_constant__ Plan 
 #define BLUR_RB 32
 #define BLUR_WARPS 4
 #define BLUR_TH (BLUR_RB * BLUR_WARPS)
-__global__ void __launch_bounds__(BLUR_WARPS * 32) k_blur(const __grid_constant__ Plan P, const u8* __restrict__ pyr, u8* __restrict__ blur,
-                                                          int cta_base /* first CTA of this launch in the all-level numbering */) {
-    const int slot = blockIdx.y, bid = (int)blockIdx.x + cta_base;
+__global__ void __launch_bounds__(BLUR_WARPS * 32) k_blur(const __grid_constant__ Plan P, const u8* __restrict__ pyr, u8* __restrict__ blur) {
+    const int slot = blockIdx.y, bid = (int)blockIdx.x;
     int l = 0;
     while (l + 1 < P.nlevels && bid >= P.lv[l + 1].blur_cta_ofs) ++l;
     const LevelGeom& G = P.lv[l];
@@ -480,15 +479,13 @@ __device__ __forceinline__ int fast_score(const u8* p, int SP, int t) {
 __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
                                                                 u32* __restrict__ cand, int* __restrict__ cellcnt,
                                                                 int SP /*strip pitch*/, int SR /*strip rows*/, int TP /*tile pitch*/, int TR /*tile rows*/,
-                                                                int LC /*list capacity per warp*/, int cta_base /*first CTA of this launch*/,
-                                                                int level /*all CTAs of this launch belong to it; -1: search*/) {
+                                                                int LC /*list capacity per warp*/) {
     extern __shared__ __align__(16) u8 smem[];
     u8* strip = smem;
     const int slot = blockIdx.y;
     int l = 0;
-    const int bid = (int)blockIdx.x + cta_base;
-    if (level >= 0) l = level;
-    else while (l + 1 < P.nlevels && bid >= P.lv[l + 1].fast_cta_ofs) ++l;
+    const int bid = (int)blockIdx.x;
+    while (l + 1 < P.nlevels && bid >= P.lv[l + 1].fast_cta_ofs) ++l;
     const LevelGeom& G = P.lv[l];
     const int local = bid - G.fast_cta_ofs;
     const int ci = local / G.fast_groups, g = local - ci * G.fast_groups;

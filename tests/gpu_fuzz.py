@@ -73,7 +73,7 @@ def run(seed=0, ncase=100, verbose=True):
 
 
 def run_batch(seed=0, ncase=10, pairs=9, verbose=True):
-    """The batched engine (>= 16 images per call: FAST / blur per level on the second stream) against the one-image API on random
+    """The batched engine (many images per launch sequence) against the one-image API on random
     geometries: keypoints, descriptors, uRight, depth, match index of every pair identical."""
     import torch
     from pyorbslam_b200 import StereoFrontend

@@ -502,7 +502,7 @@ def test_bench_shaped_batch_chunking_invariance_and_idempotence():
     d128, fe = run(128)
     d32, _ = run(32)
     assert d128 == d32
-    d4, _ = run(4)              # 8 images per call: below the threshold of the two-stream per-level schedule -> serial launch order
+    d4, _ = run(4)              # 8 images per call
     assert d4 == d128
     outs = [fe.run(left[c:c + 128], right[c:c + 128], 386.1448, 718.856) for c in range(0, B, 128)]   # again, same engine
     torch.cuda.synchronize()
