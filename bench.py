@@ -481,6 +481,13 @@ def run_b200_arm(args):
             kernels[k] = {"ms_total": tot, "share": tot / max(sum(stage_ms.values()), 1e-9), "avg_launch_ms": tot / max(prof_calls * launches_per_call[k], 1),
                           "algorithmic_bytes_per_launch": bytes_total / max(prof_calls * launches_per_call[k], 1), "achieved_gbs": gbs, "frac": gbs / peak}
         dom = max(stage_ms, key=stage_ms.get)
+        try:       # static ncu figures of the same kernels (profiles/traffic.json, from the committed --set full capture)
+            tj_all = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            for k in kernels:
+                kernels[k]["ncu"] = {"dram_bytes_per_launch_group": tj_all.get(k), "issue_slots_busy_pct": tj_all.get("_issue_slots_busy_pct", {}).get(k),
+                                     "alu_pipe_pct": tj_all.get("_alu_pipe_pct", {}).get(k), "l1_data_pipe_pct": tj_all.get("_l1_data_pipe_pct", {}).get(k)}
+        except Exception:
+            pass
         traffic, issue_pct, alu_pct = None, None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):       # static numbers from the committed ncu --set full capture of the same kernels
