@@ -150,6 +150,16 @@ int b200orb_batch_run_host(b200orb_batch* b, const uint8_t* h_left, const uint8_
                            double mbf, float fx, float* h_kps, uint8_t* h_desc, int32_t* h_nkp,
                            float* h_uRight, float* h_depth, int32_t* h_matchIdx);
 
+/* Range errors of the batched path.  Frame.compute_stereo_matches raises (IndexError / ValueError, Frame.py:192,230-250) when a
+ * keypoint's row band or SAD window leaves the pyramid view; b200orb_stereo reports that as B200ORB_E_RANGE.  The batched calls keep one
+ * flag word per pair (0 = fine): b200orb_batch_run_host returns B200ORB_E_RANGE after all outputs have reached host memory if any
+ * pair of the job is flagged (the other pairs' results are valid; a flagged pair holds -1 at the offending keypoints), and
+ * b200orb_batch_status_host copies the job's per-pair flags.  b200orb_batch_run_device is asynchronous, so its caller asks:
+ * b200orb_batch_status_device synchronises `stream`, copies the flags of the last run_device call (pair_status may be NULL) and
+ * returns B200ORB_E_RANGE if any is set. */
+int b200orb_batch_status_device(b200orb_batch* b, int n_pairs, void* stream, int32_t* pair_status);
+int b200orb_batch_status_host(const b200orb_batch* b, int32_t* pair_status, int n_pairs);
+
 /* stereo options of the batched path (same flags as b200orb_stereo_ex; default 0 = the reference's behaviour) */
 int b200orb_batch_set_stereo_flags(b200orb_batch* b, int flags);
 

@@ -70,8 +70,35 @@ class StereoFrontend:
             "matchIdx": torch.empty((n_pairs, C_), dtype=torch.int32, **kw),
         }
 
+    _OUT_SPEC = (("kps", torch.float32, lambda n, c: (2, n, c, 6)), ("desc", torch.uint8, lambda n, c: (2, n, c, 32)),
+                 ("nkp", torch.int32, lambda n, c: (2, n)), ("uRight", torch.float32, lambda n, c: (n, c)),
+                 ("depth", torch.float32, lambda n, c: (n, c)), ("matchIdx", torch.int32, lambda n, c: (n, c)))
+
+    def _check_out(self, out, n, on_device):
+        """A caller-supplied `out` is written through raw pointers: refuse anything that is not exactly what alloc_outputs(n) makes."""
+        for name, dtype, shape in self._OUT_SPEC:
+            t = out.get(name) if isinstance(out, dict) else None
+            if not isinstance(t, torch.Tensor):
+                raise ValueError(f"out[{name!r}] is missing")
+            if t.dtype != dtype or tuple(t.shape) != shape(n, self.capacity) or not t.is_contiguous():
+                raise ValueError(f"out[{name!r}] must be a contiguous {dtype} tensor of shape {shape(n, self.capacity)}, got {t.dtype} {tuple(t.shape)}")
+            if on_device and not (t.is_cuda and t.device.index == self.device):
+                raise ValueError(f"out[{name!r}] must live on cuda:{self.device}, got {t.device}")
+            if not on_device and t.is_cuda:
+                raise ValueError(f"out[{name!r}] must be a host tensor")
+
+    def check_status(self, n_pairs, stream=None):
+        """Synchronises `stream` (default: the current one) and raises IndexError if a pair of the last run() hit what the reference
+        raises for (a row band / SAD window leaving the pyramid view, Frame.py:192,230-250).  Returns the per-pair flags."""
+        st = (stream or torch.cuda.current_stream(torch.device("cuda", self.device))).cuda_stream
+        flags = np.zeros(int(n_pairs), np.int32)
+        self.last_pair_status = flags
+        _lib.check(_lib.lib().b200orb_batch_status_device(self._h, int(n_pairs), C.c_void_p(st), flags.ctypes.data))
+        return flags
+
     def run(self, left, right, mbf, fx, out=None):
-        """left/right: uint8 CUDA tensors [n, H, W] (n <= max_pairs).  Asynchronous on the current stream."""
+        """left/right: uint8 CUDA tensors [n, H, W] (n <= max_pairs).  Asynchronous on the current stream; range errors
+        (see check_status) are reported by check_status(n), not here."""
         if not (left.is_cuda and right.is_cuda) or left.dtype != torch.uint8 or right.dtype != torch.uint8:
             raise ValueError("run takes uint8 CUDA tensors")
         if not (left.is_contiguous() and right.is_contiguous()) or left.shape != right.shape:
@@ -79,8 +106,12 @@ class StereoFrontend:
         n = left.shape[0]
         if tuple(left.shape[1:]) != (self.H, self.W) or n < 1 or n > self.max_pairs:
             raise ValueError(f"expected [n <= {self.max_pairs}, {self.H}, {self.W}], got {tuple(left.shape)}")
+        if left.device.index != self.device or right.device.index != self.device:
+            raise ValueError(f"inputs must live on cuda:{self.device}")
         if out is None:
             out = self.alloc_outputs(n)
+        else:
+            self._check_out(out, n, on_device=True)
         st = torch.cuda.current_stream(left.device).cuda_stream
         _lib.check(_lib.lib().b200orb_batch_run_device(self._h, left.data_ptr(), right.data_ptr(), n, float(mbf), float(np.float32(fx)),
                                                        out["kps"].data_ptr(), out["desc"].data_ptr(), out["nkp"].data_ptr(),
@@ -102,7 +133,16 @@ class StereoFrontend:
             raise ValueError(f"expected [n, {self.H}, {self.W}] for both views, got {tuple(lt.shape)} / {tuple(rt.shape)}")
         if out is None:
             out = self.alloc_outputs(n, pinned_host=True)
-        _lib.check(_lib.lib().b200orb_batch_run_host(self._h, lt.data_ptr(), rt.data_ptr(), n, float(mbf), float(np.float32(fx)),
-                                                     out["kps"].data_ptr(), out["desc"].data_ptr(), out["nkp"].data_ptr(),
-                                                     out["uRight"].data_ptr(), out["depth"].data_ptr(), out["matchIdx"].data_ptr()))
+        else:
+            self._check_out(out, n, on_device=False)
+        rc = _lib.lib().b200orb_batch_run_host(self._h, lt.data_ptr(), rt.data_ptr(), n, float(mbf), float(np.float32(fx)),
+                                               out["kps"].data_ptr(), out["desc"].data_ptr(), out["nkp"].data_ptr(),
+                                               out["uRight"].data_ptr(), out["depth"].data_ptr(), out["matchIdx"].data_ptr())
+        self.last_out = out                      # on a range error (IndexError) the other pairs' results are still valid
+        if rc == _lib.E_RANGE:
+            flags = np.zeros(n, np.int32)
+            _lib.lib().b200orb_batch_status_host(self._h, flags.ctypes.data, n)
+            self.last_pair_status = flags
+        _lib.check(rc)
+        self.last_pair_status = np.zeros(n, np.int32)
         return out

@@ -90,6 +90,7 @@ struct HostPlan {
     std::vector<XGroup> xgrp;
     std::vector<uint2> mtab;      // IC_Angle coefficient table, see k_describe
     std::vector<YTab> ytab;
+    int rs_gA_lo[ORB_MAX_LEVELS] = {0}, rs_gA_n[ORB_MAX_LEVELS] = {0}, rs_gB_n[ORB_MAX_LEVELS] = {0};   // k_resize: interior / border column groups
     int fast_SP = 0, fast_SR = 0, fast_TP = 0, fast_TR = 0, fast_LC = 0;
     size_t fast_smem = 0;
     int oct_capN = 0, oct_capK = 0, oct_capC = 0;
@@ -195,6 +196,15 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
                 }
                 hp.xgrp[G.xtab_ofs / 4 + g] = e;
             }
+            // interior groups (word-window path) must form one contiguous run; everything else with a valid column is a border group.
+            // The word-window path needs the 4 columns of a thread to span <= 10 source bytes: scale < 2.
+            const int gv = (bw + 3) / 4;
+            int lo = -1, hi = -1;
+            bool contiguous = (double)S.w / G.w < 1.95;
+            for (int g = 0; g < gv && contiguous; ++g)
+                if (hp.xgrp[G.xtab_ofs / 4 + g].shift8 != 0xffffffffu) { if (lo < 0) lo = g; else if (hi != g) contiguous = false; hi = g + 1; }
+            if (!contiguous || lo < 0) { lo = 0; hi = 0; }
+            hp.rs_gA_lo[l] = lo; hp.rs_gA_n[l] = hi - lo; hp.rs_gB_n[l] = gv - (hi - lo);
         }
     }
     // IC_Angle (ORBextractor.cpp:77-106) as dot products: the 31 x 31 disc is read as aligned 32-bit words, 3 rows x 9 words per
@@ -259,7 +269,15 @@ struct Engine {
     float4* d_fpat = nullptr;
     YTab* d_ytab = nullptr;
     long long bytes = 0;
+    // K5 (blur) depends only on the pyramid, K2 -> K3 (FAST -> octree) likewise: per launch sequence the blur is forked onto a side
+    // stream so that it fills the SMs the latency-bound octree rounds leave idle; both join in front of K4/K6 (describe)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int fork_blur = -1;      // -1 = read B200ORB_FORK_BLUR (default on)
 
+    ~Engine() {
+        if (side) { cudaSetDevice(device); cudaStreamDestroy(side); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); }
+    }
     void release() {
         cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_cand); cudaFree(d_scratch); cudaFree(d_lvlkp);
         cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_xgrp); d_xgrp = nullptr; cudaFree(d_mtab); d_mtab = nullptr; cudaFree(d_fpat); d_fpat = nullptr; cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr;
@@ -285,7 +303,7 @@ struct Engine {
         TRY(alloc(&d_lvlkp, (size_t)S * P.kp_total));
         TRY(alloc(&d_cellcnt, (size_t)S * P.ncells));
         TRY(alloc(&d_lvlcnt, (size_t)S * P.nlevels));
-        TRY(alloc(&d_status, 1));
+        TRY(alloc(&d_status, (size_t)std::max(S, 1)));     // one range-error flag word per pair (batch API) / one in all (extractor)
         TRY(alloc(&d_rowstart, (size_t)S * (P.lv[0].h + 1)));
         TRY(alloc(&d_rmeta, (size_t)S * P.kp_total));
         if (hp.oct_global_nodes) TRY(alloc(&d_octnodes, (size_t)S * P.nlevels * hp.oct_node_stride));
@@ -296,7 +314,7 @@ struct Engine {
         TRY(alloc(&d_ytab, hp.ytab.size()));
         CU_TRY(cudaMemset(d_pyr, 0, (size_t)S * P.pyr_bytes));
         CU_TRY(cudaMemset(d_blur, 0, (size_t)S * P.blur_bytes));
-        CU_TRY(cudaMemset(d_status, 0, sizeof(int)));
+        CU_TRY(cudaMemset(d_status, 0, sizeof(int) * (size_t)std::max(S, 1)));
         if (!hp.xtab.empty()) CU_TRY(cudaMemcpy(d_xtab, hp.xtab.data(), hp.xtab.size() * sizeof(XTab), cudaMemcpyHostToDevice));
         if (!hp.xgrp.empty()) CU_TRY(cudaMemcpy(d_xgrp, hp.xgrp.data(), hp.xgrp.size() * sizeof(XGroup), cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(d_mtab, hp.mtab.data(), hp.mtab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
@@ -323,36 +341,55 @@ struct Engine {
                 cudaEvent_t* evs = nullptr) {
         if (n < 1 || n > S) return fail(B200ORB_E_ARG, "slot count out of range");
         const Plan& P = hp.P;
+        auto magic_of = [](int d) { return d > 1 ? (unsigned)((0x100000000ULL + (unsigned)d - 1) / (unsigned)d) : 0xffffffffu; };
         {
+            // 16-byte spans per row: interior ones (source bytes x0 .. x0 + 19 inside the image row) and rim ones, in separate blocks
             const LevelGeom& G = P.lv[0];
-            dim3 grid(((G.pitch >> 4) * G.rows + 255) / 256, n);
-            k_border0<<<grid, 256, 0, st>>>(P, imgA, imgB, splitA, d_pyr);
+            const int nv = (G.w + 2 * ORB_EDGE + 15) / 16;
+            const int vA_lo = 2, vA_n = std::max(0, (P.W + 15) / 16 - vA_lo), vB_n = nv - vA_n;
+            const int blkA = (vA_n * G.rows + 255) / 256, blkB = (vB_n * G.rows + 255) / 256;
+            k_border0<<<dim3(blkA + blkB, n), 256, 0, st>>>(P, imgA, imgB, splitA, d_pyr, blkA, vA_lo, vA_n, magic_of(vA_n), vB_n, magic_of(vB_n));
             ++g_launches;
             if (evs) cudaEventRecord(evs[1], st);
         }
         for (int l = 1; l < P.nlevels; ++l) {
             const LevelGeom& G = P.lv[l];
-            dim3 grid(((G.pitch >> 2) * ((G.rows + RS_ROWS - 1) / RS_ROWS) + 255) / 256, n);
-            // the word-window fast path needs the 4 columns of a thread to span <= 10 source bytes: scale < 2
-            const int fast_ok = (double)P.lv[l - 1].w / G.w < 1.95 ? 1 : 0;
-            const unsigned wpr = (unsigned)(G.pitch >> 2), wpr_magic = (unsigned)((0x100000000ULL + wpr - 1) / wpr);
-            k_resize<<<grid, 256, 0, st>>>(P, l, fast_ok, wpr_magic, d_pyr, d_xtab, d_xgrp, d_ytab);
+            const int rgroups = (G.rows + RS_ROWS - 1) / RS_ROWS;
+            const int blkA = (hp.rs_gA_n[l] * rgroups + 255) / 256, blkB = (hp.rs_gB_n[l] * rgroups + 255) / 256;
+            k_resize<<<dim3(blkA + blkB, n), 256, 0, st>>>(P, l, blkA, hp.rs_gA_lo[l], hp.rs_gA_n[l], magic_of(hp.rs_gA_n[l]), hp.rs_gB_n[l],
+                                                          magic_of(hp.rs_gB_n[l]), d_pyr, d_xtab, d_xgrp, d_ytab);
             ++g_launches;
         }
         if (evs) cudaEventRecord(evs[2], st);
-        k_blur<<<dim3(P.blur_ctas, n), BLUR_WARPS * 32, 0, st>>>(P, d_pyr, d_blur);
-        ++g_launches;
+        if (fork_blur < 0) { const char* v = getenv("B200ORB_FORK_BLUR"); fork_blur = v ? atoi(v) : 1; }
+        const bool fork = fork_blur > 0 && !evs;      // the per-stage timing pass runs the stages back to back on one stream
+        if (fork && !side) {
+            int lo = 0, hi = 0;
+            CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CU_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, fork_blur >= 3 ? lo : hi));
+            CU_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        }
+        auto launch_blur = [&]() {
+            if (fork) { cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(side, ev_fork, 0); }
+            k_blur<<<dim3(P.blur_ctas, n), BLUR_WARPS * 32, 0, fork ? side : st>>>(P, d_pyr, d_blur);
+            ++g_launches;
+            if (fork) cudaEventRecord(ev_join, side);
+        };
+        if (!fork || fork_blur == 1) launch_blur();
         if (evs) cudaEventRecord(evs[3], st);
         if (P.fast_ctas > 0) {
             k_fast_cells<<<dim3(P.fast_ctas, n), FAST_WARPS * 32, hp.fast_smem, st>>>(P, d_pyr, d_cand, d_cellcnt, hp.fast_SP, hp.fast_SR,
                                                                                    hp.fast_TP, hp.fast_TR, hp.fast_LC);
             ++g_launches;
         }
+        if (fork && fork_blur >= 2) launch_blur();
         if (evs) cudaEventRecord(evs[4], st);
         k_octree<<<dim3(n, P.nlevels), OCT_THREADS, hp.oct_smem, st>>>(P, d_cand, d_cellcnt, d_scratch, d_lvlkp, d_lvlcnt, hp.oct_capN,
                                                                       hp.oct_capK, hp.oct_capC, d_octnodes, hp.oct_node_stride);
         ++g_launches;
         if (evs) cudaEventRecord(evs[5], st);
+        if (fork) CU_TRY(cudaStreamWaitEvent(st, ev_join, 0));
         k_describe<<<dim3((P.kp_total + DESC_WARPS * DESC_KPW - 1) / (DESC_WARPS * DESC_KPW), n), DESC_WARPS * 32, 0, st>>>(P, d_pyr, d_blur, d_lvlkp, d_lvlcnt, d_mtab,
                                                                                                     d_fpat, d_kps, d_desc, d_nkp);
         ++g_launches;
@@ -395,7 +432,7 @@ int launch_stereo(const StereoGeom& SG, StereoArgs A, int max_left, int pairs, c
     A.reach = (int)ceil(2.0 * smax) + 2;
     const size_t smem = (size_t)(2 * SG.nRows + 1) * sizeof(int);
     k_rowindex<<<pairs, RI_THREADS, smem, st>>>(A.kpsR, A.nR, A.kp_stride, A.n_stride, A.kp_row, A.oct_idx, SG, (int*)A.rowStart,
-                                                (int4*)A.rmeta, A.idx_stride, A.status);
+                                                (int4*)A.rmeta, A.idx_stride, A.status, A.status_stride);
     ++g_launches;
     dim3 grid((max_left + ST_WARPS - 1) / ST_WARPS, pairs);
     k_stereo<<<grid, ST_WARPS * 32, 0, st>>>(SG, A);
@@ -445,6 +482,7 @@ struct b200orb_batch {
     float* d_uR[2] = {nullptr, nullptr}; float* d_dep[2] = {nullptr, nullptr}; int* d_mi[2] = {nullptr, nullptr};
     bool host_ready = false;
     long long host_bytes = 0;
+    int* h_status = nullptr; int h_status_cap = 0, h_status_n = 0;   // pinned: per-pair range-error flags of the last run_host
     int stereo_flags = 0;
     int* d_sad = nullptr;     // [P][C], only with the median cull
     // per-kernel timing (b200orb_batch_profile): a pool of event sets, one set per run_device call
@@ -802,6 +840,7 @@ void b200orb_batch_destroy(b200orb_batch* b) {
         if (b->ev_comp[i]) cudaEventDestroy(b->ev_comp[i]);
         if (b->ev_out[i]) cudaEventDestroy(b->ev_out[i]);
     }
+    if (b->h_status) cudaFreeHost(b->h_status);
     if (b->s_in) cudaStreamDestroy(b->s_in);
     if (b->s_comp) cudaStreamDestroy(b->s_comp);
     if (b->s_out) cudaStreamDestroy(b->s_out);
@@ -839,7 +878,9 @@ int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint
     A.pyrL = b->eng.d_pyr; A.pyrR = b->eng.d_pyr + (size_t)n_pairs * P.pyr_bytes;
     A.kp_stride = (long long)C * 6; A.desc_stride = (long long)C * 32; A.pyr_stride = P.pyr_bytes;
     A.kp_row = 6; A.oct_idx = 5; A.out_stride = (int)C;
-    A.uRight = d_uRight; A.depth = d_depth; A.matchIdx = d_matchIdx; A.status = b->eng.d_status;
+    A.uRight = d_uRight; A.depth = d_depth; A.matchIdx = d_matchIdx;
+    A.status = b->eng.d_status; A.status_stride = 1;          // flag word per pair, cleared here, read by b200orb_batch_status_device / run_host
+    CU_TRY(cudaMemsetAsync(b->eng.d_status, 0, (size_t)n_pairs * sizeof(int), st));
     A.rowStart = b->eng.d_rowstart; A.rmeta = b->eng.d_rmeta; A.idx_stride = (int)C;
     fill_stereo_consts(A, mbf, fx);
     if (b->stereo_flags & B200ORB_STEREO_MEDIAN_CULL) {
@@ -848,6 +889,28 @@ int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint
     }
     TRY(launch_stereo(SG, A, (int)C, n_pairs, st, b->stereo_flags));
     if (evs) CU_TRY(cudaEventRecord(evs[B200ORB_NSTAGE], st));
+    return 0;
+}
+
+static const char* kRangeMsg = "a SAD window or row band leaves the pyramid view in at least one pair (the reference raises IndexError/ValueError "
+                               "there, Frame.py:230-250); the per-pair flags say which";
+
+int b200orb_batch_status_device(b200orb_batch* b, int n_pairs, void* stream, int32_t* pair_status) {
+    if (!b) return fail(B200ORB_E_ARG, "NULL batch");
+    if (n_pairs < 1 || n_pairs > b->P) return fail(B200ORB_E_ARG, "n_pairs must be in [1, max_pairs]");
+    CU_TRY(cudaSetDevice(b->eng.device));
+    std::vector<int> tmp(n_pairs);
+    CU_TRY(cudaMemcpyAsync(tmp.data(), b->eng.d_status, (size_t)n_pairs * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    int any = 0;
+    for (int i = 0; i < n_pairs; ++i) { any |= tmp[i]; if (pair_status) pair_status[i] = tmp[i]; }
+    return any ? fail(B200ORB_E_RANGE, kRangeMsg) : 0;
+}
+
+int b200orb_batch_status_host(const b200orb_batch* b, int32_t* pair_status, int n_pairs) {
+    if (!b || !pair_status) return fail(B200ORB_E_ARG, "NULL argument");
+    if (n_pairs < 0 || n_pairs > b->h_status_n) return fail(B200ORB_E_ARG, "n_pairs exceeds the last run_host job");
+    memcpy(pair_status, b->h_status, (size_t)n_pairs * sizeof(int));
     return 0;
 }
 
@@ -945,6 +1008,13 @@ int b200orb_batch_run_host(b200orb_batch* b, const uint8_t* h_left, const uint8_
     TRY(batch_host_setup(b));
     const Plan& P = b->eng.hp.P;
     const size_t C = P.kp_total, HW = (size_t)b->H * b->W, NT = n_pairs;
+    if (n_pairs > b->h_status_cap) {
+        if (b->h_status) cudaFreeHost(b->h_status);
+        b->h_status = nullptr; b->h_status_cap = 0;
+        CU_TRY(cudaHostAlloc((void**)&b->h_status, (size_t)n_pairs * sizeof(int), cudaHostAllocDefault));
+        b->h_status_cap = n_pairs;
+    }
+    b->h_status_n = n_pairs;
     int k = 0;
     for (int p0 = 0; p0 < n_pairs; p0 += b->P, ++k) {
         const int s = k & 1;
@@ -957,6 +1027,8 @@ int b200orb_batch_run_host(b200orb_batch* b, const uint8_t* h_left, const uint8_
         if (k >= 2) CU_TRY(cudaStreamWaitEvent(b->s_comp, b->ev_out[s], 0));   // outputs of chunk k-2 downloaded
         TRY(b200orb_batch_run_device(b, b->d_in[s], b->d_in[s] + np * HW, (int)np, mbf, fx, b->d_kps[s], b->d_desc[s], b->d_nkp[s],
                                      b->d_uR[s], b->d_dep[s], b->d_mi[s], b->s_comp));
+        // the chunk's range-error flags travel on the compute stream itself (the next chunk's run_device clears them there)
+        CU_TRY(cudaMemcpyAsync(b->h_status + p0, b->eng.d_status, np * sizeof(int), cudaMemcpyDeviceToHost, b->s_comp));
         CU_TRY(cudaEventRecord(b->ev_comp[s], b->s_comp));
         CU_TRY(cudaStreamWaitEvent(b->s_out, b->ev_comp[s], 0));
         for (int side = 0; side < 2; ++side) {
@@ -971,6 +1043,8 @@ int b200orb_batch_run_host(b200orb_batch* b, const uint8_t* h_left, const uint8_
     }
     CU_TRY(cudaStreamSynchronize(b->s_out));
     CU_TRY(cudaStreamSynchronize(b->s_comp));
+    for (int i = 0; i < n_pairs; ++i)
+        if (b->h_status[i]) return fail(B200ORB_E_RANGE, kRangeMsg);     // every output is in host memory; flagged pairs hold -1 at the offending keypoints
     return 0;
 }
 

@@ -219,11 +219,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_co
 __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict__ kpsR, const int* __restrict__ nR, long long kp_stride,
                                                          int n_stride, int kp_row, int oct_idx, const __grid_constant__ StereoGeom SG,
                                                          int* __restrict__ rowStart, int4* __restrict__ rmeta,
-                                                         int idx_stride, int* __restrict__ status) {
+                                                         int idx_stride, int* __restrict__ status, int status_stride) {
     const int nRows = SG.nRows;
     extern __shared__ int ri_hist[];     // nRows + 1 counters, then nRows cursors
     __shared__ int ri_tmp[RI_THREADS / 32 + 1];
     const int pair = blockIdx.x;
+    status += (size_t)pair * status_stride;          // one flag word per pair in the batch API (stride 0: one word in all)
     const int n = nR[(size_t)pair * n_stride];
     const float* k = kpsR + (size_t)pair * kp_stride;
     int* rs = rowStart + (size_t)pair * (nRows + 1);
@@ -293,7 +294,8 @@ struct StereoArgs {
     int reach;                                              // bins to visit on each side of the left keypoint's row
     float mbf32, mb, maxD;
     double mbf;
-    float* uRight; float* depth; int* matchIdx; int* status;
+    float* uRight; float* depth; int* matchIdx;
+    int* status; int status_stride;                         // range-error flags: status[pair * status_stride]
     int* sadDist;                                           // optional: SAD minimum of accepted matches, -1 otherwise
 };
 
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 8) k_stereo(const __grid_consta
     const int row = (int)vL;                                // int(vL), Frame.py:192
     unsigned best = (100u << 20);                           // bestDist = TH_HIGH, bestIdxR = 0 (Frame.py:203-204)
     if (row < 0 || row >= SG.nRows) {
-        if (lane == 0) atomicOr(A.status, 1);               // the reference indexes vRowIndices[int(vL)] here
+        if (lane == 0) atomicOr(A.status + (size_t)pair * A.status_stride, 1);   // the reference indexes vRowIndices[int(vL)] here
     } else if (!(uL < 0)) {                                 // maxU < 0 -> continue (Frame.py:200-201)
         const float minU = uL - A.maxD;
         const uint4* dl = reinterpret_cast<const uint4*>(dL + (size_t)iL * 32);
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 8) k_stereo(const __grid_consta
             bool ok = !(sr < 0 || sr + 11 >= w);                                        // Frame.py:240-243
             if (ok && (sv - 5 < 0 || sv + 5 >= h || su - 5 < 0 || su + 5 >= w || sr - 10 < 0 || sr + 10 >= w)) {
                 ok = false;                                                             // the reference would raise
-                if (lane == 0) atomicOr(A.status, 1);
+                if (lane == 0) atomicOr(A.status + (size_t)pair * A.status_stride, 1);
             }
             if (ok) {
                 unsigned char* wl = s_win[warp];

@@ -19,36 +19,46 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 // imgA holds slots [0, splitA), imgB the rest (left / right image batches).
 // ------------------------------------------------------------------------------------------------
 // One thread writes 16 consecutive bytes of the bordered buffer (one 128-bit store).  Interior spans read five
-// aligned 32-bit words of the (arbitrarily aligned) source row and funnel-shift them into place.
+// aligned 32-bit words of the (arbitrarily aligned) source row and funnel-shift them into place; the spans that touch the
+// reflected rim (two or three per row on either side) are byte work.  The two kinds never share a warp: blocks
+// [0, blkA) own the interior spans [vA_lo, vA_lo + vA_n) of every row, the remaining blocks own the rim spans -- a warp
+// that held one rim thread used to pay the ~300-instruction byte path for all 32 lanes (ncu: 10 active threads per
+// instruction on average).
 __global__ void __launch_bounds__(256) k_border0(const __grid_constant__ Plan P, const u8* __restrict__ imgA,
-                                                 const u8* __restrict__ imgB, int splitA, u8* __restrict__ pyr) {
+                                                 const u8* __restrict__ imgB, int splitA, u8* __restrict__ pyr,
+                                                 int blkA, int vA_lo, int vA_n, u32 magicA, int vB_n, u32 magicB) {
     const LevelGeom& G = P.lv[0];
     const int slot = blockIdx.y;
-    const int vec_per_row = G.pitch >> 4;                       // pitch is a multiple of 64
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= vec_per_row * G.rows) return;
-    const int by = idx / vec_per_row, bx = (idx - by * vec_per_row) << 4;
+    const bool interior = (int)blockIdx.x < blkA;
+    const int idx = (interior ? (int)blockIdx.x : (int)blockIdx.x - blkA) * (int)blockDim.x + (int)threadIdx.x;
+    const int per_row = interior ? vA_n : vB_n;
+    int by = (int)__umulhi((u32)idx, interior ? magicA : magicB);     // idx / per_row via ceil(2^32 / d); may overshoot by one
+    if (by * per_row > idx) --by;
+    if (by >= G.rows) return;
+    int v = idx - by * per_row;
+    v = interior ? vA_lo + v : (v < vA_lo ? v : v + vA_n);
+    const int bx = v << 4;
     const u8* img = slot < splitA ? imgA + (size_t)slot * P.H * P.W : imgB + (size_t)(slot - splitA) * P.H * P.W;
     const u8* srow = img + (size_t)reflect101(by - ORB_EDGE, P.H) * P.W;
     const int x0 = bx - ORB_EDGE;
-    u32 v[4] = {0u, 0u, 0u, 0u};
-    if (x0 >= 0 && x0 + 19 < P.W) {                              // interior (the 5th word may touch 3 bytes past the span)
+    u32 o[4] = {0u, 0u, 0u, 0u};
+    if (interior) {                                              // x0 >= 0 && x0 + 19 < W (the 5th word may touch 3 bytes past the span)
         const size_t addr = reinterpret_cast<size_t>(srow + x0);
         const u32* wp = reinterpret_cast<const u32*>(addr & ~(size_t)3);
         const int sh = 8 * (int)(addr & 3);
         const u32 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-        v[0] = __funnelshift_r(w0, w1, sh); v[1] = __funnelshift_r(w1, w2, sh);
-        v[2] = __funnelshift_r(w2, w3, sh); v[3] = __funnelshift_r(w3, w4, sh);
+        o[0] = __funnelshift_r(w0, w1, sh); o[1] = __funnelshift_r(w1, w2, sh);
+        o[2] = __funnelshift_r(w2, w3, sh); o[3] = __funnelshift_r(w3, w4, sh);
     } else {
         const int bw = G.w + 2 * ORB_EDGE;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const int x = bx + k;
             const u32 b = x < bw ? srow[reflect101(x - ORB_EDGE, P.W)] : 0;
-            v[k >> 2] |= b << (8 * (k & 3));
+            o[k >> 2] |= b << (8 * (k & 3));
         }
     }
-    *reinterpret_cast<uint4*>(pyr + (size_t)slot * P.pyr_bytes + G.pyr_ofs + (size_t)by * G.pitch + bx) = make_uint4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<uint4*>(pyr + (size_t)slot * P.pyr_bytes + G.pyr_ofs + (size_t)by * G.pitch + bx) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -81,17 +91,24 @@ __device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel) {       // raw PRMT: 
     return d;
 }
 
-__global__ void __launch_bounds__(256, 5) k_resize(const __grid_constant__ Plan P, int l, int fast_ok, u32 wpr_magic, u8* __restrict__ pyr,
+// Thread -> work mapping: blocks [0, blkA) own the interior column groups [gA_lo, gA_lo + gA_n) of every row group (word-window
+// path, fully converged warps); the remaining blocks own the gB_n groups per row that touch the reflected border columns
+// (per-byte path).  Mixed warps used to execute both paths (ncu: 16-25 active threads per instruction).
+__global__ void __launch_bounds__(256, 5) k_resize(const __grid_constant__ Plan P, int l, int blkA, int gA_lo, int gA_n, u32 magicA,
+                                                int gB_n, u32 magicB, u8* __restrict__ pyr,
                                                 const XTab* __restrict__ xtab, const XGroup* __restrict__ xgrp,
                                                 const YTab* __restrict__ ytab) {
     const LevelGeom& G = P.lv[l];
     const LevelGeom& S = P.lv[l - 1];
     const int slot = blockIdx.y;
-    const int words_per_row = G.pitch >> 2;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    int rq = (int)__umulhi((u32)idx, wpr_magic);            // row group = idx / words_per_row via ceil(2^32 / d); may overshoot by one
-    if (rq * words_per_row > idx) --rq;
-    const int by0 = rq * RS_ROWS, gx = idx - rq * words_per_row, bx = gx << 2;
+    const bool interior = (int)blockIdx.x < blkA;
+    const int idx = (interior ? (int)blockIdx.x : (int)blockIdx.x - blkA) * (int)blockDim.x + (int)threadIdx.x;
+    const int per_row = interior ? gA_n : gB_n;
+    int rq = (int)__umulhi((u32)idx, interior ? magicA : magicB);   // row group = idx / per_row via ceil(2^32 / d); may overshoot by one
+    if (rq * per_row > idx) --rq;
+    int gx = idx - rq * per_row;
+    gx = interior ? gA_lo + gx : (gx < gA_lo ? gx : gx + gA_n);
+    const int by0 = rq * RS_ROWS, bx = gx << 2;
     if (by0 >= G.rows) return;
     u8* base = pyr + (size_t)slot * P.pyr_bytes;
     const u8* srcb = base + S.pyr_ofs;                       // bordered buffer of level l-1 (ROI at +19, +19)
@@ -100,7 +117,7 @@ __global__ void __launch_bounds__(256, 5) k_resize(const __grid_constant__ Plan 
     const int4 g0 = __ldg(gp), g1 = __ldg(gp + 1);           // {wofs, shift8, sel01, sel23}, {cf0..cf3}
     u8* dst = base + G.pyr_ofs + (size_t)by0 * G.pitch + bx;
     const int nr = min(RS_ROWS, G.rows - by0);
-    if (fast_ok && (u32)g0.y != 0xffffffffu) {
+    if (interior) {
         const u32 sh = (u32)g0.y, s0 = (u32)g0.z, s1 = (u32)g0.z >> 16, s2 = (u32)g0.w, s3 = (u32)g0.w >> 16;
         const u32 spw = (u32)S.pitch >> 2;
         const u32* wsrc = reinterpret_cast<const u32*>(srcb) + g0.x + ORB_EDGE * spw;

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     int* misc = (int*)sp; sp += 64 * 4;      // [0..32] scan tmp, [40] m
     int* tmp = misc;
     int* sh_m = misc + 40;
-    if (gnodes) sp = gnodes + ((size_t)slot * gridDim.x + l) * gnode_stride;
+    if (gnodes) sp = gnodes + ((size_t)slot * P.nlevels + l) * gnode_stride;     // [slot][level] blocks, b200orb.cu Engine::plan
     unsigned long long* skeys = (unsigned long long*)sp; sp += (size_t)capN * 8;
     int4* cc = (int4*)sp; sp += (size_t)capN * 16;
     short4* boxA = (short4*)sp; sp += (size_t)capN * 8;

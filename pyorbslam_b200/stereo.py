@@ -12,15 +12,24 @@ from . import _lib
 from .extractor import ORBextractor
 
 
-def _to_lists(uR, dep):
-    # reference: python int -1 where unmatched, float otherwise (Frame.py:163-164, 277-278)
-    u = uR.tolist()
-    d = dep.tolist()
+def _to_lists(uR, dep, mbf=None, uL=None):
+    # reference: python int -1 where unmatched (Frame.py:163-164); matched entries are the NumPy float32 SCALARS that
+    # `bestuR = mvScaleFactors[...] * (...)` and `mbf / disparity` leave under NumPy >= 2 (Frame.py:269,277-278) -- the
+    # element type decides the precision of downstream expressions such as abs(ur - mvuRight[i]) (ORBMatcher.py:356-358).
+    u = list(uR)
+    d = list(dep)
     m = uR < 0
     if m.any():
         for i in np.nonzero(m)[0].tolist():
             u[i] = -1
             d[i] = -1
+    if mbf is not None and uL is not None:
+        # the disparity <= 0 branch (Frame.py:273-275) leaves Python floats built from the literal 0.01; the kernel stores their
+        # float32 roundings, recognisable by the depth value mbf / 0.01
+        z = np.nonzero(dep == np.float32(float(mbf) / 0.01))[0]
+        for i in z.tolist():
+            u[i] = float(uL(i)) - 0.01
+            d[i] = float(mbf) / 0.01
     return u, d
 
 
@@ -85,7 +94,7 @@ def compute_stereo_matches(self):
         uR, dep, _ = stereo_host(kL, self.mDescriptors, kR, self.mDescriptorsRight, self.mvScaleFactors, self.mvInvScaleFactors,
                                  self.mvImagePyramidLeft, self.mvImagePyramidRight, self.mbf, fx,
                                  device=getattr(extL, "_device", 0))
-    self.mvuRight, self.mvDepth = _to_lists(uR, dep)
+    self.mvuRight, self.mvDepth = _to_lists(uR, dep, self.mbf, lambda i: self.mvKeys[i].pt[0])
 
 
 def install(frame_cls, median_cull=False, dense_pyramid=False):

@@ -48,10 +48,15 @@ def stereo_case(name, idx, H, W, params, fx, fy, cx, cy, mbf):
     kR = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in f.mvKeysRight], np.float32)
     uR = np.array([float(v) for v in f.mvuRight], np.float64)
     dep = np.array([float(v) for v in f.mvDepth], np.float64)
+    # element types as the reference leaves them (0 = python int -1, 1 = np.float32 scalar, 2 = python float: the disparity <= 0 branch)
+    codes = {int: 0, np.float32: 1, float: 2}
+    tu = np.array([codes[type(v)] for v in f.mvuRight], np.int8)
+    td = np.array([codes[type(v)] for v in f.mvDepth], np.int8)
     np.savez_compressed(os.path.join(HERE, name), idx=idx, H=H, W=W, params=np.array(params, np.float64),
                         fx=fx, fy=fy, cx=cx, cy=cy, mbf=mbf, image_digest=pair_digest(L, R),
-                        kpsL=kL, descL=f.mDescriptors, kpsR=kR, descR=f.mDescriptorsRight, uRight=uR, depth=dep)
-    print(name, "N", f.N, "matched", int((uR >= 0).sum()))
+                        kpsL=kL, descL=f.mDescriptors, kpsR=kR, descR=f.mDescriptorsRight, uRight=uR, depth=dep,
+                        uRight_type=tu, depth_type=td)
+    print(name, "N", f.N, "matched", int((uR >= 0).sum()), "types", np.bincount(tu, minlength=3).tolist())
 
 
 def main():
