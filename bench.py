@@ -7,6 +7,8 @@
 Workload = BASELINE.json configs[2]: a batch of synthetic KITTI-shape stereo pairs (1241x376, 2000 features,
 8 levels, 1.2, FAST 20/7), `--pairs` pairs per GPU per step (weak scaling: frames are independent, every rank
 owns its own batch, no data-path collective).  One step = one pass of the hot path over that batch.
+Scenes: `--scenes kitti_like` (default; road scenes tuned to the corner / retry / match statistics of the one real KITTI
+frame the reference ships) or `layered` (round 1's harsher generator: more FAST candidates, heavy occlusion).
   value : frames/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e   : frames/s through the host-buffer C-ABI call (pinned H2D of the images + D2H of every result inside the timing)
 Prints ONE JSON line (rank 0).
@@ -129,10 +131,12 @@ class CpuReference:
         import oracle as O
         O.build()
         self.use_ref = refext.available("shipped")
+        if self.use_ref:
+            refext._lib("shipped")      # map the compiled reference into THIS process too (the forked workers inherit the mapping),
+                                        # so a loaded-library record of the arm shows oracle/_ref/libref_shipped.so
         self.workers = workers or max(1, min(os.cpu_count() or 1, 32))
         self.pool = mp.get_context("fork").Pool(self.workers)
-        from pyorbslam_b200.synthetic import make_stereo_pair
-        self.pairs = [make_stereo_pair(i, H, W) for i in range(min(self.workers, 8))]   # a few distinct frames, reused round-robin
+        self.pairs = [make_pair(i, H, W) for i in range(min(self.workers, 8))]   # a few distinct frames, reused round-robin
 
     def step(self, n_pairs):
         work = [(self.pairs[i % len(self.pairs)][0], self.pairs[i % len(self.pairs)][1], self.use_ref) for i in range(n_pairs)]
@@ -154,6 +158,14 @@ class CpuReference:
                 f"extract L+R + KeyPoint lists + pyramids {te*1e3:.0f} ms "
                 f"({'reference ORBextractor.cpp compiled -O3 against oracle/cvshim scalar primitives' if self.use_ref else 'oracle port'}), "
                 f"compute_stereo_matches {ts*1e3:.0f} ms (Python restatement, reference structure)")
+
+
+SCENES = "kitti_like"
+
+
+def make_pair(idx, Hh, Ww):
+    from pyorbslam_b200 import synthetic
+    return (synthetic.make_kitti_like_pair if SCENES == "kitti_like" else synthetic.make_stereo_pair)(idx, Hh, Ww)
 
 
 def run_reference_arm(args):
@@ -184,7 +196,7 @@ def run_reference_arm(args):
 
 
 def workload_config(pairs, chunk):
-    return {"workload": WORKLOAD_NAME,
+    return {"workload": WORKLOAD_NAME, "scenes": SCENES,
             "image": [H, W], **ORB, "bf": MBF, "fx": FX, "pairs_per_gpu_per_step": pairs, "chunk_pairs": chunk, "concurrent_streams": STREAMS,
             "l2": "inputs of one step exceed the 126 MB L2 (0.93 MB per pair)", "parallelism": "frames sharded per GPU, no collective"}
 
@@ -268,7 +280,6 @@ def run_b200_arm(args):
     import torch
     import torch.distributed as dist
     from pyorbslam_b200 import StereoFrontend, _lib
-    from pyorbslam_b200.synthetic import make_stereo_pair
 
     if _lib.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device: pyorbslam_b200 has no CPU fallback")
@@ -276,14 +287,13 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa_node(local)    # pinned host buffers should live on the GPU's own NUMA node
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200ORB_NCCL_DEBUG", "WARN")    # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)     # fd 1 already points at stderr (claim_stdout), so NCCL_DEBUG lines cannot reach stdout
 
     B, P = args.pairs, args.chunk
     nb = args.base_pairs
     # synthetic batch: `nb` distinct scenes per rank, frame i = scene (i % nb) rolled horizontally by 9 * (i // nb) px
     # in BOTH views (disparities unchanged; every frame lands differently on the FAST cell grid)
-    base = [make_stereo_pair(1000 * rank + i, H, W) for i in range(nb)]
+    base = [make_pair(1000 * rank + i, H, W) for i in range(nb)]
     bl = torch.from_numpy(np.stack([p[0] for p in base])).to(dev)
     br = torch.from_numpy(np.stack([p[1] for p in base])).to(dev)
     left = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
@@ -357,7 +367,17 @@ def run_b200_arm(args):
     last_fe = fes[(len(chunks) - 1) % NS]
     ncand = last_fe.candidate_count(2 * chunks[-1][1]) / (2 * chunks[-1][1])
     nkp = float(torch.cat([o["nkp"].float().flatten() for o in outs]).mean())
-    matched = float(sum(int(((o["uRight"] >= 0) & (torch.arange(fe.capacity, device=dev)[None, :] < o["nkp"][0][:, None])).sum()) for o in outs)) / B
+    valid = [torch.arange(fe.capacity, device=dev)[None, :] < o["nkp"][0][:, None] for o in outs]
+    matched = float(sum(int(((o["uRight"] >= 0) & v).sum()) for o, v in zip(outs, valid))) / B
+    ham_ok = float(sum(int(((o["matchIdx"] >= 0) & v).sum()) for o, v in zip(outs, valid))) / B
+    # the same first chunk under the opt-in upstream-ORB-SLAM2 view (true level images instead of the reference's sheared caster
+    # view): how many matches the scenes give when the SAD windows are not sheared -- a scene statistic, not a result
+    fe.set_stereo_options(dense_pyramid=True)
+    c0, n0 = chunks[0]
+    od = fe.run(left[c0:c0 + n0], right[c0:c0 + n0], MBF, FX)
+    matched_dense = float(int(((od["uRight"] >= 0) & valid[0]).sum())) / n0
+    fe.set_stereo_options()
+    del od
 
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -515,6 +535,11 @@ def run_b200_arm(args):
                                     "frac": B_frame * (value / world) / 1e9 / peak},
             "kernels": kernels,
             "workload_stats": {"keypoints_per_image": nkp, "fast_candidates_per_image": ncand, "stereo_matches_per_pair": matched,
+                               "hamming_accepted_per_pair": ham_ok, "stereo_matches_per_pair_true_level_images": matched_dense,
+                               "note": "every Hamming-accepted keypoint runs the full 11-shift SAD slide (the kernel's work); the reference then "
+                                       "rejects ~30 % of them because its pyramid view is sheared (SURVEY.md F6): the windows it compares come from "
+                                       "38 px further along per row, where the disparity differs.  With true level images (opt-in flag) the same "
+                                       "scenes match like upstream ORB-SLAM2 on KITTI",
                                "workspace_bytes": sum(f.workspace_bytes() for f in fes), "rank0_cpu_affinity": numa if isinstance(numa, str) else f"{len(numa)} cpus: {numa[0]}-{numa[-1]}"},
         }
         line["dropin_single_frame_latency"] = dropin
@@ -559,19 +584,19 @@ def main():
     ap.add_argument("--pairs", type=int, default=None, help="stereo pairs per GPU per step (kitti: 4096 = BASELINE.json configs[2])")
     ap.add_argument("--chunk", type=int, default=None, help="pairs per kernel-sequence launch (kitti: 128)")
     ap.add_argument("--base-pairs", type=int, default=16, help="distinct synthetic scenes per rank")
-    ap.add_argument("--e2e-pairs", type=int, default=None, help="pairs per end-to-end step, capped at --pairs; default 4096, 2048 when more than 4 ranks "
-                    "share the host (pinned host memory: 0.93 MB in + 0.25 MB out per pair and rank)")
+    ap.add_argument("--e2e-pairs", type=int, default=2048, help="pairs per end-to-end step, capped at --pairs; the same at every --gpus "
+                    "(pinned host memory: 0.93 MB in + 0.25 MB out per pair and rank)")
     ap.add_argument("--streams", type=int, default=1, help="front-ends running consecutive chunks concurrently (own workspace + stream each)")
+    ap.add_argument("--scenes", default="kitti_like", choices=["kitti_like", "layered"], help="synthetic scene generator (pyorbslam_b200/synthetic.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    global STREAMS, H, W, ORB, WORKLOAD_NAME
+    global STREAMS, H, W, ORB, WORKLOAD_NAME, SCENES
     STREAMS = args.streams
+    SCENES = args.scenes
     wl = WORKLOADS[args.workload]
     H, W, ORB, WORKLOAD_NAME = wl["H"], wl["W"], wl["orb"], wl["name"]
     args.pairs = args.pairs or wl["pairs"]
     args.chunk = args.chunk or wl["chunk"]
-    if args.e2e_pairs is None:
-        args.e2e_pairs = 4096 if int(os.environ.get("WORLD_SIZE", "1")) <= 4 else 2048
     args.e2e_pairs = min(args.e2e_pairs, args.pairs)
     claim_stdout()
     if args.impl == "reference":

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200orb.so")
+LIB_PATH = os.environ.get("B200ORB_LIB") or os.path.join(_HERE, "libb200orb.so")   # B200ORB_LIB: A/B runs of two builds of the library
 _lib = None
 
 E_ARG, E_CUDA, E_STATE, E_RANGE = -1, -2, -3, -4

@@ -3,6 +3,7 @@
 //   K1 border + 7 x resize  ->  K5 blur  ->  K2 FAST cells  ->  K3 octree  ->  K4/K6 orient+describe  ->  K7/K8 stereo
 // for S images at a time (S = 1 for the reference-compatible extractor object, 2 x pairs for the batch API).
 // There is deliberately no CPU implementation behind these entry points.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cmath>
@@ -90,8 +91,10 @@ struct HostPlan {
     std::vector<XGroup> xgrp;
     std::vector<uint2> mtab;      // IC_Angle coefficient table, see k_describe
     std::vector<YTab> ytab;
+    std::vector<unsigned char> roottab;   // k_octree: root index of every candidate column, per level
     int rs_gA_lo[ORB_MAX_LEVELS] = {0}, rs_gA_n[ORB_MAX_LEVELS] = {0}, rs_gB_n[ORB_MAX_LEVELS] = {0};   // k_resize: interior / border column groups
-    int fast_SP = 0, fast_SR = 0, fast_TP = 0, fast_TR = 0, fast_LC = 0;
+    int fast_SP = 0, fast_SR = 0, fast_TP = 0, fast_TR = 0, fast_LC = 0, fast_RQ = 0, fast_cells = 0, fast_WS = 0;
+    LevelMaps maps;               // TMA tensor maps of the pyramid levels (k_fast_cells), rebuilt by Engine::plan
     size_t fast_smem = 0;
     int oct_capN = 0, oct_capK = 0, oct_capC = 0;
     size_t oct_smem = 0, oct_node_stride = 0;
@@ -107,7 +110,7 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
     memset(&P, 0, sizeof(P));
     P.nlevels = prm.nlevels; P.H = H; P.W = W; P.iniTh = prm.iniTh; P.minTh = prm.minTh;
     for (int v = 0; v < 16; ++v) P.umax[v] = prm.umax[v];
-    hp.xtab.clear(); hp.ytab.clear(); hp.xgrp.clear();
+    hp.xtab.clear(); hp.ytab.clear(); hp.xgrp.clear(); hp.roottab.clear();
     int pyr = 0, blr = 0, cells = 0, cand = 0, kpt = 0, fctas = 0, bctas = 0, maxw = 0, maxh = 0, maxcap = 0, maxcells = 0;
     for (int l = 0; l < prm.nlevels; ++l) {
         LevelGeom& G = P.lv[l];
@@ -142,6 +145,15 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
             G.nIni = (int)roundf((float)(G.maxBX - ORB_DET_ORIGIN) / (G.maxBY - ORB_DET_ORIGIN));   // ORBextractor.cpp:543
             if (G.nIni < 1) return fail(B200ORB_E_ARG, "image taller than 2x its width: the reference divides by zero here");
             G.hX = (float)(G.maxBX - ORB_DET_ORIGIN) / G.nIni;
+            if (G.nIni > 250) return fail(B200ORB_E_ARG, "more than 250 octree roots (extreme aspect ratio)");
+            G.root_ofs = (int)hp.roottab.size();
+            // vpIniNodes[pt.x / hX] (ORBextractor.cpp:567): the float division evaluated here for every candidate column; the quotient
+            // is clamped like nothing in the reference is -- x <= maxBX - 16 - 1 keeps it below nIni except by float rounding, where the
+            // reference would index past its vector
+            for (int x = 0; x <= 4095; ++x) {
+                if (x > G.maxBX - ORB_DET_ORIGIN + 8) break;
+                hp.roottab.push_back((unsigned char)std::min((int)((float)x / G.hX), G.nIni - 1));
+            }
         }
         G.kp_cap = nRows ? std::max(4 * G.nIni, G.quota + 3) : 0;
         G.kp_ofs = kpt; kpt += G.kp_cap;
@@ -225,16 +237,17 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
             }
     P.pyr_bytes = pyr; P.blur_bytes = blr; P.ncells = std::max(cells, 1); P.cand_entries = std::max(cand, 4);
     P.kp_total = std::max(kpt, 1); P.fast_ctas = fctas; P.blur_ctas = bctas; P.max_cells_level = maxcells;
-    hp.fast_SP = round_up(15 + FAST_WARPS * maxw + 6 + 16, 16);   // rows are bulk-copied in 16-byte units from a 16-byte aligned start
+    hp.fast_SP = round_up(15 + maxw + 6, 16);  // TMA box: starts at the 16-byte boundary below the window, width a multiple of 16
     hp.fast_SR = maxh + 6;
     hp.fast_TP = round_up(maxw + 2, 4);
     hp.fast_TR = round_up(maxh + 2, 4);       // TP * TR is a multiple of 16: the tiles are cleared with 128-bit stores
     if (maxw > 63 || maxh > 63) return fail(B200ORB_E_ARG, "FAST cell larger than 63 px (level narrower than 62 px after the border?)");
-    hp.fast_LC = round_up(std::max(maxw * maxh, 2), 8);            // 16-byte multiple: the row bitmaps behind the lists are read as uint2 / uint4
-    hp.fast_smem = (size_t)hp.fast_SP * hp.fast_SR + (size_t)FAST_WARPS * hp.fast_TP * hp.fast_TR + (size_t)FAST_WARPS * hp.fast_LC * 2 +
-                   (size_t)FAST_WARPS * 1024;
-    hp.fast_smem = (hp.fast_smem + 15) & ~(size_t)15;
+    hp.fast_LC = round_up(std::max(maxw * maxh, 2), 8);            // 16-byte multiple
+    hp.fast_RQ = 2 * round_up(std::max(maxh, 1), 4) * (maxw > 32 ? 16 : 8);   // per warp: rows x quads x (min | ini nibble pair)
+    hp.fast_WS = round_up(hp.fast_SP * hp.fast_SR + hp.fast_TP * hp.fast_TR + hp.fast_LC * 2 + hp.fast_RQ + 16, 128);   // +16: phase 1 reads whole words past the last row
+    hp.fast_smem = (size_t)FAST_WARPS * hp.fast_WS;
     if (hp.fast_smem > 200 * 1024) return fail(B200ORB_E_ARG, "cell size too large for the FAST kernel's shared memory");
+    hp.fast_cells = cells;
     hp.oct_capN = round_up(maxcap + 8, 4);
     hp.oct_capC = round_up(std::max(maxcells, 1), 4);
     // node arrays go to shared memory when they fit next to >= 2048 keys in ~200 KB, else to a global scratch block
@@ -263,6 +276,8 @@ struct Engine {
     int *d_cellcnt = nullptr, *d_lvlcnt = nullptr, *d_status = nullptr, *d_rowstart = nullptr;
     int4* d_rmeta = nullptr;
     unsigned char* d_octnodes = nullptr;     // node arrays of k_octree when they do not fit in shared memory
+    unsigned char* d_roottab = nullptr;
+    int* d_fastctr = nullptr;                // k_fast_cells: next unclaimed cell
     XTab* d_xtab = nullptr;
     XGroup* d_xgrp = nullptr;
     uint2* d_mtab = nullptr;
@@ -273,20 +288,48 @@ struct Engine {
     // stream so that it fills the SMs the latency-bound octree rounds leave idle; both join in front of K4/K6 (describe)
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int fork_blur = -1;      // -1 = read B200ORB_FORK_BLUR (default on)
+    int fork_blur = -1;      // -1 = read B200ORB_FORK_BLUR (default off: measured, no gain -- the block scheduler drains the earlier launch first)
+    int sm_count = 148;
 
     ~Engine() {
         if (side) { cudaSetDevice(device); cudaStreamDestroy(side); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); }
     }
     void release() {
         cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_cand); cudaFree(d_scratch); cudaFree(d_lvlkp);
-        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_xgrp); d_xgrp = nullptr; cudaFree(d_mtab); d_mtab = nullptr; cudaFree(d_fpat); d_fpat = nullptr; cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr;
+        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_xgrp); d_xgrp = nullptr; cudaFree(d_mtab); d_mtab = nullptr; cudaFree(d_fpat); d_fpat = nullptr; cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr; cudaFree(d_roottab); d_roottab = nullptr; cudaFree(d_fastctr); d_fastctr = nullptr;
         d_pyr = d_blur = nullptr; d_cand = d_scratch = d_lvlkp = nullptr; d_cellcnt = d_lvlcnt = d_status = d_rowstart = nullptr;
         d_xtab = nullptr; d_ytab = nullptr; planned = false; bytes = 0;
     }
     template <typename T> int alloc(T** p, size_t n) {
         CU_TRY(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
         bytes += (long long)(n * sizeof(T));
+        return 0;
+    }
+    // one 3-D tensor map per level over the slots' bordered buffers: {x: pitch bytes, y: rows, z: slot}; box = the FAST window
+    int make_level_maps() {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+            if (!fn || q != cudaDriverEntryPointSuccess) return fail(B200ORB_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+            encode = (EncodeFn)fn;
+        }
+        const Plan& P = hp.P;
+        memset(&hp.maps, 0, sizeof(hp.maps));
+        for (int l = 0; l < P.nlevels; ++l) {
+            const LevelGeom& G = P.lv[l];
+            const cuuint64_t dims[3] = {(cuuint64_t)G.pitch, (cuuint64_t)G.rows, (cuuint64_t)S};
+            const cuuint64_t strides[2] = {(cuuint64_t)G.pitch, (cuuint64_t)P.pyr_bytes};      // bytes, dimensions 1 and 2
+            const cuuint32_t box[3] = {(cuuint32_t)hp.fast_SP, (cuuint32_t)hp.fast_SR, 1u};
+            const cuuint32_t estr[3] = {1u, 1u, 1u};
+            const CUresult r = encode(&hp.maps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + G.pyr_ofs, dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(B200ORB_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        }
         return 0;
     }
     int plan(int H, int W, int slots) {
@@ -307,6 +350,9 @@ struct Engine {
         TRY(alloc(&d_rowstart, (size_t)S * (P.lv[0].h + 1)));
         TRY(alloc(&d_rmeta, (size_t)S * P.kp_total));
         if (hp.oct_global_nodes) TRY(alloc(&d_octnodes, (size_t)S * P.nlevels * hp.oct_node_stride));
+        TRY(alloc(&d_fastctr, 1));
+        TRY(alloc(&d_roottab, hp.roottab.size() + 16));
+        if (!hp.roottab.empty()) CU_TRY(cudaMemcpy(d_roottab, hp.roottab.data(), hp.roottab.size(), cudaMemcpyHostToDevice));
         TRY(alloc(&d_xtab, hp.xtab.size()));
         TRY(alloc(&d_xgrp, hp.xgrp.size()));
         TRY(alloc(&d_mtab, hp.mtab.size()));
@@ -329,7 +375,9 @@ struct Engine {
             CU_TRY(cudaMemcpy(d_fpat, fp.data(), fp.size() * sizeof(float4), cudaMemcpyHostToDevice));
         }
         if (!hp.ytab.empty()) CU_TRY(cudaMemcpy(d_ytab, hp.ytab.data(), hp.ytab.size() * sizeof(YTab), cudaMemcpyHostToDevice));
+        TRY(make_level_maps());
         CU_TRY(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.fast_smem));
+        CU_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
         CU_TRY(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.oct_smem));
         planned = true;
         return 0;
@@ -361,7 +409,7 @@ struct Engine {
             ++g_launches;
         }
         if (evs) cudaEventRecord(evs[2], st);
-        if (fork_blur < 0) { const char* v = getenv("B200ORB_FORK_BLUR"); fork_blur = v ? atoi(v) : 1; }
+        if (fork_blur < 0) { const char* v = getenv("B200ORB_FORK_BLUR"); fork_blur = v ? atoi(v) : 0; }
         const bool fork = fork_blur > 0 && !evs;      // the per-stage timing pass runs the stages back to back on one stream
         if (fork && !side) {
             int lo = 0, hi = 0;
@@ -378,15 +426,19 @@ struct Engine {
         };
         if (!fork || fork_blur == 1) launch_blur();
         if (evs) cudaEventRecord(evs[3], st);
-        if (P.fast_ctas > 0) {
-            k_fast_cells<<<dim3(P.fast_ctas, n), FAST_WARPS * 32, hp.fast_smem, st>>>(P, d_pyr, d_cand, d_cellcnt, hp.fast_SP, hp.fast_SR,
-                                                                                   hp.fast_TP, hp.fast_TR, hp.fast_LC);
+        if (hp.fast_cells > 0) {
+            // persistent: every warp walks cells of the whole launch; 8 CTAs of FAST_WARPS warps per SM are resident
+            const int total = n * hp.fast_cells;
+            const int ctas = std::min((total + FAST_WARPS - 1) / FAST_WARPS, sm_count * 8);
+            CU_TRY(cudaMemsetAsync(d_fastctr, 0, sizeof(int), st));
+            k_fast_cells<<<ctas, FAST_WARPS * 32, hp.fast_smem, st>>>(P, hp.maps, d_cand, d_cellcnt, total, hp.fast_cells, d_fastctr, hp.fast_SP, hp.fast_SR,
+                                                                      hp.fast_TP, hp.fast_TR, hp.fast_LC, hp.fast_RQ, hp.fast_WS);
             ++g_launches;
         }
         if (fork && fork_blur >= 2) launch_blur();
         if (evs) cudaEventRecord(evs[4], st);
         k_octree<<<dim3(n, P.nlevels), OCT_THREADS, hp.oct_smem, st>>>(P, d_cand, d_cellcnt, d_scratch, d_lvlkp, d_lvlcnt, hp.oct_capN,
-                                                                      hp.oct_capK, hp.oct_capC, d_octnodes, hp.oct_node_stride);
+                                                                      hp.oct_capK, hp.oct_capC, d_octnodes, hp.oct_node_stride, d_roottab);
         ++g_launches;
         if (evs) cudaEventRecord(evs[5], st);
         if (fork) CU_TRY(cudaStreamWaitEvent(st, ev_join, 0));

@@ -1,6 +1,7 @@
 // Image-domain kernels: K1 pyramid (border + resize chain), K5 Gaussian blur, K2 per-cell FAST.
 // All integer / byte work, HBM- and shared-memory-bound; no tensor cores by design (no dense contraction).
 #pragma once
+#include <cuda.h>      // CUtensorMap (the FAST windows are 2-D TMA boxes)
 #include "plan.h"
 
 typedef unsigned char u8;
@@ -293,6 +294,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 3-D tiled tensor copy (SASS: UTMALDG): one instruction moves a whole box {x .. x+BW, y .. y+BH, z} of a level into shared memory,
+// rows packed BW bytes apart; coordinates are element indices -- the innermost one must be a multiple of 16 bytes (anything else
+// raises an illegal-instruction fault on B200) --, out-of-range parts are zero-filled
+__device__ __forceinline__ void tma_box_g2s(void* dst_smem, const CUtensorMap* tmap, int x, int y, int z, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+                 : "memory");
+}
+struct alignas(64) LevelMaps { CUtensorMap m[ORB_MAX_LEVELS]; };     // one tensor map per pyramid level: {pitch, rows, slots} bytes
 // bounded wait: a byte-count mistake must end in a trap, never in a hung GPU
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
     u32 done = 0;
@@ -307,14 +317,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
 // ------------------------------------------------------------------------------------------------
 // K2: FAST-9/16 per 30-px cell with the iniThFAST -> minThFAST retry (ORBextractor.cpp:788-828) and
 // cv::FAST's cell-confined strict non-max suppression.
-// One CTA = one strip of FAST_WARPS consecutive cells of a cell row: the raw strip (cells + 3-px rim) is
-// staged in shared memory once by the copy engine (one cp.async.bulk per row, mbarrier completion), then one
-// warp per cell runs quick reject -> compacted work list -> exact corner strength -> strict NMS inside its own
-// detection window, first at iniThFAST and again at minThFAST only if nothing survived, and emits the
-// survivors in row-major order with ballot-ranked stores.
+// Persistent, barrier-free: every WARP is an independent worker that walks the cells c = global warp id, + total warps, ...
+// of the whole launch (all images, all levels).  A cell's raw window (detection area + 3-px rim) is staged in the warp's private
+// shared-memory buffer by ONE tensor-map TMA copy (cp.async.bulk.tensor.3d of a BW x BH box at the cell's pixel coordinates,
+// completion counted on the warp's own mbarrier); the copy of the NEXT cell is issued as soon as the current cell's last
+// scoring pass is done, so it lands underneath the NMS / emission work and nobody ever waits at a block-wide barrier (the
+// strip-per-CTA version lost 22 % of its warp time there; per-row bulk copies issued by 32 lanes cost ~10 instructions each).
+// Per cell: quick reject of every pixel at both thresholds -> row bitmaps -> ordered work list -> exact corner strength ->
+// strict NMS inside the cell's own detection window, at iniThFAST first and at minThFAST only if nothing survived ->
+// survivors emitted in row-major order with ballot-ranked stores.
 // Output per cell: count + packed (x | y<<12 | score<<24), x/y relative to the (16,16) detection origin.
 // ------------------------------------------------------------------------------------------------
-#define FAST_WARPS 8
+#define FAST_WARPS 4      // independent warps per CTA
 
 // The 16 ring pixels of the Bresenham circle, clockwise from (0,+3) (OpenCV FAST pattern 16).
 __device__ __forceinline__ void fast_ring(const u8* p, int SP, int (&q)[16]) {
@@ -334,69 +348,92 @@ __device__ __forceinline__ bool fast_quick(const u8* p, int SP, int t) {
     return br | dk;
 }
 
-// The same reject for FOUR consecutive pixels of a row (address o, o & 3 == AL) from aligned 32-bit shared-memory words:
-// the five operands (centre, x-3, x+3, y-3, y+3) are cut out of the words with funnel shifts, spread into 16-bit lanes
-// (pixels 0|2 and 1|3) and tested two pixels per instruction with the packed min / max (VIMNMX.U16x2):
-//   bright <=> min(max(a,b), max(c,d)) > v + t,   dark <=> max(min(a,b), min(c,d)) < v - t
-// and  m + (0x7fff - t) - v  sets bit 15 of a lane  <=>  m - v > t  (lanes stay inside [0x7e01, 0x80fe]: no carry, no borrow).
-// Returns a nibble: bit k = pixel k passes.
-__device__ __forceinline__ u32 fast_quick2(u32 v, u32 a, u32 b, u32 c, u32 d, u32 Kt) {
+// The same reject for FOUR consecutive pixels of a row (address o, o & 3 == AL) from aligned 32-bit shared-memory words, for BOTH
+// thresholds at once (iniThFAST and minThFAST, ORBextractor.cpp:808-815): the five operands (centre, x-3, x+3, y-3, y+3) are cut
+// out of the words with funnel shifts, spread into 16-bit lanes (pixels 0|2 and 1|3) and tested two pixels per instruction with
+// the packed min / max (VIMNMX.U16x2):
+//   bright at t <=> min(max(a,b), max(c,d)) - v > t,   dark at t <=> v - max(min(a,b), min(c,d)) > t
+// With A = mn + 0x7fff - v and B = v + 0x7fff - mx per lane (both inside [0x7f00, 0x80fe]: no carry, no borrow),
+// (A - t) | (B - t) has bit 15 of a lane set <=> the pixel passes at t.  ri / rm: bit 15 / 31 = pixel of the low / high lane.
+__device__ __forceinline__ void fast_quick2(u32 v, u32 a, u32 b, u32 c, u32 d, u32 Ti, u32 Tm, u32& ri, u32& rm) {
     const u32 mn = __vminu2(__vmaxu2(a, b), __vmaxu2(c, d));
     const u32 mx = __vmaxu2(__vminu2(a, b), __vminu2(c, d));
-    return ((mn + Kt - v) | (v + Kt - mx)) & 0x80008000u;
+    const u32 A = mn + (0x7fff7fffu - v), B = (v + 0x7fff7fffu) - mx;
+    ri = ((A - Ti) | (B - Ti)) & 0x80008000u;
+    rm = ((A - Tm) | (B - Tm)) & 0x80008000u;
 }
-template <int OFS>
-__device__ __forceinline__ u32 fast_cut4(const u32* w) {       // bytes OFS .. OFS + 3 of the word array
-    if constexpr ((OFS & 3) == 0) return w[OFS >> 2];
-    else return __funnelshift_r(w[OFS >> 2], w[(OFS >> 2) + 1], 8 * (OFS & 3));
+// -> min-threshold nibble in bits 0..3, ini-threshold nibble in bits 8..11 (bit k = pixel k passes).
+// o = address of the first of the four pixels; al = o & 3 is loop-invariant per cell, so the word offsets / funnel-shift
+// amounts of the five operands are plain registers (one code path for all four alignments: the kernel used to carry four
+// template copies of this loop and stalled on instruction fetch).
+struct FastCut { int wL, wR, shL, shC, shR; };     // word index of L / R relative to the centre-row base, byte shifts * 8
+__device__ __forceinline__ FastCut fast_cut_setup(int al) {
+    FastCut c;
+    c.wL = (al + 1) >> 2; c.wR = (al + 7) >> 2;
+    c.shL = 8 * ((al + 1) & 3); c.shC = 8 * (al & 3); c.shR = 8 * ((al + 7) & 3);
+    return c;
 }
-template <int AL>
-__device__ __forceinline__ u32 fast_quick4(const u8* o, int SP, u32 Kt) {
-    const u32* wc = reinterpret_cast<const u32*>(o - AL - 4);            // centre row: bytes -AL-4 .. of the pixel group
-    const u32* wt = reinterpret_cast<const u32*>(o - AL + 3 * SP);
-    const u32* wb = reinterpret_cast<const u32*>(o - AL - 3 * SP);
-    const u32 L = fast_cut4<AL + 1>(wc), C = fast_cut4<AL + 4>(wc), R = fast_cut4<AL + 7>(wc);
-    const u32 T = fast_cut4<AL>(wt), B = fast_cut4<AL>(wb);
-    const u32 pe = fast_quick2(__byte_perm(C, 0, 0x4240), __byte_perm(T, 0, 0x4240), __byte_perm(B, 0, 0x4240),
-                               __byte_perm(R, 0, 0x4240), __byte_perm(L, 0, 0x4240), Kt);      // pixels 0 | 2
-    const u32 po = fast_quick2(__byte_perm(C, 0, 0x4341), __byte_perm(T, 0, 0x4341), __byte_perm(B, 0, 0x4341),
-                               __byte_perm(R, 0, 0x4341), __byte_perm(L, 0, 0x4341), Kt);      // pixels 1 | 3
-    const u32 x = (pe >> 15) | (po >> 14);
-    return (x | (x >> 14)) & 0xfu;
+__device__ __forceinline__ u32 fast_quick4(const u8* o, int al, const FastCut& fc, int SP, u32 Ti, u32 Tm) {
+    const u32* wc = reinterpret_cast<const u32*>(o - al - 4);            // centre row: bytes -al-4 .. of the pixel group
+    const u32* wt = reinterpret_cast<const u32*>(o - al + 3 * SP);
+    const u32* wb = reinterpret_cast<const u32*>(o - al - 3 * SP);
+    const u32 c0 = wc[0], c1 = wc[1], c2 = wc[2], c3 = wc[3];            // bytes -al-4 .. -al+11 (the strip rows carry 16 bytes of slack)
+    const u32 L = __funnelshift_r(fc.wL ? c1 : c0, fc.wL ? c2 : c1, fc.shL);
+    const u32 C = __funnelshift_r(c1, c2, fc.shC);
+    const u32 R = __funnelshift_r(fc.wR == 1 ? c1 : c2, fc.wR == 1 ? c2 : c3, fc.shR);
+    const u32 T = __funnelshift_r(wt[0], wt[1], fc.shC), B = __funnelshift_r(wb[0], wb[1], fc.shC);
+    u32 ei, em, oi, om;
+    fast_quick2(__byte_perm(C, 0, 0x4240), __byte_perm(T, 0, 0x4240), __byte_perm(B, 0, 0x4240),
+                __byte_perm(R, 0, 0x4240), __byte_perm(L, 0, 0x4240), Ti, Tm, ei, em);            // pixels 0 | 2
+    fast_quick2(__byte_perm(C, 0, 0x4341), __byte_perm(T, 0, 0x4341), __byte_perm(B, 0, 0x4341),
+                __byte_perm(R, 0, 0x4341), __byte_perm(L, 0, 0x4341), Ti, Tm, oi, om);            // pixels 1 | 3
+    const u32 e = ei | (em >> 8), o2 = oi | (om >> 8);      // bits 15 / 31 = ini, bits 7 / 23 = min
+    const u32 x = (e >> 7) | (o2 >> 6);                     // min: bits 0,1,16,17   ini: bits 8,9,24,25
+    return (x | (x >> 14)) & 0x0f0fu;
 }
 
 // Phase 1 of a cell (detection window up to 63 x 63): a lane tests 4 consecutive pixels of a row -- 8 lanes per row and 4 rows
-// per step for windows up to 32 px wide, 16 lanes per row and 2 rows per step beyond -- and drops the nibble into a per-row
-// bitmap; then lane r turns the masks of rows r and r + 32 into list entries at the offsets an exclusive warp scan of the
-// row counts gives: row-major order by construction, no per-pixel ballot.
-template <int AL>
-__device__ __forceinline__ int fast_phase1_quads(const u8* s0, int SP, int cw, int ch, int T, u8* rowbits, unsigned short* list, int lane) {
+// per step for windows up to 32 px wide, 16 lanes per row and 2 rows per step beyond -- and drops the two nibbles (one 16-bit
+// store) into a per-row table: rowq[row][quad], 8 or 16 quads per row.
+__device__ __forceinline__ void fast_phase1_bits(const u8* s0, int SP, int cw, int ch, int Ti, int Tm, unsigned short* rowq, int lane) {
     const bool wide = cw > 32;
     const int sh = wide ? 4 : 3, r = lane >> sh, q = lane & ((1 << sh) - 1), rstep = 32 >> sh;
-    const u32 Kt = (u32)(0x7fff - T) * 0x00010001u;
+    const u32 ti = (u32)Ti * 0x00010001u, tm = (u32)Tm * 0x00010001u;
+    const int al = (int)(reinterpret_cast<size_t>(s0) & 3);              // rows are SP apart (multiple of 16), groups 4 apart
+    const FastCut fc = fast_cut_setup(al);
     if (4 * q < cw) {
         const u8* o = s0 + r * SP + 4 * q;
-        u8* rb = rowbits + (r << sh) + q;
+        unsigned short* rb = rowq + (r << sh) + q;
 #pragma unroll 2
-        for (int y = r; y < ch; y += rstep, o += rstep * SP, rb += 32) *rb = (u8)fast_quick4<AL>(o, SP, Kt);
+        for (int y = r; y < ch; y += rstep, o += rstep * SP, rb += 32) *rb = (unsigned short)fast_quick4(o, al, fc, SP, ti, tm);
     }
     __syncwarp();
-    // nibble bytes -> 64-bit row masks of rows lane and lane + 32
-    auto squeeze = [](u32 w) { u32 a = (w | (w >> 4)) & 0x00ff00ffu; return (a | (a >> 8)) & 0xffffu; };
+}
+
+// Row-major work list of a cell from the phase-1 table: lane r turns the masks of rows r and r + 32 into list entries (y << 6 | x)
+// at the offsets an exclusive warp scan of the row counts gives -- row-major order by construction, no per-pixel ballot.
+// which = 0: pixels passing at iniThFAST;  1: pixels passing at minThFAST but not at iniThFAST;  2: all passing at minThFAST.
+__device__ __forceinline__ int fast_expand(const unsigned short* rowq, int cw, int ch, int which, unsigned short* list, int lane) {
+    const bool wide = cw > 32;
+    // a 32-bit word holds two quads: min nibbles at bits 0..3 / 16..19, ini nibbles at bits 8..11 / 24..27
+    auto nib_min = [](u32 w) { return (w & 0xfu) | ((w >> 12) & 0xf0u); };
+    auto nib_ini = [](u32 w) { return ((w >> 8) & 0xfu) | ((w >> 20) & 0xf0u); };
     const unsigned long long colmask = (1ull << cw) - 1ull;
     unsigned long long m[2] = {0ull, 0ull};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int row = lane + 32 * h;
         if (row < ch) {
+            unsigned long long mi, mm;
+            const uint4 w = *reinterpret_cast<const uint4*>(rowq + row * (wide ? 16 : 8));
+            mi = nib_ini(w.x) | (nib_ini(w.y) << 8) | (nib_ini(w.z) << 16) | (nib_ini(w.w) << 24);
+            mm = nib_min(w.x) | (nib_min(w.y) << 8) | (nib_min(w.z) << 16) | (nib_min(w.w) << 24);
             if (wide) {
-                const uint4 w = *reinterpret_cast<const uint4*>(rowbits + row * 16);
-                m[h] = (unsigned long long)(squeeze(w.x) | (squeeze(w.y) << 16)) | ((unsigned long long)(squeeze(w.z) | (squeeze(w.w) << 16)) << 32);
-            } else {
-                const uint2 w = *reinterpret_cast<const uint2*>(rowbits + row * 8);
-                m[h] = squeeze(w.x) | (squeeze(w.y) << 16);
+                const uint4 w2 = *reinterpret_cast<const uint4*>(rowq + row * 16 + 8);
+                mi |= (unsigned long long)(nib_ini(w2.x) | (nib_ini(w2.y) << 8) | (nib_ini(w2.z) << 16) | (nib_ini(w2.w) << 24)) << 32;
+                mm |= (unsigned long long)(nib_min(w2.x) | (nib_min(w2.y) << 8) | (nib_min(w2.z) << 16) | (nib_min(w2.w) << 24)) << 32;
             }
-            m[h] &= colmask;
+            m[h] = (which == 0 ? mi : which == 1 ? (mm & ~mi) : mm) & colmask;
         }
     }
     int base = 0;
@@ -488,137 +525,177 @@ __device__ __forceinline__ int fast_score(const u8* p, int SP, int t) {
 
 // Work list entry: y << 6 | x inside the cell's detection window (both < 64), bit 15 = survives NMS.
 // Phases per cell (one warp), each on FULL warps thanks to in-place ordered compaction of the list:
-//   1 quick reject over all window pixels        -> list A (row-major)
-//   2+3 exact corner strength of list A (packed 3-input min/max); entries with score >= threshold -> list B (in place)
-//       and the score tile (zero elsewhere = "non-corner / outside scores 0")
-//   4 strict 8-neighbour NMS on list B; any survivor with score >= iniThFAST decides the threshold
-//   5 ordered emission of survivors with score >= T
-__global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_cells(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
-                                                                u32* __restrict__ cand, int* __restrict__ cellcnt,
-                                                                int SP /*strip pitch*/, int SR /*strip rows*/, int TP /*tile pitch*/, int TR /*tile rows*/,
-                                                                int LC /*list capacity per warp*/) {
-    extern __shared__ __align__(16) u8 smem[];
-    u8* strip = smem;
-    const int slot = blockIdx.y;
+//   1   quick reject of all window pixels at BOTH thresholds, once                        -> per-row bit table
+//   2+3 exact corner strength (packed 3-input min/max) of the pixels passing at iniThFAST -> score tile (every score >= 1);
+//       entries with score >= iniThFAST stay in the list (in place)
+//   4   strict 8-neighbour NMS on that list
+//   R   only if nothing survived (ORBextractor.cpp:811): score the pixels passing at minThFAST but not at iniThFAST, rebuild the
+//       list from the minThFAST bits, keep score >= minThFAST, NMS again
+//   5   ordered emission of the survivors
+// Survivors at T are exactly the strict local maxima among the pixels with score >= T: a neighbour with a lower score never
+// suppresses, so scores below T left in the tile are harmless and nothing is cleared between the two attempts.
+struct FastCell {            // geometry of one cell (warp-uniform)
+    int slot, level, cell;   // cell = index inside the level
+    int iniX, iniY, cw, ch;  // window origin (incl. the 3-px rim, level coordinates) and detection size; cw <= 0: the reference skips the cell
+};
+__device__ __forceinline__ void fast_cell_geom(const Plan& P, int c, int cells_per_slot, FastCell& g) {
+    const int slot = c / cells_per_slot, rem = c - slot * cells_per_slot;
     int l = 0;
-    const int bid = (int)blockIdx.x;
-    while (l + 1 < P.nlevels && bid >= P.lv[l + 1].fast_cta_ofs) ++l;
+    while (l + 1 < P.nlevels && rem >= P.lv[l + 1].cell_ofs) ++l;      // levels without cells share their successor's offset
     const LevelGeom& G = P.lv[l];
-    const int local = bid - G.fast_cta_ofs;
-    const int ci = local / G.fast_groups, g = local - ci * G.fast_groups;
-    const int j0 = g * FAST_WARPS;
+    const int local = rem - G.cell_ofs;
+    const int ci = local / G.nCols, j = local - ci * G.nCols;
+    g.slot = slot; g.level = l; g.cell = local;
+    g.iniY = ORB_DET_ORIGIN + ci * G.hCell;
+    const int maxY = min(g.iniY + G.hCell + 6, G.maxBY);
+    g.iniX = ORB_DET_ORIGIN + j * G.wCell;
+    const int maxX = min(g.iniX + G.wCell + 6, G.maxBX);
+    g.cw = maxX - g.iniX - 6; g.ch = maxY - g.iniY - 6;                  // detection window (FAST skips a 3-px rim)
+    if (g.iniY >= G.maxBY - 3 || g.iniX >= G.maxBX - 6 || g.ch <= 0) g.cw = 0;   // ORBextractor.cpp:793,801 / image < 7 px
+}
+
+__global__ void __launch_bounds__(FAST_WARPS * 32, 8) k_fast_cells(const __grid_constant__ Plan P, const __grid_constant__ LevelMaps M,
+                                                                   u32* __restrict__ cand, int* __restrict__ cellcnt,
+                                                                   int total_cells, int cells_per_slot, int* __restrict__ next_cell,
+                                                                   int SP /*window pitch = box width*/, int SR /*window rows = box height*/,
+                                                                   int TP /*tile pitch*/, int TR /*tile rows*/,
+                                                                   int LC /*list capacity*/, int RQ /*bytes of the row table*/, int WS /*bytes per warp*/) {
+    extern __shared__ __align__(128) u8 smem[];
+    __shared__ unsigned long long win_bar[FAST_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 lt = (1u << lane) - 1;
-
-    const int iniY = ORB_DET_ORIGIN + ci * G.hCell;
-    const int maxY = min(iniY + G.hCell + 6, G.maxBY);
-    const bool rowSkip = iniY >= G.maxBY - 3;            // ORBextractor.cpp:793
-    const int sx0 = ORB_DET_ORIGIN + j0 * G.wCell;
-    const int sx1 = min(ORB_DET_ORIGIN + min(j0 + FAST_WARPS, G.nCols) * G.wCell + 6, G.maxBX);
-    const int srows = maxY - iniY;
-    // stage the strip with the copy engine: one bulk copy per row (16-byte aligned on both sides), completion counted on an
-    // mbarrier; meanwhile every warp zeroes its score tile
-    __shared__ unsigned long long strip_bar;
-    const int bufx0 = sx0 + ORB_EDGE, ax0 = bufx0 & ~15, shift = bufx0 - ax0;
-    const bool have_strip = !rowSkip && sx1 > sx0;
-    const u32 row_bytes = have_strip ? (u32)((shift + (sx1 - sx0) + 15) & ~15) : 0u;
-    if (threadIdx.x == 0) mbar_init(&strip_bar, 1);
-    __syncthreads();
-    if (have_strip && warp == 0) {
-        if (lane == 0) mbar_expect_tx(&strip_bar, row_bytes * (u32)srows);
-        __syncwarp();
-        const u8* src = pyr + (size_t)slot * P.pyr_bytes + G.pyr_ofs + (size_t)(iniY + ORB_EDGE) * G.pitch + ax0;
-        for (int r = lane; r < srows; r += 32) bulk_g2s(strip + r * SP, src + (size_t)r * G.pitch, row_bytes, &strip_bar);
-    }
-    // zero this warp's score tile while the copies are in flight (the rim is what "outside the window scores 0" means)
-    u8* tile = smem + SP * SR + warp * (TP * TR);
-    for (int i = lane; i < (TP * TR) >> 4; i += 32) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);   // TP, TR multiples of 4
-    if (have_strip) mbar_wait(&strip_bar, 0);
+    // the warp's private carve-out (128-byte aligned): window | score tile | work list | row table
+    u8* win = smem + (size_t)warp * WS;
+    u8* tile = win + SP * SR;
+    unsigned short* list = reinterpret_cast<unsigned short*>(tile + TP * TR);
+    unsigned short* rowq = list + LC;
+    unsigned long long* bar = &win_bar[warp];
+    if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
-
-    const int j = j0 + warp;
-    if (j >= G.nCols) return;
-    const int cell = ci * G.nCols + j;
-    int* cnt_out = cellcnt + (size_t)slot * P.ncells + G.cell_ofs + cell;
-    const int iniX = ORB_DET_ORIGIN + j * G.wCell;
-    const int maxX = min(iniX + G.wCell + 6, G.maxBX);
-    const int cw = maxX - iniX - 6, ch = maxY - iniY - 6;   // detection window (FAST skips a 3-px rim)
-    if (rowSkip || iniX >= G.maxBX - 6 || cw <= 0 || ch <= 0) {   // ORBextractor.cpp:793,801 / image < 7 px
-        if (lane == 0) *cnt_out = 0;
-        return;
-    }
-    unsigned short* list = reinterpret_cast<unsigned short*>(smem + SP * SR + FAST_WARPS * (TP * TR)) + warp * LC;
-    u8* rowbits = smem + SP * SR + FAST_WARPS * (TP * TR) + FAST_WARPS * LC * 2 + warp * 1024;  // 64 rows x 16 nibble bytes
-    const u8* s0 = strip + 3 * SP + (iniX - sx0) + shift + 3;
-
-    // Threshold schedule = the reference's own (ORBextractor.cpp:808-815): detect at iniThFAST; only if nothing survives
-    // the NMS, detect again at minThFAST.  Survivors at T are exactly the strict local maxima among corners with
-    // score >= T (corners below T count 0), so running the whole pipeline at T first is equivalent to thresholding a
-    // minThFAST score map -- and far cheaper for textured cells, whose quick-test pass rate at 20 is a fraction of that at 7.
+    // dynamic work distribution: a warp takes the next unclaimed cell (global counter, zeroed by the host before the launch), so the
+    // launch ends when the cells run out, not when the unluckiest static share does
+    auto claim = [&]() { int v = 0; if (lane == 0) v = atomicAdd(next_cell, 1); return __shfl_sync(0xffffffffu, v, 0); };
+    int c = claim();
+    FastCell cur;
+    // stage a cell's window: one elected lane, one TMA box copy
+    const CUtensorMap* const maps = M.m;          // address inside the kernel parameter block (__grid_constant__): valid for the TMA unit
+    const u32 box_bytes = (u32)(SP * SR);
+    auto stage = [&](const FastCell& g) {
+        if (g.cw <= 0 || lane != 0) return;
+        mbar_expect_tx(bar, box_bytes);
+        tma_box_g2s(win, maps + g.level, (g.iniX + ORB_EDGE) & ~15, g.iniY + ORB_EDGE, g.slot, bar);   // the box must start 16-byte aligned
+    };
+    if (c < total_cells) { fast_cell_geom(P, c, cells_per_slot, cur); stage(cur); }
     const int iniTh = max(0, min(P.iniTh, 255)), minTh = max(0, min(P.minTh, 255));
-    int T = iniTh, nB = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        // ---- phase 1 ----
-        int nA = 0;
-        switch ((int)(reinterpret_cast<size_t>(s0) & 3)) {     // four pixels per lane, see fast_phase1_quads
-            case 0: nA = fast_phase1_quads<0>(s0, SP, cw, ch, T, rowbits, list, lane); break;
-            case 1: nA = fast_phase1_quads<1>(s0, SP, cw, ch, T, rowbits, list, lane); break;
-            case 2: nA = fast_phase1_quads<2>(s0, SP, cw, ch, T, rowbits, list, lane); break;
-            default: nA = fast_phase1_quads<3>(s0, SP, cw, ch, T, rowbits, list, lane); break;
-        }
-        __syncwarp();
-        // ---- phases 2 + 3: exact corner strength of every quick-test survivor; corner at T <=> best > T <=> score >= T
-        // (a score of 0 can never win the strict NMS, so it is dropped like a non-corner) ----
-        const int tKeep = max(T, 1);
-        nB = 0;
-        for (int b = 0; b < nA; b += 32) {
+    u32 parity = 0;
+#pragma unroll 1
+    while (c < total_cells) {
+    const LevelGeom& G = P.lv[cur.level];
+    int* cnt_out = cellcnt + (size_t)cur.slot * P.ncells + G.cell_ofs + cur.cell;
+    const int cw = cur.cw, ch = cur.ch;
+    FastCell nxt;
+    const int cn = claim();
+    const bool more = cn < total_cells;
+    if (more) fast_cell_geom(P, cn, cells_per_slot, nxt);
+    if (cw <= 0) {                                          // cell the reference skips: nothing was staged for it
+        if (lane == 0) *cnt_out = 0;
+        if (more) stage(nxt);
+        cur = nxt; c = cn;
+        continue;
+    }
+    // zero the score tile (the rim is what "outside the window scores 0" means), then make sure the window has landed
+    for (int i = lane; i < (TP * TR) >> 4; i += 32) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);   // TP, TR multiples of 4
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    __syncwarp();
+    const u8* s0 = win + 3 * SP + ((cur.iniX + ORB_EDGE) & 15) + 3;     // first detection pixel (the box starts at the 16-byte boundary below the window)
+
+    // ---- phase 1, both thresholds ----
+    fast_phase1_bits(s0, SP, cw, ch, iniTh, minTh, rowq, lane);     // four pixels per lane
+    // exact corner strength of list[0, n): every score >= 1 goes to the tile (a score of 0 can never win the strict NMS, so it is
+    // dropped like a non-corner); entries with score >= tKeep are kept, compacted in place.  corner at T <=> best > T <=> score >= T
+    auto score_list = [&](int n, int tKeep) {
+        int kept = 0;
+        for (int b = 0; b < n; b += 32) {
             const int i = b + lane;
-            const int e = i < nA ? list[i] : 0;
+            const int e = i < n ? list[i] : 0;
             const int y = e >> 6, x = e & 63;
-            const int s = i < nA ? fast_corner_score(s0 + y * SP + x, SP) : 0;
-            const bool c = s >= tKeep;
+            const int sc = i < n ? fast_corner_score(s0 + y * SP + x, SP) : 0;
+            const bool c = sc >= tKeep;
             const u32 m = __ballot_sync(0xffffffffu, c);
             __syncwarp();
-            if (c) {
-                list[nB + __popc(m & lt)] = (unsigned short)e;
-                tile[(y + 1) * TP + x + 1] = (u8)s;
-            }
-            nB += __popc(m);
+            if (sc > 0) tile[(y + 1) * TP + x + 1] = (u8)sc;
+            if (c) list[kept + __popc(m & lt)] = (unsigned short)e;
+            kept += __popc(m);
         }
         __syncwarp();
-        // ---- phase 4: strict 8-neighbour NMS inside the window ----
+        return kept;
+    };
+    // strict 8-neighbour NMS inside the window: survivors get bit 15
+    auto nms_list = [&](int n) {
         bool any = false;
-        for (int i = lane; i < nB; i += 32) {
+        for (int i = lane; i < n; i += 32) {
             const int e = list[i];
             const u8* t = tile + ((e >> 6) + 1) * TP + (e & 63) + 1;
-            const int s = t[0];
-            const bool keep = s > t[-1] && s > t[1] && s > t[-TP - 1] && s > t[-TP] && s > t[-TP + 1] &&
-                              s > t[TP - 1] && s > t[TP] && s > t[TP + 1];
+            const int sc = t[0];
+            const bool keep = sc > t[-1] && sc > t[1] && sc > t[-TP - 1] && sc > t[-TP] && sc > t[-TP + 1] &&
+                              sc > t[TP - 1] && sc > t[TP] && sc > t[TP + 1];
             if (keep) { list[i] = (unsigned short)(e | 0x8000); any = true; }
         }
         __syncwarp();
-        if (__any_sync(0xffffffffu, any) || minTh >= T) break;      // vKeysCell non-empty, or the retry cannot add anything
-        for (int i = lane; i < nB; i += 32) {                        // clear the tile for the second attempt
-            const int e = list[i];
-            tile[((e >> 6) + 1) * TP + (e & 63) + 1] = 0;
+        return __any_sync(0xffffffffu, any);
+    };
+    // One loop body for the three list passes (a single copy of the expansion / scoring / NMS code: the kernel is sensitive to
+    // instruction-cache misses):
+    //   pass 0  pixels passing at iniThFAST: score, keep score >= iniThFAST, NMS (ORBextractor.cpp:808-809); done if anything survives
+    //   pass 1  vKeysCell.empty() (:811): pixels passing at minThFAST but not at iniThFAST: score only (the others are in the tile)
+    //   pass 2  all pixels passing at minThFAST: keep tile score >= minThFAST, NMS (:813-815)
+    int nB = 0;
+    bool staged = false;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        const int n = fast_expand(rowq, cw, ch, pass, list, lane);
+        if (pass < 2) {
+            nB = score_list(n, pass == 0 ? max(iniTh, 1) : 256);
+            if (pass == 1) {      // last pass that reads the window: the next cell's copy may start now
+                __syncwarp();
+                if (more) stage(nxt);
+                staged = true;
+                continue;
+            }
+        } else {
+            const int tKeep = max(minTh, 1);
+            nB = 0;
+            for (int b0 = 0; b0 < n; b0 += 32) {
+                const int i = b0 + lane;
+                const int e = i < n ? list[i] : 0;
+                const bool cc = i < n && tile[((e >> 6) + 1) * TP + (e & 63) + 1] >= tKeep;
+                const u32 m = __ballot_sync(0xffffffffu, cc);
+                __syncwarp();
+                if (cc) list[nB + __popc(m & lt)] = (unsigned short)e;
+                nB += __popc(m);
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        T = minTh;
-        nB = 0;
+        if (nms_list(nB) || minTh >= iniTh) break;
     }
+    if (!staged && more) { __syncwarp(); stage(nxt); }
     // ---- phase 5 ----
-    u32* out = cand + (size_t)slot * P.cand_entries + G.cand_ofs + (size_t)cell * G.cell_cap;
+    u32* out = cand + (size_t)cur.slot * P.cand_entries + G.cand_ofs + (size_t)cur.cell * G.cell_cap;
     int count = 0;
-    const int xrel0 = iniX - ORB_DET_ORIGIN + 3, yrel0 = iniY - ORB_DET_ORIGIN + 3;
-    for (int b = 0; b < nB; b += 32) {
-        const int i = b + lane;
+    const int xrel0 = cur.iniX - ORB_DET_ORIGIN + 3, yrel0 = cur.iniY - ORB_DET_ORIGIN + 3;
+    for (int b0 = 0; b0 < nB; b0 += 32) {
+        const int i = b0 + lane;
         const int e = i < nB ? list[i] : 0;
         const int y = (e >> 6) & 63, x = e & 63;
-        const int s = tile[(y + 1) * TP + x + 1];
+        const int sc = tile[(y + 1) * TP + x + 1];
         const bool keep = (e & 0x8000) != 0;
         const u32 m = __ballot_sync(0xffffffffu, keep);
-        if (keep) out[count + __popc(m & lt)] = (u32)(xrel0 + x) | ((u32)(yrel0 + y) << 12) | ((u32)s << 24);
+        if (keep) out[count + __popc(m & lt)] = (u32)(xrel0 + x) | ((u32)(yrel0 + y) << 12) | ((u32)sc << 24);
         count += __popc(m);
     }
     if (lane == 0) *cnt_out = count;
+    __syncwarp();
+    cur = nxt; c = cn;
+    }
 }

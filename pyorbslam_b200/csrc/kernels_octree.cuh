@@ -124,7 +124,8 @@ __host__ __device__ inline size_t oct_base_bytes(int capK, int capC) { return (s
 __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ Plan P, const u32* __restrict__ cand,
                                                         const int* __restrict__ cellcnt, u32* __restrict__ scratch,
                                                         u32* __restrict__ lvl_kp, int* __restrict__ lvl_cnt,
-                                                        int capN, int capK, int capC, unsigned char* gnodes, size_t gnode_stride) {
+                                                        int capN, int capK, int capC, unsigned char* gnodes, size_t gnode_stride,
+                                                        const unsigned char* __restrict__ roottab) {
     extern __shared__ __align__(16) unsigned char oct_smem[];
     const int l = blockIdx.y, slot = blockIdx.x;     // slots fastest: the long level-0 CTAs of all images start first, the short top levels fill the tail
     const LevelGeom& G = P.lv[l];
@@ -178,26 +179,58 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     __syncthreads();
 
     // ---- roots (ORBextractor.cpp:549-584): stable partition by (int)(x / hX) from keys[1] into keys[0] ----
+    // The root of a key comes from a host-built table root_of[x] (the same float division, evaluated once per column), and four
+    // roots are counted / scattered per round with 16-bit counters packed in two ints: one pass + one pair of block scans per
+    // four roots instead of a pass with a float division and a scan per root.
     const int per = (K + OCT_THREADS - 1) / OCT_THREADS;
     const int kb = min(tid * per, K), ke = min(kb + per, K);
+    const unsigned char* rt = roottab + G.root_ofs;
     int nNodes = 0, rootBase = 0;
-    for (int r = 0; r < G.nIni; ++r) {
-        int mine = 0;
-        for (int i = kb; i < ke; ++i) mine += ((int)__fdiv_rn((float)(keys[1][i] & 0xfff), G.hX) == r);
-        int total;
-        int pos = rootBase + block_excl_scan(mine, tmp, &total);
+    // 16-bit counters (4 roots per round) while K < 2^16, else plain 32-bit ones (2 roots per round: the global-scratch path of a
+    // level with more candidates than that)
+    const bool narrow = K < 65536;
+    const int step = narrow ? 4 : 2;
+    for (int r0 = 0; r0 < G.nIni; r0 += step) {
+        int lo = 0, hi = 0;
+        for (int i = kb; i < ke; ++i) {
+            const int r = (int)rt[keys[1][i] & 0xfff] - r0;
+            if ((unsigned)r >= (unsigned)step) continue;
+            if (narrow) { if (r < 2) lo += 1 << (16 * r); else hi += 1 << (16 * (r - 2)); }
+            else { if (r == 0) ++lo; else ++hi; }
+        }
+        int totLo, totHi;
+        const int exLo = block_excl_scan(lo, tmp, &totLo);
+        const int exHi = block_excl_scan(hi, tmp, &totHi);
+        int tot[4], pos[4];
+        if (narrow) {
+            tot[0] = totLo & 0xffff; tot[1] = (int)((unsigned)totLo >> 16); tot[2] = totHi & 0xffff; tot[3] = (int)((unsigned)totHi >> 16);
+            pos[0] = exLo & 0xffff; pos[1] = (int)((unsigned)exLo >> 16); pos[2] = exHi & 0xffff; pos[3] = (int)((unsigned)exHi >> 16);
+        } else {
+            tot[0] = totLo; tot[1] = totHi; tot[2] = tot[3] = 0;
+            pos[0] = exLo; pos[1] = exHi; pos[2] = pos[3] = 0;
+        }
+        pos[0] += rootBase; pos[1] += rootBase + tot[0]; pos[2] += rootBase + tot[0] + tot[1]; pos[3] += rootBase + tot[0] + tot[1] + tot[2];
         for (int i = kb; i < ke; ++i) {
             const u32 key = keys[1][i];
-            if ((int)__fdiv_rn((float)(key & 0xfff), G.hX) == r) keys[0][pos++] = key;
-        }
-        if (total > 0) {
-            if (tid == 0) {
-                boxA[nNodes] = make_short4((short)(int)(G.hX * (float)r), 0, (short)(int)(G.hX * (float)(r + 1)),
-                                           (short)(G.maxBY - ORB_DET_ORIGIN));
-                begA[nNodes] = rootBase; cntA[nNodes] = total; metaA[nNodes] = (total == 1) ? 1 : 0;
+            const int r = (int)rt[key & 0xfff] - r0;
+            if ((unsigned)r < (unsigned)step) {
+                int d;
+                if (r == 0) d = pos[0]++; else if (r == 1) d = pos[1]++; else if (r == 2) d = pos[2]++; else d = pos[3]++;
+                keys[0][d] = key;
             }
-            ++nNodes;
-            rootBase += total;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = r0 + q;
+            if (q < step && r < G.nIni && tot[q] > 0) {
+                if (tid == 0) {
+                    boxA[nNodes] = make_short4((short)(int)(G.hX * (float)r), 0, (short)(int)(G.hX * (float)(r + 1)),
+                                               (short)(G.maxBY - ORB_DET_ORIGIN));
+                    begA[nNodes] = rootBase; cntA[nNodes] = tot[q]; metaA[nNodes] = (tot[q] == 1) ? 1 : 0;
+                }
+                ++nNodes;
+                rootBase += tot[q];
+            }
         }
     }
     __syncthreads();

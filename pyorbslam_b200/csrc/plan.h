@@ -23,6 +23,7 @@ struct LevelGeom {
     int kp_ofs, kp_cap;     // level segment in the slot's level-keypoint array
     int nIni;               // DistributeOctTree root count, ORBextractor.cpp:543
     float hX;               // root width, ORBextractor.cpp:545
+    int root_ofs;           // offset of this level's root_of[x] table (k_octree): (int)((float)x / hX) for x = 0 .. maxBX - 16
     float sf, isf;          // mvScaleFactor / mvInvScaleFactor
     int psize;              // (int)(31 * sf), ORBextractor.cpp:834
     int xtab_ofs, ytab_ofs; // resize tables (level >= 1)

@@ -24,7 +24,7 @@ import cv2  # noqa: E402
 from Frame import Frame  # noqa: E402  (the reference's own class)
 
 from oracle.refext import RefExtractor  # noqa: E402
-from pyorbslam_b200.synthetic import make_stereo_pair, pair_digest  # noqa: E402
+from pyorbslam_b200.synthetic import make_kitti_like_pair, make_stereo_pair, pair_digest  # noqa: E402
 
 
 def sha(*arrays):
@@ -38,8 +38,8 @@ def frame_args(fx, fy, cx, cy, W, H):   # Tracking.py:97-109 with zero distortio
     return [fx, fy, cx, cy, 1.0 / fx, 1.0 / fy, 64.0 / W, 48.0 / H, 0.0, float(W), 0.0, float(H), 48, 64]
 
 
-def stereo_case(name, idx, H, W, params, fx, fy, cx, cy, mbf):
-    L, R = make_stereo_pair(idx, H, W)
+def stereo_case(name, idx, H, W, params, fx, fy, cx, cy, mbf, gen=make_stereo_pair):
+    L, R = gen(idx, H, W)
     eL, eR = RefExtractor(*params), RefExtractor(*params)
     mK = np.eye(3, dtype=np.float32)
     mK[0, 0], mK[1, 1], mK[0, 2], mK[1, 2] = fx, fy, cx, cy
@@ -74,6 +74,8 @@ def main():
     # config 2: KITTI00-02 camera (configs/KITTI00-02.yaml:7-24)
     stereo_case("stereo_kitti_shape.npz", 0, 376, 1241, (2000, 1.2, 8, 20, 7), 718.856, 718.856, 607.1928, 185.2157, 386.1448)
     stereo_case("stereo_small.npz", 7, 240, 640, (1000, 1.2, 6, 20, 7), 500.0, 500.0, 320.0, 120.0, 100.0)
+    # the bench's default scenes (KITTI-like road scene, pyorbslam_b200/synthetic.py:make_kitti_like_pair)
+    stereo_case("stereo_kitti_like.npz", 1000, 376, 1241, (2000, 1.2, 8, 20, 7), 718.856, 718.856, 607.1928, 185.2157, 386.1448, gen=make_kitti_like_pair)
     # config 4 (digests only: the arrays would be ~0.5 MB); input = left view of synthetic pair 4 at 2560x1440
     big, _ = make_stereo_pair(4, 1440, 2560)
     e4 = RefExtractor(8000, 1.2, 12, 20, 7)

@@ -15,7 +15,7 @@ import pytest
 import oracle as O
 from pyorbslam_b200 import ORBextractor, _lib, install
 from pyorbslam_b200.stereo import compute_stereo_matches, stereo_host, stereo_resident
-from pyorbslam_b200.synthetic import make_stereo_pair, pair_digest
+from pyorbslam_b200.synthetic import make_kitti_like_pair, make_stereo_pair, pair_digest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -61,10 +61,11 @@ def test_config1_fixture_image_vs_reference_golden(golden_dir):
         assert t2 == tuples and np.array_equal(d2, desc)
 
 
-@pytest.mark.parametrize("name", ["stereo_kitti_shape.npz", "stereo_small.npz"])
+@pytest.mark.parametrize("name", ["stereo_kitti_shape.npz", "stereo_small.npz", "stereo_kitti_like.npz"])
 def test_config2_stereo_pair_vs_reference_frame_golden(golden_dir, name):
     g = np.load(os.path.join(golden_dir, name))
-    L, R = make_stereo_pair(int(g["idx"]), int(g["H"]), int(g["W"]))
+    gen = make_kitti_like_pair if "kitti_like" in name else make_stereo_pair       # the bench's default scenes / round 1's generator
+    L, R = gen(int(g["idx"]), int(g["H"]), int(g["W"]))
     assert pair_digest(L, R) == str(g["image_digest"])
     p = g["params"]
     params = (int(p[0]), float(p[1]), int(p[2]), int(p[3]), int(p[4]))

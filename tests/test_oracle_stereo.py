@@ -7,19 +7,20 @@ import pytest
 
 import oracle as O
 from oracle import stereo_py
-from pyorbslam_b200.synthetic import make_stereo_pair, pair_digest
+from pyorbslam_b200.synthetic import make_kitti_like_pair, make_stereo_pair, pair_digest
 
 
 def _load(golden_dir, name):
     g = np.load(os.path.join(golden_dir, name))
-    L, R = make_stereo_pair(int(g["idx"]), int(g["H"]), int(g["W"]))
+    gen = make_kitti_like_pair if "kitti_like" in name else make_stereo_pair
+    L, R = gen(int(g["idx"]), int(g["H"]), int(g["W"]))
     assert pair_digest(L, R) == str(g["image_digest"]), "synthetic generator drifted from the fixture"
     p = g["params"]
     params = (int(p[0]), float(p[1]), int(p[2]), int(p[3]), int(p[4]))
     return g, L, R, params
 
 
-@pytest.mark.parametrize("name", ["stereo_kitti_shape.npz", "stereo_small.npz"])
+@pytest.mark.parametrize("name", ["stereo_kitti_shape.npz", "stereo_small.npz", "stereo_kitti_like.npz"])
 def test_c_stereo_bit_exact_vs_reference_frame(golden_dir, name):
     g, L, R, params = _load(golden_dir, name)
     eL, eR = O.OracleExtractor(*params), O.OracleExtractor(*params)
