@@ -307,7 +307,7 @@ __device__ __forceinline__ const u8* view_ptr(const u8* base, const StereoGeom& 
 }
 
 __global__ void __launch_bounds__(ST_WARPS * 32, 8) k_stereo(const __grid_constant__ StereoGeom SG, const StereoArgs A) {
-    __shared__ unsigned char s_win[ST_WARPS][11 * 11 + 11 * 21 + 4];
+    __shared__ __align__(16) unsigned char s_win[ST_WARPS][11 * 12 + 11 * 24 + 4];     // 400 bytes per warp: word-aligned window rows
     const int pair = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nL = A.nL[(size_t)pair * A.n_stride];
     const int iL = blockIdx.x * ST_WARPS + warp;
@@ -364,23 +364,55 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 8) k_stereo(const __grid_consta
                 if (lane == 0) atomicOr(A.status + (size_t)pair * A.status_stride, 1);
             }
             if (ok) {
-                unsigned char* wl = s_win[warp];
-                unsigned char* wr = wl + 121;
+                // Stage the 11 x 11 left and 11 x 21 right windows of the (sheared) pyramid view.  A window row is a run of consecutive
+                // LOGICAL bytes; it is contiguous in the padded buffer too unless it crosses the logical pitch, so lane r (left) /
+                // lane 11 + r (right) fetches its whole row as aligned 32-bit words, funnel-shifts them into place and stores words
+                // (rows padded to 12 / 24 bytes in shared memory); the rare row that does cross is copied byte by byte.
+                unsigned char* wl = s_win[warp];          // [11][12]
+                unsigned char* wr = wl + 11 * 12;          // [11][24]
                 const u8* bl = A.pyrL + (size_t)pair * A.pyr_stride;
                 const u8* br = A.pyrR + (size_t)pair * A.pyr_stride;
-                for (int t = lane; t < 121; t += 32) { const int r = t / 11, cc = t - r * 11; wl[t] = *view_ptr(bl, SG, oL, sv - 5 + r, su - 5 + cc); }
-                for (int t = lane; t < 231; t += 32) { const int r = t / 21, cc = t - r * 21; wr[t] = *view_ptr(br, SG, oL, sv - 5 + r, sr - 10 + cc); }
+                if (lane < 22) {
+                    const bool left = lane < 11;
+                    const int r = left ? lane : lane - 11, n = left ? 11 : 21;
+                    const int lin = SG.off0[oL] + (sv - 5 + r) * SG.vstride[oL] + (left ? su - 5 : sr - 10);
+                    int pr = (int)__umulhi((unsigned)lin, SG.magic[oL]);           // lin / plog via ceil(2^32 / plog); may overshoot by one
+                    if (pr * SG.plog[oL] > lin) --pr;
+                    const int pc = lin - pr * SG.plog[oL];
+                    const u8* src = (left ? bl : br) + SG.base[oL] + (size_t)pr * SG.pitch[oL] + pc;
+                    unsigned char* dst = left ? wl + r * 12 : wr + r * 24;
+                    if (pc + n <= SG.plog[oL] || SG.pitch[oL] == SG.plog[oL]) {
+                        const size_t addr = reinterpret_cast<size_t>(src);
+                        const u32* wp = reinterpret_cast<const u32*>(addr & ~(size_t)3);
+                        const int sh = 8 * (int)(addr & 3);
+                        u32* dw = reinterpret_cast<u32*>(dst);
+                        u32 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+                        dw[0] = __funnelshift_r(w0, w1, sh); dw[1] = __funnelshift_r(w1, w2, sh); dw[2] = __funnelshift_r(w2, w3, sh);
+                        if (!left) {
+                            w0 = wp[4]; w1 = wp[5]; w2 = wp[6];
+                            dw[3] = __funnelshift_r(w3, w0, sh); dw[4] = __funnelshift_r(w0, w1, sh); dw[5] = __funnelshift_r(w1, w2, sh);
+                        }
+                    } else {
+                        const int wrap = SG.pitch[oL] - SG.plog[oL];
+                        for (int k = 0; k < n; ++k) dst[k] = src[k + (pc + k >= SG.plog[oL] ? wrap : 0)];
+                    }
+                }
                 __syncwarp();
-                const int lc = wl[5 * 11 + 5];
+                const int lc = wl[5 * 12 + 5];
+                // SAD of the centre-subtracted patches for the 11 shifts: |(L - Lc) - (R - Rc_inc)| = |(L - Lc + Rc_inc) - R|, one
+                // add and one absolute-difference-accumulate per (pixel, shift)
+                int rc[11];
+#pragma unroll
+                for (int inc = 0; inc < 11; ++inc) rc[inc] = (int)wr[5 * 24 + inc + 5] - lc;
                 int dist[11];
 #pragma unroll
                 for (int inc = 0; inc < 11; ++inc) dist[inc] = 0;
                 for (int t = lane; t < 121; t += 32) {        // this lane's pixels; all 11 shifts per pixel
                     const int r = t / 11, cc = t - r * 11;
-                    const int lv = wl[t] - lc;
-                    const unsigned char* rp = wr + r * 21 + cc;
+                    const int lv = wl[r * 12 + cc];
+                    const unsigned char* rp = wr + r * 24 + cc;
 #pragma unroll
-                    for (int inc = 0; inc < 11; ++inc) dist[inc] += abs(lv - (rp[inc] - wr[5 * 21 + inc + 5]));
+                    for (int inc = 0; inc < 11; ++inc) dist[inc] = (int)__sad(lv + rc[inc], (int)rp[inc], (unsigned)dist[inc]);
                 }
 #pragma unroll
                 for (int inc = 0; inc < 11; ++inc) {
