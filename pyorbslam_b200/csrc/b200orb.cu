@@ -95,6 +95,7 @@ struct HostPlan {
     int rs_gA_lo[ORB_MAX_LEVELS] = {0}, rs_gA_n[ORB_MAX_LEVELS] = {0}, rs_gB_n[ORB_MAX_LEVELS] = {0};   // k_resize: interior / border column groups
     int fast_SP = 0, fast_SR = 0, fast_TP = 0, fast_TR = 0, fast_LC = 0, fast_RQ = 0, fast_cells = 0, fast_WS = 0;
     LevelMaps maps;               // TMA tensor maps of the pyramid levels (k_fast_cells), rebuilt by Engine::plan
+    LevelMaps bmaps;              // ... and of the blurred levels (k_describe: 64 x 37 boxes)
     size_t fast_smem = 0;
     int oct_capN = 0, oct_capK = 0, oct_capC = 0;
     size_t oct_smem = 0, oct_node_stride = 0;
@@ -319,16 +320,28 @@ struct Engine {
         }
         const Plan& P = hp.P;
         memset(&hp.maps, 0, sizeof(hp.maps));
+        memset(&hp.bmaps, 0, sizeof(hp.bmaps));
         for (int l = 0; l < P.nlevels; ++l) {
             const LevelGeom& G = P.lv[l];
-            const cuuint64_t dims[3] = {(cuuint64_t)G.pitch, (cuuint64_t)G.rows, (cuuint64_t)S};
-            const cuuint64_t strides[2] = {(cuuint64_t)G.pitch, (cuuint64_t)P.pyr_bytes};      // bytes, dimensions 1 and 2
-            const cuuint32_t box[3] = {(cuuint32_t)hp.fast_SP, (cuuint32_t)hp.fast_SR, 1u};
             const cuuint32_t estr[3] = {1u, 1u, 1u};
-            const CUresult r = encode(&hp.maps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + G.pyr_ofs, dims, strides, box, estr,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return fail(B200ORB_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+            {   // bordered raw level, box = FAST window
+                const cuuint64_t dims[3] = {(cuuint64_t)G.pitch, (cuuint64_t)G.rows, (cuuint64_t)S};
+                const cuuint64_t strides[2] = {(cuuint64_t)G.pitch, (cuuint64_t)P.pyr_bytes};      // bytes, dimensions 1 and 2
+                const cuuint32_t box[3] = {(cuuint32_t)hp.fast_SP, (cuuint32_t)hp.fast_SR, 1u};
+                const CUresult r = encode(&hp.maps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + G.pyr_ofs, dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return fail(B200ORB_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+            }
+            {   // blurred level (dense rows), box = the descriptor's 37-row sample window
+                const cuuint64_t dims[3] = {(cuuint64_t)G.blur_pitch, (cuuint64_t)G.h, (cuuint64_t)S};
+                const cuuint64_t strides[2] = {(cuuint64_t)G.blur_pitch, (cuuint64_t)P.blur_bytes};
+                const cuuint32_t box[3] = {(cuuint32_t)DESC_PP, 37u, 1u};
+                const CUresult r = encode(&hp.bmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_blur + G.blur_ofs, dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return fail(B200ORB_E_CUDA, "cuTensorMapEncodeTiled (blur) failed with CUresult " + std::to_string((int)r));
+            }
         }
         return 0;
     }
@@ -442,7 +455,7 @@ struct Engine {
         ++g_launches;
         if (evs) cudaEventRecord(evs[5], st);
         if (fork) CU_TRY(cudaStreamWaitEvent(st, ev_join, 0));
-        k_describe<<<dim3((P.kp_total + DESC_WARPS * DESC_KPW - 1) / (DESC_WARPS * DESC_KPW), n), DESC_WARPS * 32, 0, st>>>(P, d_pyr, d_blur, d_lvlkp, d_lvlcnt, d_mtab,
+        k_describe<<<dim3((P.kp_total + DESC_WARPS * DESC_KPW - 1) / (DESC_WARPS * DESC_KPW), n), DESC_WARPS * 32, 0, st>>>(P, hp.bmaps, d_pyr, d_lvlkp, d_lvlcnt, d_mtab,
                                                                                                     d_fpat, d_kps, d_desc, d_nkp);
         ++g_launches;
         if (evs) cudaEventRecord(evs[6], st);

@@ -76,14 +76,15 @@ __device__ __forceinline__ void glibc_sincosf(float y, float* sp, float* cp) {
 // ------------------------------------------------------------------------------------------------
 #define DESC_WARPS 8
 #define DESC_KPW 8     // keypoints per warp
-#define DESC_PP 40     // pitch of the staged descriptor window (37 columns + alignment slack)
+#define DESC_PP 64     // pitch of the staged descriptor window = width of its TMA box (37 columns + up to 15 bytes of alignment shift)
+#define DESC_WIN (19 * 128)   // bytes per warp: 37 rows x 64, rounded up to the 128-byte alignment a TMA destination needs
 __device__ __forceinline__ int dp4a_us(u32 a_u8x4, u32 b_s8x4, int c) {     // unsigned bytes x signed bytes
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
     return d;
 }
-__global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
-                                                              const u8* __restrict__ blur, const u32* __restrict__ lvl_kp,
+__global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_constant__ Plan P, const __grid_constant__ LevelMaps BM,
+                                                              const u8* __restrict__ pyr, const u32* __restrict__ lvl_kp,
                                                               const int* __restrict__ lvl_cnt, const uint2* __restrict__ mtab,
                                                               const float4* __restrict__ fpat, float* __restrict__ kps,
                                                               u8* __restrict__ desc, int* __restrict__ nkp) {
@@ -91,7 +92,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_co
     // the moment table goes to shared memory once per CTA, the float pattern into registers once per warp; every warp then
     // walks DESC_KPW consecutive keypoints
     __shared__ uint2 s_mtab[4 * MOM_STEPS * 32];
-    __shared__ u32 s_patch[DESC_WARPS * 37 * (DESC_PP / 4)];    // per warp: 37 rows x DESC_PP bytes of the blurred level
+    __shared__ __align__(128) u8 s_patch[DESC_WARPS * DESC_WIN];   // per warp: 37 rows x DESC_PP bytes of the blurred level (one TMA box)
+    __shared__ unsigned long long s_bar[DESC_WARPS];
     for (int k = threadIdx.x; k < 4 * MOM_STEPS * 32; k += DESC_WARPS * 32) s_mtab[k] = __ldg(mtab + k);
     __shared__ float4 s_fpat[256];
     for (int k = threadIdx.x; k < 256; k += DESC_WARPS * 32) s_fpat[k] = __ldg(fpat + k);
@@ -106,6 +108,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_co
     if (blockIdx.x == 0 && threadIdx.x == 0) nkp[slot] = total;
     __syncthreads();
     const int i0 = (blockIdx.x * DESC_WARPS + (threadIdx.x >> 5)) * DESC_KPW;
+    u8* const win = s_patch + (threadIdx.x >> 5) * DESC_WIN;
+    unsigned long long* const bar = &s_bar[threadIdx.x >> 5];
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    const CUtensorMap* const bmaps = BM.m;
+    u32 parity = 0;
     for (int i = i0; i < min(i0 + DESC_KPW, total); ++i) {
     const int l = __popc(__ballot_sync(0xffffffffu, lane < P.nlevels && i >= lend));
     const int off = __shfl_sync(0xffffffffu, lend, max(l - 1, 0)) & (l ? -1 : 0);
@@ -113,11 +121,14 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_co
     const u32 packed = lvl_kp[(size_t)slot * P.kp_total + G.kp_ofs + (i - off)];
     const int x = packed & 0xfff, y = (packed >> 12) & 0xfff, resp = packed >> 24;
 
-    // the descriptor stage below reads a 37-row window of the blurred level: ask for its lines now, the orientation work hides the latency
-    {
-        const u8* w0 = blur + (size_t)slot * P.blur_bytes + G.blur_ofs + ((ptrdiff_t)y - 18) * G.blur_pitch + (x - 18);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(w0 + (ptrdiff_t)lane * G.blur_pitch + 18));
-        if (lane < 5) asm volatile("prefetch.global.L1 [%0];" ::"l"(w0 + (ptrdiff_t)(lane + 32) * G.blur_pitch + 18));
+    // The descriptor stage below samples a 37 x 37 window of the blurred level: one TMA box copy (64 x 37 bytes from the 16-byte
+    // boundary below the window's left edge; rows / columns outside the level are zero-filled and never sampled) is issued now and
+    // lands in the warp's buffer while the orientation is computed -- no load / store instructions are spent on the staging.
+    const int wx0 = (x - 18) & ~15, wshift = (x - 18) - wx0;
+    __syncwarp();                                               // the previous keypoint's samples are done
+    if (lane == 0) {
+        mbar_expect_tx(bar, (u32)(DESC_PP * 37));
+        tma_box_g2s(win, bmaps + l, wx0, y - 18, slot, bar);
     }
     // ---- orientation ----
     const u8* c = pyr + (size_t)slot * P.pyr_bytes + G.pyr_ofs + (size_t)(y + ORB_EDGE) * G.pitch + (x + ORB_EDGE);
@@ -154,30 +165,16 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_co
     glibc_sincosf(angle * factorPI, &b, &a);
     // Sample coordinates: cvRound(x * b + y * a) rows, cvRound(x * a - y * b) columns (ORBextractor.cpp:117-120, products and sums
     // rounded separately: --fmad=false); |coordinate| <= 18 (the pattern's largest radius is 18.38).
-    // The 37 x 37 window of the blurred level around the keypoint is staged in shared memory first (aligned words, 3 rows x 10
-    // words per step): read straight from global memory the 16 samples of a lane hit ~25 different cache lines per warp
-    // instruction and the L1 tag stage becomes the bound of the kernel.
+    // The samples come from the window the TMA unit staged in shared memory: read straight from global memory the 16 samples of a
+    // lane hit ~25 different cache lines per warp instruction and the L1 tag stage becomes the bound of the kernel.
     // Rounding to nearest-even is done by adding 1.5 * 2^23 (FADD, exact for |v| < 2^22) instead of a float->int conversion: the
     // integer then sits in the low mantissa bits, biased by K = 0x4B400000, and the shared-memory byte address
     // rbits * DESC_PP + cbits + D (mod 2^32) absorbs the bias in the per-keypoint constant D.
-    const u8* bc = blur + (size_t)slot * P.blur_bytes + G.blur_ofs + (size_t)y * G.blur_pitch + x;
-    u32 D;
-    {
-        const u8* a0 = bc - 18 * (ptrdiff_t)G.blur_pitch - 18;                 // window corner (-18, -18)
-        const int al2 = (int)(reinterpret_cast<size_t>(a0) & 3);
-        const int rs = (lane * 205) >> 11, wi = lane - 10 * rs;                 // lane / 10, lane % 10
-        const u32* src = reinterpret_cast<const u32*>(a0 - al2) + (ptrdiff_t)rs * (G.blur_pitch >> 2) + wi;
-        const ptrdiff_t step = 3 * (G.blur_pitch >> 2);
-        u32* dstw = s_patch + (threadIdx.x >> 5) * (37 * (DESC_PP / 4)) + rs * (DESC_PP / 4) + wi;
-        __syncwarp();                                                           // the previous keypoint's samples are done
-#pragma unroll
-        for (int s = 0; s < 13; ++s, src += step, dstw += 3 * (DESC_PP / 4))
-            if (lane < 30 && 3 * s + rs < 37) *dstw = *src;
-        __syncwarp();
-        D = (u32)(18 * DESC_PP + 18 + al2) - 0x4B400000u * (u32)(DESC_PP + 1);
-    }
+    const u32 D = (u32)(18 * DESC_PP + 18 + wshift) - 0x4B400000u * (u32)(DESC_PP + 1);
+    mbar_wait(bar, parity);
+    parity ^= 1u;
     const float RN = 12582912.f;
-    const u8* sp = reinterpret_cast<const u8*>(s_patch + (threadIdx.x >> 5) * (37 * (DESC_PP / 4)));
+    const u8* sp = win;
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
