@@ -518,14 +518,29 @@ int launch_stereo(const StereoGeom& SG, StereoArgs A, int max_left, int pairs, c
 // ================================================================================================
 struct b200orb_extractor {
     Engine eng;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st_pyr = nullptr;    // st: the launch sequence; st_pyr: background download of the pyramid (GetImagePyramid)
+    cudaEvent_t ev_done = nullptr, ev_pyr = nullptr;
     u8* d_img = nullptr; size_t img_cap = 0;
-    float* d_kps = nullptr; u8* d_desc = nullptr; int* d_nkp = nullptr;
-    float *d_uR = nullptr, *d_depth = nullptr; int *d_match = nullptr, *d_sad = nullptr;
+    // results of the last call in ONE device block [nkp, pad to 256 B | kps C x 24, pad to 256 B | desc C x 32] so that one copy brings them back
+    u8* d_out = nullptr; u8* h_out = nullptr;        // device block / its pinned host mirror
+    float* d_kps = nullptr; u8* d_desc = nullptr; int* d_nkp = nullptr;       // views into d_out
+    // stereo outputs likewise: [uRight C | depth C | matchIdx C | sadDist C | status]
+    u8* d_sout = nullptr; u8* h_sout = nullptr;
+    float *d_uR = nullptr, *d_depth = nullptr; int *d_match = nullptr, *d_sad = nullptr, *d_sstatus = nullptr;
     int out_cap = 0;
-    u8* h_stage = nullptr; size_t stage_cap = 0;   // pinned staging for GetImagePyramid
+    u8* h_img = nullptr; size_t h_img_cap = 0;       // pinned upload staging
+    u8* h_pyr = nullptr; size_t h_pyr_cap = 0;       // pinned mirror of the pyramid blob (physical layout)
+    bool pyr_inflight = false, pyr_valid = false;
+    // the launch sequence of one image (upload, 8 pyramid kernels, blur, FAST, octree, describe, result download) as a CUDA graph,
+    // captured once per image size: one cudaGraphLaunch instead of ~17 stream operations
+    cudaGraphExec_t graph = nullptr;
+    int graph_H = 0, graph_W = 0;
+    long long graph_kernels = 0;     // kernels one graph launch runs (for b200orb_kernel_launches)
+    int use_graph = -1;          // -1: read B200ORB_GRAPH (default 1)
+    int prefetch_pyramid = 1;    // start the pyramid download behind the results (Frame.__init__ always asks for it, Frame.py:59-60)
     int n = -1;          // keypoints of the last call, -1 = none yet
     bool empty_last = false;
+    void drop_graph() { if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; } }
 };
 
 struct b200orb_vocab {
@@ -584,11 +599,19 @@ void b200orb_extractor_destroy(b200orb_extractor* e) {
     if (!e) return;
     if (e->st || e->d_img || e->eng.planned) {
         cudaSetDevice(e->eng.device);
+        if (e->st) cudaStreamSynchronize(e->st);
+        if (e->st_pyr) cudaStreamSynchronize(e->st_pyr);
+        e->drop_graph();
         e->eng.release();
-        cudaFree(e->d_img); cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_nkp);
-        cudaFree(e->d_uR); cudaFree(e->d_depth); cudaFree(e->d_match); cudaFree(e->d_sad);
+        cudaFree(e->d_img); cudaFree(e->d_out); cudaFree(e->d_sout);
+        if (e->h_out) cudaFreeHost(e->h_out);
+        if (e->h_sout) cudaFreeHost(e->h_sout);
+        if (e->h_img) cudaFreeHost(e->h_img);
+        if (e->h_pyr) cudaFreeHost(e->h_pyr);
+        if (e->ev_done) cudaEventDestroy(e->ev_done);
+        if (e->ev_pyr) cudaEventDestroy(e->ev_pyr);
         if (e->st) cudaStreamDestroy(e->st);
-        if (e->h_stage) cudaFreeHost(e->h_stage);
+        if (e->st_pyr) cudaStreamDestroy(e->st_pyr);
     }
     delete e;
 }
@@ -606,6 +629,9 @@ int b200orb_get_features_per_level(const b200orb_extractor* e, int* out) {
     return 0;
 }
 
+static size_t out_desc_ofs(int C) { return 256 + (((size_t)C * 24 + 255) & ~(size_t)255); }     // descriptors are read as 16-byte vectors
+static size_t out_block_bytes(int C) { return out_desc_ofs(C) + (size_t)C * 32; }
+
 int b200orb_extract(b200orb_extractor* e, const uint8_t* image, int H, int W, int* n_keypoints) {
     if (!e || !n_keypoints) return fail(B200ORB_E_ARG, "NULL argument");
     if (H == 0 || W == 0 || !image) {       // ORBextractor.cpp:1045-1046: empty image -> nothing happens
@@ -614,44 +640,99 @@ int b200orb_extract(b200orb_extractor* e, const uint8_t* image, int H, int W, in
     }
     if (H < 0 || W < 0) return fail(B200ORB_E_ARG, "negative image size");
     CU_TRY(cudaSetDevice(e->eng.device));
-    if (!e->st) CU_TRY(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    if (!e->st) {
+        CU_TRY(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&e->st_pyr, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&e->ev_pyr, cudaEventDisableTiming));
+    }
+    if (e->use_graph < 0) { const char* v = getenv("B200ORB_GRAPH"); e->use_graph = v ? atoi(v) : 1; }
+    if (e->pyr_inflight) {                  // the previous call's pyramid download reads the blob the new call overwrites
+        CU_TRY(cudaStreamSynchronize(e->st_pyr));
+        e->pyr_inflight = false;
+    }
+    e->pyr_valid = false;
+    const bool replanned = !(e->eng.planned && e->eng.hp.P.H == H && e->eng.hp.P.W == W);
     TRY(e->eng.plan(H, W, 1));
     const Plan& P = e->eng.hp.P;
-    if ((size_t)H * W > e->img_cap) {
-        cudaFree(e->d_img);
-        e->d_img = nullptr;
-        CU_TRY(cudaMalloc((void**)&e->d_img, (size_t)H * W));
-        e->img_cap = (size_t)H * W;
+    const size_t HW = (size_t)H * W;
+    if (replanned || HW > e->img_cap || e->out_cap != P.kp_total) e->drop_graph();     // the graph holds the old buffers' addresses
+    if (HW > e->img_cap) {
+        cudaFree(e->d_img); e->d_img = nullptr;
+        if (e->h_img) cudaFreeHost(e->h_img);
+        e->h_img = nullptr;
+        CU_TRY(cudaMalloc((void**)&e->d_img, HW));
+        CU_TRY(cudaHostAlloc((void**)&e->h_img, HW, cudaHostAllocDefault));
+        e->img_cap = HW; e->h_img_cap = HW;
     }
     if (e->out_cap != P.kp_total) {
-        cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_nkp); cudaFree(e->d_uR); cudaFree(e->d_depth); cudaFree(e->d_match); cudaFree(e->d_sad);
-        e->d_kps = nullptr; e->d_desc = nullptr; e->d_nkp = nullptr; e->d_uR = e->d_depth = nullptr; e->d_match = nullptr; e->d_sad = nullptr;
-        CU_TRY(cudaMalloc((void**)&e->d_kps, (size_t)P.kp_total * 6 * 4));
-        CU_TRY(cudaMalloc((void**)&e->d_desc, (size_t)P.kp_total * 32));
-        CU_TRY(cudaMalloc((void**)&e->d_nkp, 4));
-        CU_TRY(cudaMalloc((void**)&e->d_uR, (size_t)P.kp_total * 4));
-        CU_TRY(cudaMalloc((void**)&e->d_depth, (size_t)P.kp_total * 4));
-        CU_TRY(cudaMalloc((void**)&e->d_match, (size_t)P.kp_total * 4));
-        CU_TRY(cudaMalloc((void**)&e->d_sad, (size_t)P.kp_total * 4));
-        e->out_cap = P.kp_total;
+        const int C = P.kp_total;
+        cudaFree(e->d_out); cudaFree(e->d_sout);
+        if (e->h_out) cudaFreeHost(e->h_out);
+        if (e->h_sout) cudaFreeHost(e->h_sout);
+        e->d_out = e->d_sout = nullptr; e->h_out = e->h_sout = nullptr; e->out_cap = 0;
+        CU_TRY(cudaMalloc((void**)&e->d_out, out_block_bytes(C)));
+        CU_TRY(cudaHostAlloc((void**)&e->h_out, out_block_bytes(C), cudaHostAllocDefault));
+        CU_TRY(cudaMalloc((void**)&e->d_sout, (size_t)C * 16 + 16));
+        CU_TRY(cudaHostAlloc((void**)&e->h_sout, (size_t)C * 16 + 16, cudaHostAllocDefault));
+        e->d_nkp = (int*)e->d_out; e->d_kps = (float*)(e->d_out + 256); e->d_desc = e->d_out + out_desc_ofs(C);
+        e->d_uR = (float*)e->d_sout; e->d_depth = e->d_uR + C; e->d_match = (int*)(e->d_depth + C); e->d_sad = e->d_match + C;
+        e->d_sstatus = e->d_sad + C;
+        e->out_cap = C;
     }
-    CU_TRY(cudaMemcpyAsync(e->d_img, image, (size_t)H * W, cudaMemcpyHostToDevice, e->st));
-    TRY(e->eng.extract(e->d_img, e->d_img, 1, 1, e->d_kps, e->d_desc, e->d_nkp, e->st));
-    int n = 0;
-    CU_TRY(cudaMemcpyAsync(&n, e->d_nkp, 4, cudaMemcpyDeviceToHost, e->st));
-    CU_TRY(cudaStreamSynchronize(e->st));
-    e->n = n; e->empty_last = false;
-    *n_keypoints = n;
+    if ((size_t)P.pyr_bytes > e->h_pyr_cap) {
+        if (e->h_pyr) cudaFreeHost(e->h_pyr);
+        e->h_pyr = nullptr; e->h_pyr_cap = 0;
+        CU_TRY(cudaHostAlloc((void**)&e->h_pyr, (size_t)P.pyr_bytes, cudaHostAllocDefault));
+        e->h_pyr_cap = (size_t)P.pyr_bytes;
+    }
+    memcpy(e->h_img, image, HW);            // the caller's array is pageable; one host copy into the pinned staging buffer
+    auto enqueue = [&]() -> int {
+        CU_TRY(cudaMemcpyAsync(e->d_img, e->h_img, HW, cudaMemcpyHostToDevice, e->st));
+        TRY(e->eng.extract(e->d_img, e->d_img, 1, 1, e->d_kps, e->d_desc, e->d_nkp, e->st));
+        CU_TRY(cudaMemcpyAsync(e->h_out, e->d_out, out_block_bytes(P.kp_total), cudaMemcpyDeviceToHost, e->st));
+        return 0;
+    };
+    if (e->use_graph) {
+        if (!e->graph) {
+            cudaGraph_t g = nullptr;
+            const long long before = g_launches.load();
+            CU_TRY(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue();
+            e->graph_kernels = g_launches.load() - before;
+            g_launches -= e->graph_kernels;          // counted per launch of the graph below
+            const cudaError_t ce = cudaStreamEndCapture(e->st, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (ce != cudaSuccess) return fail(B200ORB_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+            const cudaError_t ie = cudaGraphInstantiate(&e->graph, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { e->graph = nullptr; return fail(B200ORB_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+            e->graph_H = H; e->graph_W = W;
+        }
+        CU_TRY(cudaGraphLaunch(e->graph, e->st));
+        g_launches += e->graph_kernels;
+    } else {
+        TRY(enqueue());
+    }
+    CU_TRY(cudaEventRecord(e->ev_done, e->st));
+    if (e->prefetch_pyramid) {              // the pyramid follows on its own stream while the caller already works on the keypoints
+        CU_TRY(cudaStreamWaitEvent(e->st_pyr, e->ev_done, 0));
+        CU_TRY(cudaMemcpyAsync(e->h_pyr, e->eng.d_pyr, (size_t)P.pyr_bytes, cudaMemcpyDeviceToHost, e->st_pyr));
+        e->pyr_inflight = true;
+    }
+    CU_TRY(cudaEventSynchronize(e->ev_done));
+    e->n = *reinterpret_cast<const int*>(e->h_out);
+    e->empty_last = false;
+    *n_keypoints = e->n;
     return 0;
 }
 
 int b200orb_get_results(b200orb_extractor* e, float* kps, uint8_t* desc) {
     if (!e || e->n < 0) return fail(B200ORB_E_STATE, "no extract() call yet");
     if (e->n == 0) return 0;
-    CU_TRY(cudaSetDevice(e->eng.device));
-    if (kps) CU_TRY(cudaMemcpyAsync(kps, e->d_kps, (size_t)e->n * 24, cudaMemcpyDeviceToHost, e->st));
-    if (desc) CU_TRY(cudaMemcpyAsync(desc, e->d_desc, (size_t)e->n * 32, cudaMemcpyDeviceToHost, e->st));
-    CU_TRY(cudaStreamSynchronize(e->st));
+    // the results already sit in the pinned mirror (one copy at the end of the launch sequence)
+    if (kps) memcpy(kps, e->h_out + 256, (size_t)e->n * 24);
+    if (desc) memcpy(desc, e->h_out + out_desc_ofs(e->out_cap), (size_t)e->n * 32);
     return 0;
 }
 
@@ -669,50 +750,52 @@ int b200orb_level_size(const b200orb_extractor* e, int level, int* w, int* h) {
     return 0;
 }
 
+// host mirror of the pyramid blob (physical layout) of the last extract; downloaded once, in the background when prefetch is on
+static int fetch_pyramid(b200orb_extractor* e) {
+    if (e->pyr_valid) return 0;
+    CU_TRY(cudaSetDevice(e->eng.device));
+    if (!e->pyr_inflight) {
+        CU_TRY(cudaMemcpyAsync(e->h_pyr, e->eng.d_pyr, (size_t)e->eng.hp.P.pyr_bytes, cudaMemcpyDeviceToHost, e->st_pyr));
+    }
+    CU_TRY(cudaStreamSynchronize(e->st_pyr));
+    e->pyr_inflight = false;
+    e->pyr_valid = true;
+    return 0;
+}
+// the caster's step-ignoring copy (opencv_type_casters.h:230-239): rows*cols contiguous LOGICAL bytes from the ROI start of the
+// (w + 38)-pitch bordered buffer; the mirror has the padded physical pitch, so the run is gathered row by row
+static void sheared_view(const b200orb_extractor* e, int level, uint8_t* out) {
+    const LevelGeom& G = e->eng.hp.P.lv[level];
+    const int plog = G.w + 2 * ORB_EDGE;
+    const u8* base = e->h_pyr + G.pyr_ofs;
+    size_t lin = (size_t)ORB_EDGE * plog + ORB_EDGE, left = (size_t)G.w * G.h;
+    while (left) {
+        const size_t pr = lin / plog, pc = lin - pr * plog, n = std::min(left, (size_t)plog - pc);
+        memcpy(out, base + pr * G.pitch + pc, n);
+        out += n; lin += n; left -= n;
+    }
+}
+
 int b200orb_get_pyramid_level(b200orb_extractor* e, int level, uint8_t* out) {
     TRY(need_pyramid(e, level));
     if (!out) return fail(B200ORB_E_ARG, "out is NULL");
-    CU_TRY(cudaSetDevice(e->eng.device));
-    const LevelGeom& G = e->eng.hp.P.lv[level];
-    const int plog = G.w + 2 * ORB_EDGE;
-    std::vector<u8> tmp((size_t)plog * G.rows);
-    CU_TRY(cudaMemcpy2DAsync(tmp.data(), plog, e->eng.d_pyr + G.pyr_ofs, G.pitch, plog, G.rows, cudaMemcpyDeviceToHost, e->st));
-    CU_TRY(cudaStreamSynchronize(e->st));
-    // the caster's step-ignoring copy: rows*cols contiguous bytes from the ROI start (opencv_type_casters.h:230-239)
-    memcpy(out, tmp.data() + (size_t)ORB_EDGE * plog + ORB_EDGE, (size_t)G.w * G.h);
+    TRY(fetch_pyramid(e));
+    sheared_view(e, level, out);
     return 0;
 }
 
 int b200orb_get_pyramid_all(b200orb_extractor* e, uint8_t* out, long long cap) {
     TRY(need_pyramid(e, 0));
     if (!out) return fail(B200ORB_E_ARG, "out is NULL");
-    CU_TRY(cudaSetDevice(e->eng.device));
     const Plan& P = e->eng.hp.P;
-    size_t need = 0, total = 0;
-    for (int l = 0; l < P.nlevels; ++l) { need += (size_t)(P.lv[l].w + 2 * ORB_EDGE) * P.lv[l].rows; total += (size_t)P.lv[l].w * P.lv[l].h; }
+    size_t total = 0;
+    for (int l = 0; l < P.nlevels; ++l) total += (size_t)P.lv[l].w * P.lv[l].h;
     if ((long long)total > cap) return fail(B200ORB_E_ARG, "output buffer too small for the pyramid views");
-    if (need > e->stage_cap) {
-        if (e->h_stage) cudaFreeHost(e->h_stage);
-        e->h_stage = nullptr; e->stage_cap = 0;
-        CU_TRY(cudaHostAlloc((void**)&e->h_stage, need, cudaHostAllocDefault));
-        e->stage_cap = need;
-    }
-    size_t off = 0;
-    for (int l = 0; l < P.nlevels; ++l) {     // all levels in flight, one synchronisation
-        const LevelGeom& G = P.lv[l];
-        const int plog = G.w + 2 * ORB_EDGE;
-        CU_TRY(cudaMemcpy2DAsync(e->h_stage + off, plog, e->eng.d_pyr + G.pyr_ofs, G.pitch, plog, G.rows, cudaMemcpyDeviceToHost, e->st));
-        off += (size_t)plog * G.rows;
-    }
-    CU_TRY(cudaStreamSynchronize(e->st));
-    off = 0;
+    TRY(fetch_pyramid(e));
     size_t o = 0;
-    for (int l = 0; l < P.nlevels; ++l) {     // the caster's step-ignoring copy (opencv_type_casters.h:230-239), level by level
-        const LevelGeom& G = P.lv[l];
-        const int plog = G.w + 2 * ORB_EDGE;
-        memcpy(out + o, e->h_stage + off + (size_t)ORB_EDGE * plog + ORB_EDGE, (size_t)G.w * G.h);
-        o += (size_t)G.w * G.h;
-        off += (size_t)plog * G.rows;
+    for (int l = 0; l < P.nlevels; ++l) {
+        sheared_view(e, l, out + o);
+        o += (size_t)P.lv[l].w * P.lv[l].h;
     }
     return 0;
 }
@@ -781,18 +864,20 @@ int b200orb_stereo_ex(b200orb_extractor* L, b200orb_extractor* R, double mbf, fl
     A.kpsR = R->d_kps; A.descR = R->d_desc; A.nR = R->d_nkp;
     A.pyrL = L->eng.d_pyr; A.pyrR = R->eng.d_pyr;
     A.kp_row = 6; A.oct_idx = 5; A.out_stride = PL.kp_total;
-    A.uRight = L->d_uR; A.depth = L->d_depth; A.matchIdx = L->d_match; A.status = L->eng.d_status; A.sadDist = L->d_sad;
+    A.uRight = L->d_uR; A.depth = L->d_depth; A.matchIdx = L->d_match; A.status = L->d_sstatus; A.sadDist = L->d_sad;
     A.rowStart = L->eng.d_rowstart; A.rmeta = L->eng.d_rmeta; A.idx_stride = PL.kp_total;
     fill_stereo_consts(A, mbf, fx);
-    CU_TRY(cudaMemsetAsync(L->eng.d_status, 0, 4, L->st));
+    const size_t C = (size_t)PL.kp_total;
+    CU_TRY(cudaMemsetAsync(L->d_sstatus, 0, 4, L->st));
     TRY(launch_stereo(SG, A, L->n, 1, L->st, flags));
-    int status = 0;
-    CU_TRY(cudaMemcpyAsync(uRight, L->d_uR, (size_t)L->n * 4, cudaMemcpyDeviceToHost, L->st));
-    CU_TRY(cudaMemcpyAsync(depth, L->d_depth, (size_t)L->n * 4, cudaMemcpyDeviceToHost, L->st));
-    if (matchIdx) CU_TRY(cudaMemcpyAsync(matchIdx, L->d_match, (size_t)L->n * 4, cudaMemcpyDeviceToHost, L->st));
-    if (sadDist) CU_TRY(cudaMemcpyAsync(sadDist, L->d_sad, (size_t)L->n * 4, cudaMemcpyDeviceToHost, L->st));
-    CU_TRY(cudaMemcpyAsync(&status, L->eng.d_status, 4, cudaMemcpyDeviceToHost, L->st));
+    CU_TRY(cudaMemcpyAsync(L->h_sout, L->d_sout, C * 16 + 16, cudaMemcpyDeviceToHost, L->st));     // all four arrays + the status word
     CU_TRY(cudaStreamSynchronize(L->st));
+    const size_t nb = (size_t)L->n * 4;
+    memcpy(uRight, L->h_sout, nb);
+    memcpy(depth, L->h_sout + C * 4, nb);
+    if (matchIdx) memcpy(matchIdx, L->h_sout + C * 8, nb);
+    if (sadDist) memcpy(sadDist, L->h_sout + C * 12, nb);
+    const int status = *reinterpret_cast<const int*>(L->h_sout + C * 16);
     if (status) return fail(B200ORB_E_RANGE, "a SAD window leaves the pyramid view (the reference raises IndexError/ValueError here)");
     return 0;
 }
