@@ -359,7 +359,7 @@ struct Engine {
         TRY(alloc(&d_lvlkp, (size_t)S * P.kp_total));
         TRY(alloc(&d_cellcnt, (size_t)S * P.ncells));
         TRY(alloc(&d_lvlcnt, (size_t)S * P.nlevels));
-        TRY(alloc(&d_status, (size_t)std::max(S, 1)));     // one range-error flag word per pair (batch API) / one in all (extractor)
+        TRY(alloc(&d_status, (size_t)2 * std::max(S, 1)));     // one range-error flag word per pair, two banks (run_host alternates them per chunk)
         TRY(alloc(&d_rowstart, (size_t)S * (P.lv[0].h + 1)));
         TRY(alloc(&d_rmeta, (size_t)S * P.kp_total));
         if (hp.oct_global_nodes) TRY(alloc(&d_octnodes, (size_t)S * P.nlevels * hp.oct_node_stride));
@@ -373,7 +373,7 @@ struct Engine {
         TRY(alloc(&d_ytab, hp.ytab.size()));
         CU_TRY(cudaMemset(d_pyr, 0, (size_t)S * P.pyr_bytes));
         CU_TRY(cudaMemset(d_blur, 0, (size_t)S * P.blur_bytes));
-        CU_TRY(cudaMemset(d_status, 0, sizeof(int) * (size_t)std::max(S, 1)));
+        CU_TRY(cudaMemset(d_status, 0, sizeof(int) * (size_t)2 * std::max(S, 1)));
         if (!hp.xtab.empty()) CU_TRY(cudaMemcpy(d_xtab, hp.xtab.data(), hp.xtab.size() * sizeof(XTab), cudaMemcpyHostToDevice));
         if (!hp.xgrp.empty()) CU_TRY(cudaMemcpy(d_xgrp, hp.xgrp.data(), hp.xgrp.size() * sizeof(XGroup), cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(d_mtab, hp.mtab.data(), hp.mtab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
@@ -563,6 +563,8 @@ struct b200orb_batch {
     bool host_ready = false;
     long long host_bytes = 0;
     int* h_status = nullptr; int h_status_cap = 0, h_status_n = 0;   // pinned: per-pair range-error flags of the last run_host
+    int status_bank = 0;      // which half of eng.d_status the next run_device uses (run_host: the chunk's slot, so that the
+                              // previous chunk's flag download on the output stream never races with the next chunk's clear)
     int stereo_flags = 0;
     int* d_sad = nullptr;     // [P][C], only with the median cull
     // per-kernel timing (b200orb_batch_profile): a pool of event sets, one set per run_device call
@@ -1029,8 +1031,8 @@ int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint
     A.kp_stride = (long long)C * 6; A.desc_stride = (long long)C * 32; A.pyr_stride = P.pyr_bytes;
     A.kp_row = 6; A.oct_idx = 5; A.out_stride = (int)C;
     A.uRight = d_uRight; A.depth = d_depth; A.matchIdx = d_matchIdx;
-    A.status = b->eng.d_status; A.status_stride = 1;          // flag word per pair, cleared here, read by b200orb_batch_status_device / run_host
-    CU_TRY(cudaMemsetAsync(b->eng.d_status, 0, (size_t)n_pairs * sizeof(int), st));
+    A.status = b->eng.d_status + (size_t)b->status_bank * b->eng.S; A.status_stride = 1;   // flag word per pair, cleared here, read by b200orb_batch_status_device / run_host
+    CU_TRY(cudaMemsetAsync(A.status, 0, (size_t)n_pairs * sizeof(int), st));
     A.rowStart = b->eng.d_rowstart; A.rmeta = b->eng.d_rmeta; A.idx_stride = (int)C;
     fill_stereo_consts(A, mbf, fx);
     if (b->stereo_flags & B200ORB_STEREO_MEDIAN_CULL) {
@@ -1165,22 +1167,40 @@ int b200orb_batch_run_host(b200orb_batch* b, const uint8_t* h_left, const uint8_
         b->h_status_cap = n_pairs;
     }
     b->h_status_n = n_pairs;
-    int k = 0;
-    for (int p0 = 0; p0 < n_pairs; p0 += b->P, ++k) {
+    // chunk schedule: full chunks of max_pairs, with a short ramp at both ends of a long job (P/4, P/2, P ... P, P/2, P/4) so that the
+    // first kernels start after a quarter-chunk upload and only a quarter-chunk download is left when the last kernels finish
+    std::vector<int> sizes;
+    {
+        const int P = b->P;
+        int left = n_pairs;
+        std::vector<int> tail;
+        if (n_pairs >= 4 * P && P >= 8) {
+            sizes.push_back(P / 4); sizes.push_back(P / 2);
+            tail.push_back(P / 2); tail.push_back(P / 4);
+            left -= 2 * (P / 4 + P / 2);
+        }
+        while (left > 0) { const int c = std::min(P, left); sizes.push_back(c); left -= c; }
+        sizes.insert(sizes.end(), tail.begin(), tail.end());
+    }
+    int p0 = 0;
+    for (int k = 0; k < (int)sizes.size(); p0 += sizes[k], ++k) {
         const int s = k & 1;
-        const size_t np = std::min(b->P, n_pairs - p0);
+        const size_t np = (size_t)sizes[k];
         if (k >= 2) CU_TRY(cudaStreamWaitEvent(b->s_in, b->ev_comp[s], 0));     // inputs of chunk k-2 consumed
         CU_TRY(cudaMemcpyAsync(b->d_in[s], h_left + (size_t)p0 * HW, np * HW, cudaMemcpyHostToDevice, b->s_in));
         CU_TRY(cudaMemcpyAsync(b->d_in[s] + np * HW, h_right + (size_t)p0 * HW, np * HW, cudaMemcpyHostToDevice, b->s_in));
         CU_TRY(cudaEventRecord(b->ev_in[s], b->s_in));
         CU_TRY(cudaStreamWaitEvent(b->s_comp, b->ev_in[s], 0));
         if (k >= 2) CU_TRY(cudaStreamWaitEvent(b->s_comp, b->ev_out[s], 0));   // outputs of chunk k-2 downloaded
-        TRY(b200orb_batch_run_device(b, b->d_in[s], b->d_in[s] + np * HW, (int)np, mbf, fx, b->d_kps[s], b->d_desc[s], b->d_nkp[s],
-                                     b->d_uR[s], b->d_dep[s], b->d_mi[s], b->s_comp));
-        // the chunk's range-error flags travel on the compute stream itself (the next chunk's run_device clears them there)
-        CU_TRY(cudaMemcpyAsync(b->h_status + p0, b->eng.d_status, np * sizeof(int), cudaMemcpyDeviceToHost, b->s_comp));
+        b->status_bank = s;
+        const int rrc = b200orb_batch_run_device(b, b->d_in[s], b->d_in[s] + np * HW, (int)np, mbf, fx, b->d_kps[s], b->d_desc[s], b->d_nkp[s],
+                                                 b->d_uR[s], b->d_dep[s], b->d_mi[s], b->s_comp);
+        b->status_bank = 0;
+        if (rrc) return rrc;
         CU_TRY(cudaEventRecord(b->ev_comp[s], b->s_comp));
         CU_TRY(cudaStreamWaitEvent(b->s_out, b->ev_comp[s], 0));
+        // the chunk's range-error flags travel with its outputs (bank s is cleared again by chunk k + 2, which waits for ev_out[s])
+        CU_TRY(cudaMemcpyAsync(b->h_status + p0, b->eng.d_status + (size_t)s * b->eng.S, np * sizeof(int), cudaMemcpyDeviceToHost, b->s_out));
         for (int side = 0; side < 2; ++side) {
             CU_TRY(cudaMemcpyAsync(h_kps + (side * NT + p0) * C * 6, b->d_kps[s] + side * np * C * 6, np * C * 24, cudaMemcpyDeviceToHost, b->s_out));
             CU_TRY(cudaMemcpyAsync(h_desc + (side * NT + p0) * C * 32, b->d_desc[s] + side * np * C * 32, np * C * 32, cudaMemcpyDeviceToHost, b->s_out));
