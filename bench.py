@@ -609,6 +609,40 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
+def run_multi_runner(args):
+    """`--impl multi --gpus N`: ONE process drives N GPUs through the library's own runner (pyorbslam_b200.StereoFrontendMulti: one
+    engine + host thread per GPU, contiguous frame ranges, one set of result arrays).  The driver's N > 1 runs use torchrun (one
+    process per GPU); this leg shows the same sharding as a library feature.  value = e2e frames/s from pinned host buffers."""
+    import torch
+    from pyorbslam_b200 import StereoFrontendMulti, _lib
+    G = max(1, min(args.gpus, _lib.device_count()))
+    fe = StereoFrontendMulti(ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"], H, W, args.chunk, devices=list(range(G)))
+    n = args.e2e_pairs * G
+    nb = args.base_pairs
+    base = [make_pair(i, H, W) for i in range(nb)]
+    lh = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
+    rh = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
+    for g in range(0, n, nb):
+        m = min(nb, n - g)
+        lh[g:g + m] = torch.from_numpy(np.stack([np.roll(p[0], 9 * (g // nb), axis=1) for p in base[:m]]))
+        rh[g:g + m] = torch.from_numpy(np.stack([np.roll(p[1], 9 * (g // nb), axis=1) for p in base[:m]]))
+    out = fe.alloc_outputs(n)
+    for _ in range(max(args.warmup, 2)):
+        fe.run_host(lh, rh, MBF, FX, out=out)
+    l0 = _lib.kernel_launches()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fe.run_host(lh, rh, MBF, FX, out=out)
+    dt = time.perf_counter() - t0
+    d2h = sum(v.numel() * v.element_size() for v in out.values())
+    emit({"impl": "multi", "metric": METRIC, "value": n * args.steps / dt, "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": max(args.warmup, 2),
+          "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+          "config": workload_config(args.e2e_pairs, args.chunk),
+          "e2e": {"value": n * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * n * H * W, "d2h_bytes_per_step": d2h, "pairs_per_step": n},
+          "gpu_launches": _lib.kernel_launches() - l0, "shards": fe.shards(n),
+          "what": "one process, one host thread + engine per GPU (StereoFrontendMulti.run_host), wall clock around the call"})
+
+
 _REAL_STDOUT = None
 
 
@@ -636,7 +670,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "multi"])
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS), help="kitti = the headline metric's configuration")
     ap.add_argument("--pairs", type=int, default=None, help="stereo pairs per GPU per step (kitti: 4096 = BASELINE.json configs[2])")
     ap.add_argument("--chunk", type=int, default=None, help="pairs per kernel-sequence launch (kitti: 128)")
@@ -658,6 +692,8 @@ def main():
     claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.impl == "multi":
+        run_multi_runner(args)
     else:
         run_b200_arm(args)
 

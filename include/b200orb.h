@@ -150,6 +150,15 @@ int b200orb_batch_run_host(b200orb_batch* b, const uint8_t* h_left, const uint8_
                            double mbf, float fx, float* h_kps, uint8_t* h_desc, int32_t* h_nkp,
                            float* h_uRight, float* h_depth, int32_t* h_matchIdx);
 
+/* One shard of a larger job (frames are independent, SURVEY.md 8e: contiguous frame ranges per GPU, no collective): processes
+ * pairs [first_pair, first_pair + n_pairs) of a job of job_pairs pairs.  h_left / h_right point at THIS shard's images; the output
+ * pointers are the JOB's arrays (layout above with n_pairs = job_pairs) and only this shard's rows are written, so several engines
+ * -- one per GPU, each called from its own host thread -- fill one set of result arrays.  b200orb_batch_run_host is the shard
+ * (job_pairs = n_pairs, first_pair = 0).  pyorbslam_b200.StereoFrontendMulti is the host side of this. */
+int b200orb_batch_run_host_shard(b200orb_batch* b, const uint8_t* h_left, const uint8_t* h_right, int n_pairs,
+                                 double mbf, float fx, float* h_kps, uint8_t* h_desc, int32_t* h_nkp,
+                                 float* h_uRight, float* h_depth, int32_t* h_matchIdx, int job_pairs, int first_pair);
+
 /* Range errors of the batched path.  Frame.compute_stereo_matches raises (IndexError / ValueError, Frame.py:192,230-250) when a
  * keypoint's row band or SAD window leaves the pyramid view; b200orb_stereo reports that as B200ORB_E_RANGE.  The batched calls keep one
  * flag word per pair (0 = fine): b200orb_batch_run_host returns B200ORB_E_RANGE after all outputs have reached host memory if any

@@ -56,6 +56,7 @@ def lib():
     l.b200orb_batch_workspace_bytes.restype = C.c_longlong
     l.b200orb_batch_run_device.argtypes = [vp, vp, vp, i32, f64, f32, vp, vp, vp, vp, vp, vp, vp]
     l.b200orb_batch_run_host.argtypes = [vp, vp, vp, i32, f64, f32, vp, vp, vp, vp, vp, vp]
+    l.b200orb_batch_run_host_shard.argtypes = [vp, vp, vp, i32, f64, f32, vp, vp, vp, vp, vp, vp, i32, i32]
     l.b200orb_batch_status_device.argtypes = [vp, i32, vp, vp]
     l.b200orb_batch_status_host.argtypes = [vp, vp, i32]
     l.b200orb_batch_candidate_count.argtypes = [vp, i32, C.POINTER(C.c_longlong)]

@@ -1154,12 +1154,23 @@ static int batch_host_setup(b200orb_batch* b) {
 
 int b200orb_batch_run_host(b200orb_batch* b, const uint8_t* h_left, const uint8_t* h_right, int n_pairs, double mbf, float fx,
                            float* h_kps, uint8_t* h_desc, int32_t* h_nkp, float* h_uRight, float* h_depth, int32_t* h_matchIdx) {
+    return b200orb_batch_run_host_shard(b, h_left, h_right, n_pairs, mbf, fx, h_kps, h_desc, h_nkp, h_uRight, h_depth, h_matchIdx, n_pairs, 0);
+}
+
+int b200orb_batch_run_host_shard(b200orb_batch* b, const uint8_t* h_left, const uint8_t* h_right, int n_pairs, double mbf, float fx,
+                                 float* h_kps, uint8_t* h_desc, int32_t* h_nkp, float* h_uRight, float* h_depth, int32_t* h_matchIdx,
+                                 int job_pairs, int first_pair) {
     if (!b || !h_left || !h_right || !h_kps || !h_desc || !h_nkp || !h_uRight || !h_depth) return fail(B200ORB_E_ARG, "NULL argument");
     if (n_pairs < 1) return fail(B200ORB_E_ARG, "n_pairs must be >= 1");
+    if (first_pair < 0 || job_pairs < first_pair + n_pairs) return fail(B200ORB_E_ARG, "shard [first_pair, first_pair + n_pairs) leaves the job");
+    // output arrays are dimensioned for the whole job; this call fills the rows of its own pairs
+    h_kps += (size_t)first_pair * b->eng.hp.P.kp_total * 6; h_desc += (size_t)first_pair * b->eng.hp.P.kp_total * 32; h_nkp += first_pair;
+    h_uRight += (size_t)first_pair * b->eng.hp.P.kp_total; h_depth += (size_t)first_pair * b->eng.hp.P.kp_total;
+    if (h_matchIdx) h_matchIdx += (size_t)first_pair * b->eng.hp.P.kp_total;
     CU_TRY(cudaSetDevice(b->eng.device));
     TRY(batch_host_setup(b));
     const Plan& P = b->eng.hp.P;
-    const size_t C = P.kp_total, HW = (size_t)b->H * b->W, NT = n_pairs;
+    const size_t C = P.kp_total, HW = (size_t)b->H * b->W, NT = (size_t)job_pairs;     // NT: pairs between the two sides of kps / desc / nkp
     if (n_pairs > b->h_status_cap) {
         if (b->h_status) cudaFreeHost(b->h_status);
         b->h_status = nullptr; b->h_status_cap = 0;

@@ -145,3 +145,32 @@ def test_caller_supplied_outputs_are_validated():
     del bad["nkp"]
     with pytest.raises(ValueError):
         fe.run(left, right, 100.0, 300.0, out=bad)
+
+
+def test_multi_gpu_runner_equals_single_engine():
+    """StereoFrontendMulti (one engine + host thread per device, frames sharded by contiguous ranges, all writing one set of
+    result arrays -- SURVEY.md 8e) against one engine's run_host.  On a one-GPU box both engines live on device 0, which still
+    exercises the sharding, the shard offsets of the C ABI and the concurrent host threads; with two GPUs it uses both."""
+    import torch
+    from pyorbslam_b200 import StereoFrontend, StereoFrontendMulti, _lib
+    from pyorbslam_b200.synthetic import make_kitti_like_pair
+    params = (800, 1.2, 5, 20, 7)
+    H, W, n = 200, 480, 7
+    pairs = [make_kitti_like_pair(60 + i, H, W) for i in range(n)]
+    left = torch.from_numpy(np.stack([p[0] for p in pairs])).pin_memory()
+    right = torch.from_numpy(np.stack([p[1] for p in pairs])).pin_memory()
+    one = StereoFrontend(*params, H, W, 3).run_host(left, right, 120.0, 400.0)
+    devs = [0, 1] if _lib.device_count() >= 2 else [0, 0]
+    for devices in (devs, [0, 0, 0]):
+        multi = StereoFrontendMulti(*params, H, W, 2, devices=devices)
+        assert [s[1:] for s in multi.shards(n)] == [tuple(map(int, (-(-r * n // len(devices)), min(-(-(r + 1) * n // len(devices)), n)))) for r in range(len(devices))]
+        got = multi.run_host(left, right, 120.0, 400.0)
+        assert torch.equal(got["nkp"], one["nkp"]) and int(got["nkp"].min()) > 100
+        for i in range(n):
+            nl, nr = int(one["nkp"][0, i]), int(one["nkp"][1, i])
+            assert torch.equal(got["kps"][0, i, :nl], one["kps"][0, i, :nl]) and torch.equal(got["kps"][1, i, :nr], one["kps"][1, i, :nr])
+            assert torch.equal(got["desc"][0, i, :nl], one["desc"][0, i, :nl]) and torch.equal(got["desc"][1, i, :nr], one["desc"][1, i, :nr])
+            for key in ("uRight", "depth", "matchIdx"):
+                assert torch.equal(got[key][i, :nl], one[key][i, :nl])
+        assert int(multi.last_pair_status.sum()) == 0
+        multi.close()
