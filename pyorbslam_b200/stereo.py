@@ -97,11 +97,16 @@ def compute_stereo_matches(self):
     self.mvuRight, self.mvDepth = _to_lists(uR, dep, self.mbf, lambda i: self.mvKeys[i].pt[0])
 
 
-def install(frame_cls, median_cull=False, dense_pyramid=False):
+def install(frame_cls, median_cull=False, dense_pyramid=False, fix_undistort=False):
     """Frame.compute_stereo_matches = the GPU matcher.  Returns the original method (to restore / compare).
-    The two keyword options switch on upstream-ORB-SLAM2 behaviour the reference does not have (device-resident path
-    only); leave them off for parity with the reference."""
+    median_cull / dense_pyramid switch on upstream-ORB-SLAM2 behaviour the reference does not have (device-resident path
+    only); fix_undistort replaces Frame.undistort_keypoints, which is broken for distorted cameras (Frame.py:298-322:
+    undefined name, result never assigned), by what it intends (frame_fixes.py).  Leave all three off for the reference's
+    behaviour exactly as shipped."""
     OPTIONS["flags"] = (MEDIAN_CULL if median_cull else 0) | (DENSE_PYRAMID if dense_pyramid else 0)
     original = frame_cls.compute_stereo_matches
     frame_cls.compute_stereo_matches = compute_stereo_matches
+    if fix_undistort:
+        from .frame_fixes import undistort_keypoints
+        frame_cls.undistort_keypoints = undistort_keypoints
     return original
