@@ -483,6 +483,11 @@ def run_b200_arm(args):
                           "Python API, one pair at a time (CUDA graph per image, results in one pinned copy, pyramid downloaded in the background); "
                           "_array_api = the same calls returning arrays (no 2 x 2000 Python tuples, which cost more than the GPU work)"}
 
+    # ---- the other BASELINE.json configurations (not the headline metric; recorded so that the driver's line carries them) ----
+    other_configs = None
+    if rank == 0 and world == 1 and not args.skip_other_configs:
+        other_configs = measure_other_configs(local, dev, not args.no_cpu_baseline)
+
     # ---- BoW transform of one frame's descriptors (Frame.compute_BoW), GPU vs the Python restatement ----
     bow_extra = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -600,6 +605,7 @@ def run_b200_arm(args):
                                "workspace_bytes": sum(f.workspace_bytes() for f in fes), "rank0_cpu_affinity": numa if isinstance(numa, str) else f"{len(numa)} cpus: {numa[0]}-{numa[-1]}"},
         }
         line["dropin_single_frame_latency"] = dropin
+        line["other_baseline_configs"] = other_configs
         line["bow_transform_8f_rank2"] = bow_extra
         line["projection_search_8f_rank1"] = proj_extra
         if cpu_baseline is not None:
@@ -607,6 +613,110 @@ def run_b200_arm(args):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_other_configs(local, dev, with_cpu):
+    """BASELINE.json configs[0], [3], [4] next to the headline configs[2]: timings only (parity of each is a -m gpu test)."""
+    import torch
+    from pyorbslam_b200 import ORBextractor, StereoFrontend
+    from pyorbslam_b200.stereo import stereo_host
+    from pyorbslam_b200.synthetic import make_kitti_like_pair
+    out = {}
+
+    def timed(fn, n, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - t0) / n
+
+    # configs[0]: pyORBExtractor/test.py on the bundled kitti06-436.png (stored as raw gray pixels), 20 iterations like test.py:28-38
+    fixture = os.path.join(ROOT, "tests", "golden", "kitti06-436.gray.npy")
+    kitti_prm = (2000, 1.2, 8, 20, 7)
+    if os.path.exists(fixture):
+        img = np.load(fixture)
+        e = ORBextractor(*kitti_prm, device=local, reuse_identical_input=False)
+        n = len(e.extract_arrays(img)[0])
+        out["config0_fixture_image"] = {"image": list(img.shape), "keypoints": n, "iterations": 20,
+                                        "ms_per_iter_operator_kd": timed(lambda: e.operator_kd(img), 20),
+                                        "ms_per_iter_arrays": timed(lambda: e.extract_arrays(img), 20),
+                                        "what": "test.py's loop: operator_kd (6-tuple list + descriptors) per iteration; _arrays = the same call returning arrays"}
+    # configs[3]: 2560x1440, 8000 features, 12 levels
+    try:
+        Hh, Ww, Ph, nbh, Bh = 1440, 2560, 16, 2, 64
+        prm = (8000, 1.2, 12, 20, 7)
+        base = [make_kitti_like_pair(5000 + i, Hh, Ww) for i in range(nbh)]
+        fe = StereoFrontend(*prm, Hh, Ww, Ph, device=local)
+        lh = torch.empty((Bh, Hh, Ww), dtype=torch.uint8, pin_memory=True)
+        rh = torch.empty((Bh, Hh, Ww), dtype=torch.uint8, pin_memory=True)
+        for g in range(0, Bh, nbh):
+            for j in range(nbh):
+                lh[g + j] = torch.from_numpy(np.roll(base[j][0], 9 * (g // nbh), axis=1))
+                rh[g + j] = torch.from_numpy(np.roll(base[j][1], 9 * (g // nbh), axis=1))
+        ld, rd = lh.to(dev), rh.to(dev)
+        outs = [fe.alloc_outputs(Ph) for _ in range(0, Bh, Ph)]
+
+        def step():
+            for k, c in enumerate(range(0, Bh, Ph)):
+                fe.run(ld[c:c + Ph], rd[c:c + Ph], MBF, FX, out=outs[k])
+        ms = timed(step, 3)
+        oh = fe.alloc_outputs(Bh, pinned_host=True)
+        ms_e2e = timed(lambda: fe.run_host(lh, rh, MBF, FX, out=oh), 3, warm=1)
+        nk = float(oh["nkp"].float().mean())
+        out["config3_hires"] = {"image": [Hh, Ww], "nfeatures": 8000, "nlevels": 12, "pairs_per_step": Bh, "chunk_pairs": Ph,
+                                "frames_per_sec_device_resident": Bh / (ms / 1e3), "frames_per_sec_e2e": Bh / (ms_e2e / 1e3),
+                                "keypoints_per_image": nk, "scenes": "kitti_like"}
+        del fe, ld, rd, lh, rh, oh, outs
+        torch.cuda.empty_cache()
+    except Exception as ex:       # a side measurement must not cost the headline line
+        out["config3_hires"] = {"error": repr(ex)}
+    # configs[4]: compute_stereo_matches only, 1k..16k keypoints per image (synthetic keypoints / descriptors on real pyramids)
+    try:
+        L, R = make_kitti_like_pair(12, H, W)
+        eL, eR = ORBextractor(*kitti_prm, device=local), ORBextractor(*kitti_prm, device=local)
+        eL.extract_arrays(L)
+        eR.extract_arrays(R)
+        pyrL, pyrR = eL.GetImagePyramid(), eR.GetImagePyramid()
+        sf, isf = np.array(eL.GetScaleFactors(), np.float32), np.array(eL.GetInverseScaleFactors(), np.float32)
+        quota = np.array(eL.features_per_level(), np.float64)
+        sweep = []
+        for n in (1000, 2000, 4000, 8000, 16000):
+            rng = np.random.default_rng(n)
+            octv = rng.choice(len(sf), size=n, p=quota / quota.sum())
+            s_ = sf[octv]
+            lx = rng.integers(19, (W / s_ - 20).astype(int)).astype(np.float32)
+            ly = rng.integers(19, (H / s_ - 20).astype(int)).astype(np.float32)
+            disp = rng.integers(1, 80, n).astype(np.float32)
+            kL = np.stack([np.where(octv > 0, lx * s_, lx), np.where(octv > 0, ly * s_, ly), octv.astype(np.float32)], 1).astype(np.float32)
+            rx = np.maximum(lx - np.floor(disp / s_), 19).astype(np.float32)
+            kR = np.stack([np.where(octv > 0, rx * s_, rx), kL[:, 1], octv.astype(np.float32)], 1).astype(np.float32)
+            dL = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+            dR = dL ^ np.packbits(rng.random((n, 256)) < 0.1, axis=1, bitorder="little")
+            perm = rng.permutation(n)
+            kR, dR = kR[perm], dR[perm]
+            gu = stereo_host(kL, dL, kR, dR, sf, isf, pyrL, pyrR, MBF, FX, device=local)[0]
+            row = {"keypoints": n, "gpu_ms": timed(lambda: stereo_host(kL, dL, kR, dR, sf, isf, pyrL, pyrR, MBF, FX, device=local), 5, warm=1),
+                   "matches": int((gu >= 0).sum())}
+            if with_cpu:          # CPU leg: the Python restatement on a bounded sample of the left keypoints (its cost is linear in them)
+                from oracle import stereo_py
+                m = min(n, 96)
+                keysR = [(float(a), float(b), int(c)) for a, b, c in kR]
+                keysL = [(float(a), float(b), int(c)) for a, b, c in kL[:m]]
+                t0 = time.perf_counter()
+                cu, _ = stereo_py.stereo_matches(keysL, dL[:m], keysR, dR, sf.tolist(), isf.tolist(), pyrL, pyrR, MBF, np.float32(FX))
+                row["cpu_python_ms_extrapolated"] = 1e3 * (time.perf_counter() - t0) * n / m
+                row["cpu_sample_left_keypoints"] = m
+                row["identical_on_sample"] = bool(np.array_equal(np.array([float(v) for v in cu], np.float32), gu[:m]))
+            sweep.append(row)
+        out["config4_stereo_only_sweep"] = {"what": "b200orb_stereo_host (uploads the caller's keypoints, descriptors and pyramid views, K7 + K8, downloads) vs the "
+                                            "Python restatement of Frame.compute_stereo_matches (row index built over all right keypoints, then a bounded "
+                                            "sample of left keypoints, extrapolated linearly)", "rows": sweep}
+    except Exception as ex:
+        out["config4_stereo_only_sweep"] = {"error": repr(ex)}
+    return out
 
 
 def run_multi_runner(args):
@@ -680,6 +790,7 @@ def main():
     ap.add_argument("--streams", type=int, default=1, help="front-ends running consecutive chunks concurrently (own workspace + stream each)")
     ap.add_argument("--scenes", default="kitti_like", choices=["kitti_like", "layered"], help="synthetic scene generator (pyorbslam_b200/synthetic.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-other-configs", action="store_true", help="skip the config 1 / 4 / 5 side measurements (fixture image, hires, stereo-only sweep)")
     args = ap.parse_args()
     global STREAMS, H, W, ORB, WORKLOAD_NAME, SCENES
     STREAMS = args.streams

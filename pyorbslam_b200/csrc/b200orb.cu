@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -915,36 +917,44 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
         if (o < 0 || o >= nlevels) return fail(B200ORB_E_RANGE, "left keypoint octave out of range");
         if ((int)kpsL[3 * i + 1] < 0 || (int)kpsL[3 * i + 1] >= lh[0]) return fail(B200ORB_E_RANGE, "left keypoint row outside the image");
     }
-    u8 *d_blob = nullptr, *d_dL = nullptr, *d_dR = nullptr;
-    float *d_kL = nullptr, *d_kR = nullptr, *d_u = nullptr, *d_d = nullptr;
-    int *d_m = nullptr, *d_n = nullptr, *d_rs = nullptr;
-    int4* d_rm = nullptr;
-    int rc = 0;
-    auto cleanup = [&]() { cudaFree(d_blob); cudaFree(d_dL); cudaFree(d_dR); cudaFree(d_kL); cudaFree(d_kR); cudaFree(d_u); cudaFree(d_d); cudaFree(d_m); cudaFree(d_n); cudaFree(d_rs); cudaFree(d_rm); };
-#define CU_TRY2(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(B200ORB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
-    CU_TRY2(cudaMalloc((void**)&d_blob, (size_t)total * 2));
-    CU_TRY2(cudaMalloc((void**)&d_kL, (size_t)nLeft * 12));
-    CU_TRY2(cudaMalloc((void**)&d_dL, (size_t)nLeft * 32));
-    CU_TRY2(cudaMalloc((void**)&d_kR, (size_t)std::max(nRight, 1) * 12));
-    CU_TRY2(cudaMalloc((void**)&d_dR, (size_t)std::max(nRight, 1) * 32));
-    CU_TRY2(cudaMalloc((void**)&d_u, (size_t)nLeft * 4));
-    CU_TRY2(cudaMalloc((void**)&d_d, (size_t)nLeft * 4));
-    CU_TRY2(cudaMalloc((void**)&d_m, (size_t)nLeft * 4));
-    CU_TRY2(cudaMalloc((void**)&d_n, 12));
-    CU_TRY2(cudaMalloc((void**)&d_rs, (size_t)(lh[0] + 1) * 4));
-    CU_TRY2(cudaMalloc((void**)&d_rm, (size_t)std::max(nRight, 1) * 16));
-    for (int l = 0; l < nlevels; ++l) {
-        CU_TRY2(cudaMemcpy(d_blob + SG.base[l], pyrL[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice));
-        CU_TRY2(cudaMemcpy(d_blob + total + SG.base[l], pyrR[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice));
+    // Device scratch of this entry point is cached per device and only grows (the first version paid eleven cudaMalloc / cudaFree
+    // pairs per call -- ~10 ms before any work).  One arena, carved into 256-byte aligned pieces; the uploads are plain copies of the
+    // caller's (pageable) arrays.
+    struct HostStereoWS { u8* base = nullptr; size_t cap = 0; cudaStream_t st = nullptr; };
+    static std::mutex ws_mutex;
+    static std::map<int, HostStereoWS> ws_map;
+    std::lock_guard<std::mutex> guard(ws_mutex);
+    HostStereoWS& ws = ws_map[device];
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t nR1 = (size_t)std::max(nRight, 1);
+    const size_t o_blob = 0, o_kL = o_blob + al((size_t)total * 2), o_dL = o_kL + al((size_t)nLeft * 12), o_kR = o_dL + al((size_t)nLeft * 32),
+                 o_dR = o_kR + al(nR1 * 12), o_out = o_dR + al(nR1 * 32), o_n = o_out + al((size_t)nLeft * 12), o_rs = o_n + 256,
+                 o_rm = o_rs + al((size_t)(lh[0] + 1) * 4), need = o_rm + al(nR1 * 16);
+    if (need > ws.cap) {
+        if (ws.base) cudaFree(ws.base);
+        ws.base = nullptr; ws.cap = 0;
+        CU_TRY(cudaMalloc((void**)&ws.base, need + need / 4));
+        ws.cap = need + need / 4;
     }
-    CU_TRY2(cudaMemcpy(d_kL, kpsL, (size_t)nLeft * 12, cudaMemcpyHostToDevice));
-    CU_TRY2(cudaMemcpy(d_dL, descL, (size_t)nLeft * 32, cudaMemcpyHostToDevice));
+    if (!ws.st) CU_TRY(cudaStreamCreateWithFlags(&ws.st, cudaStreamNonBlocking));
+    cudaStream_t st = ws.st;
+    u8* d_blob = ws.base + o_blob;
+    float* d_kL = (float*)(ws.base + o_kL); u8* d_dL = ws.base + o_dL;
+    float* d_kR = (float*)(ws.base + o_kR); u8* d_dR = ws.base + o_dR;
+    float* d_u = (float*)(ws.base + o_out); float* d_d = d_u + nLeft; int* d_m = (int*)(d_d + nLeft);
+    int* d_n = (int*)(ws.base + o_n); int* d_rs = (int*)(ws.base + o_rs); int4* d_rm = (int4*)(ws.base + o_rm);
+    for (int l = 0; l < nlevels; ++l) {
+        CU_TRY(cudaMemcpyAsync(d_blob + SG.base[l], pyrL[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_blob + total + SG.base[l], pyrR[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice, st));
+    }
+    CU_TRY(cudaMemcpyAsync(d_kL, kpsL, (size_t)nLeft * 12, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_dL, descL, (size_t)nLeft * 32, cudaMemcpyHostToDevice, st));
     if (nRight) {
-        CU_TRY2(cudaMemcpy(d_kR, kpsR, (size_t)nRight * 12, cudaMemcpyHostToDevice));
-        CU_TRY2(cudaMemcpy(d_dR, descR, (size_t)nRight * 32, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpyAsync(d_kR, kpsR, (size_t)nRight * 12, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_dR, descR, (size_t)nRight * 32, cudaMemcpyHostToDevice, st));
     }
     const int hn[3] = {nLeft, nRight, 0};
-    CU_TRY2(cudaMemcpy(d_n, hn, 12, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpyAsync(d_n, hn, 12, cudaMemcpyHostToDevice, st));
     StereoArgs A;
     memset(&A, 0, sizeof(A));
     A.kpsL = d_kL; A.descL = d_dL; A.nL = d_n; A.kpsR = d_kR; A.descR = d_dR; A.nR = d_n + 1;
@@ -953,14 +963,13 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     A.uRight = d_u; A.depth = d_d; A.matchIdx = d_m; A.status = d_n + 2;
     A.rowStart = d_rs; A.rmeta = d_rm; A.idx_stride = std::max(nRight, 1);
     fill_stereo_consts(A, mbf, fx);
-    rc = launch_stereo(SG, A, nLeft, 1, nullptr);
-    if (rc) { cleanup(); return rc; }
+    TRY(launch_stereo(SG, A, nLeft, 1, st));
     int status = 0;
-    CU_TRY2(cudaMemcpy(uRight, d_u, (size_t)nLeft * 4, cudaMemcpyDeviceToHost));
-    CU_TRY2(cudaMemcpy(depth, d_d, (size_t)nLeft * 4, cudaMemcpyDeviceToHost));
-    if (matchIdx) CU_TRY2(cudaMemcpy(matchIdx, d_m, (size_t)nLeft * 4, cudaMemcpyDeviceToHost));
-    CU_TRY2(cudaMemcpy(&status, d_n + 2, 4, cudaMemcpyDeviceToHost));
-    cleanup();
+    CU_TRY(cudaMemcpyAsync(uRight, d_u, (size_t)nLeft * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(depth, d_d, (size_t)nLeft * 4, cudaMemcpyDeviceToHost, st));
+    if (matchIdx) CU_TRY(cudaMemcpyAsync(matchIdx, d_m, (size_t)nLeft * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(&status, d_n + 2, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
     if (status) return fail(B200ORB_E_RANGE, "a SAD window leaves the pyramid view (the reference raises IndexError/ValueError here)");
     return 0;
 }

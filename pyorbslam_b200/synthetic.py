@@ -194,9 +194,9 @@ def make_kitti_like_pair(idx, H=376, W=1241, max_disp=88.0, noise_sigma=0.6, nob
         ow = int(rng.uniform(0.3, 1.0) * (60 + 520 * scale) * obj_scale)
         side = rng.random() < 0.8                                 # most objects flank the road
         if side:
-            x0 = int(rng.uniform(0, 0.30 * WW - ow * 0.5)) if rng.random() < 0.5 else int(rng.uniform(0.70 * WW - ow * 0.5, WW - 8))
+            x0 = int(rng.uniform(0, max(0.30 * WW - ow * 0.5, 1.0))) if rng.random() < 0.5 else int(rng.uniform(min(0.70 * WW - ow * 0.5, WW - 9.0), WW - 8))
         else:
-            x0 = int(rng.uniform(0.30 * WW, 0.70 * WW - 4))
+            x0 = int(rng.uniform(0.30 * WW, max(0.70 * WW - 4, 0.30 * WW + 1)))
         y1, y0 = int(yb), max(int(yb) - oh, 0)
         x0 = max(x0, 0)
         x1 = min(x0 + max(ow, 8), WW)
