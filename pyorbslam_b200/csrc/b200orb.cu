@@ -513,6 +513,35 @@ int launch_stereo(const StereoGeom& SG, StereoArgs A, int max_left, int pairs, c
     return 0;
 }
 
+// Grow-only device scratch per device for the stateless entry points (all-pairs Hamming, area queries): carving a cached block
+// replaces a dozen cudaMalloc / cudaFree pairs per call.  Calls on one device are serialised by the arena's mutex.
+struct ScratchArena {
+    std::mutex mu;
+    unsigned char* base = nullptr;
+    size_t cap = 0, used = 0;
+    int reserve(size_t bytes) {
+        used = 0;
+        if (bytes <= cap) return 0;
+        if (base) cudaFree(base);
+        base = nullptr; cap = 0;
+        CU_TRY(cudaMalloc((void**)&base, bytes + bytes / 4 + 4096));
+        cap = bytes + bytes / 4 + 4096;
+        return 0;
+    }
+    template <typename T> T* take(size_t n) {
+        unsigned char* p = base + used;
+        used += (n * sizeof(T) + 255) & ~(size_t)255;
+        return reinterpret_cast<T*>(p);
+    }
+    static size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+};
+ScratchArena& arena_of(int device) {
+    static std::mutex m;
+    static std::map<int, ScratchArena> arenas;
+    std::lock_guard<std::mutex> g(m);
+    return arenas[device];
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -1323,21 +1352,19 @@ int b200orb_hamming_matrix(int device, const uint8_t* A, int nA, const uint8_t* 
     if (nA == 0 || nB == 0) return 0;
     if (!A || !B || !out) return fail(B200ORB_E_ARG, "NULL argument");
     CU_TRY(cudaSetDevice(device));
-    u8 *dA = nullptr, *dB = nullptr;
-    unsigned short* dO = nullptr;
-    auto done = [&](int rc) { cudaFree(dA); cudaFree(dB); cudaFree(dO); return rc; };
-    cudaError_t e;
-    if ((e = cudaMalloc((void**)&dA, (size_t)nA * 32)) != cudaSuccess || (e = cudaMalloc((void**)&dB, (size_t)nB * 32)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&dO, (size_t)nA * nB * 2)) != cudaSuccess)
-        return done(fail(B200ORB_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)));
-    if ((e = cudaMemcpy(dA, A, (size_t)nA * 32, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(dB, B, (size_t)nB * 32, cudaMemcpyHostToDevice)) != cudaSuccess)
-        return done(fail(B200ORB_E_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e)));
+    ScratchArena& ar = arena_of(device);
+    std::lock_guard<std::mutex> guard(ar.mu);
+    TRY(ar.reserve(ScratchArena::padded((size_t)nA * 32) + ScratchArena::padded((size_t)nB * 32) + ScratchArena::padded((size_t)nA * nB * 2)));
+    u8* dA = ar.take<u8>((size_t)nA * 32);
+    u8* dB = ar.take<u8>((size_t)nB * 32);
+    unsigned short* dO = ar.take<unsigned short>((size_t)nA * nB);
+    CU_TRY(cudaMemcpy(dA, A, (size_t)nA * 32, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(dB, B, (size_t)nB * 32, cudaMemcpyHostToDevice));
     k_hamming_matrix<<<dim3((nB + 127) / 128, (nA + HM_ROWS - 1) / HM_ROWS), 128>>>(dA, nA, dB, nB, dO);
     ++g_launches;
-    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpy(out, dO, (size_t)nA * nB * 2, cudaMemcpyDeviceToHost)) != cudaSuccess)
-        return done(fail(B200ORB_E_CUDA, std::string("k_hamming_matrix: ") + cudaGetErrorString(e)));
-    return done(0);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(out, dO, (size_t)nA * nB * 2, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 // ---------------------------------------------------------------- projection searches
@@ -1363,23 +1390,37 @@ int b200orb_area_hamming(int device, int f32_mode, int N, const float* kxy, cons
         qc[4 * q] = empty ? 1 : c0; qc[4 * q + 1] = empty ? 0 : c1; qc[4 * q + 2] = empty ? 0 : r0; qc[4 * q + 3] = empty ? 0 : r1;
     }
     CU_TRY(cudaSetDevice(device));
-    double* d_q = nullptr; int *d_lvl = nullptr, *d_cell = nullptr, *d_cs = nullptr, *d_ci = nullptr, *d_oct = nullptr, *d_cnt = nullptr, *d_oi = nullptr, *d_od = nullptr;
-    u8 *d_qd = nullptr, *d_kd = nullptr; float* d_xy = nullptr;
-    auto done = [&](int rc) {
-        cudaFree(d_q); cudaFree(d_lvl); cudaFree(d_cell); cudaFree(d_cs); cudaFree(d_ci); cudaFree(d_oct); cudaFree(d_cnt); cudaFree(d_oi);
-        cudaFree(d_od); cudaFree(d_qd); cudaFree(d_kd); cudaFree(d_xy);
-        return rc;
-    };
-    cudaError_t e = cudaSuccess;
-    auto up = [&](auto** dp, const void* src, size_t bytes) {
-        if (e != cudaSuccess) return;
-        if ((e = cudaMalloc((void**)dp, std::max<size_t>(bytes, 16))) != cudaSuccess) return;
-        if (bytes && src) e = cudaMemcpy(*dp, src, bytes, cudaMemcpyHostToDevice);
-    };
-    up(&d_q, qxyr, (size_t)M * 24); up(&d_lvl, qlvl, (size_t)M * 8); up(&d_cell, qc.data(), (size_t)M * 16); up(&d_qd, qdesc, (size_t)M * 32);
-    up(&d_cs, cell_start, (size_t)(ncell + 1) * 4); up(&d_ci, cell_idx, (size_t)nidx * 4); up(&d_xy, kxy, (size_t)N * 8);
-    up(&d_oct, koct, (size_t)N * 4); up(&d_kd, kdesc, (size_t)N * 32); up(&d_cnt, nullptr, (size_t)(M + 1) * 4);
-    if (e != cudaSuccess) return done(fail(B200ORB_E_CUDA, std::string("area_hamming upload: ") + cudaGetErrorString(e)));
+    ScratchArena& ar = arena_of(device);
+    std::lock_guard<std::mutex> guard(ar.mu);
+    const size_t capn = (size_t)std::max(cap, 1);
+    size_t need = 0;
+    for (size_t b : {(size_t)M * 24, (size_t)M * 8, (size_t)M * 16, (size_t)M * 32, (size_t)(ncell + 1) * 4, (size_t)std::max(nidx, 1) * 4,
+                     (size_t)std::max(N, 1) * 8, (size_t)std::max(N, 1) * 4, (size_t)std::max(N, 1) * 32, (size_t)(M + 1) * 4, capn * 4, capn * 4})
+        need += ScratchArena::padded(b);
+    TRY(ar.reserve(need));
+    double* d_q = ar.take<double>((size_t)M * 3);
+    int* d_lvl = ar.take<int>((size_t)M * 2);
+    int* d_cell = ar.take<int>((size_t)M * 4);
+    u8* d_qd = ar.take<u8>((size_t)M * 32);
+    int* d_cs = ar.take<int>((size_t)ncell + 1);
+    int* d_ci = ar.take<int>((size_t)std::max(nidx, 1));
+    float* d_xy = ar.take<float>((size_t)std::max(N, 1) * 2);
+    int* d_oct = ar.take<int>((size_t)std::max(N, 1));
+    u8* d_kd = ar.take<u8>((size_t)std::max(N, 1) * 32);
+    int* d_cnt = ar.take<int>((size_t)M + 1);
+    int* d_oi = ar.take<int>(capn);
+    int* d_od = ar.take<int>(capn);
+    CU_TRY(cudaMemcpy(d_q, qxyr, (size_t)M * 24, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(d_lvl, qlvl, (size_t)M * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(d_cell, qc.data(), (size_t)M * 16, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(d_qd, qdesc, (size_t)M * 32, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(d_cs, cell_start, (size_t)(ncell + 1) * 4, cudaMemcpyHostToDevice));
+    if (nidx) CU_TRY(cudaMemcpy(d_ci, cell_idx, (size_t)nidx * 4, cudaMemcpyHostToDevice));
+    if (N) {
+        CU_TRY(cudaMemcpy(d_xy, kxy, (size_t)N * 8, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(d_oct, koct, (size_t)N * 4, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(d_kd, kdesc, (size_t)N * 32, cudaMemcpyHostToDevice));
+    }
     const dim3 grid((M + AQ_WARPS - 1) / AQ_WARPS);
     auto launch = [&](int count_only, const int* d_start, int* oi, int* od) {
         if (f32_mode) k_area_hamming<float><<<grid, AQ_WARPS * 32>>>(M, d_q, d_lvl, d_cell, d_qd, rows, d_cs, d_ci, d_xy, d_oct, d_kd, count_only, d_cnt, d_start, oi, od);
@@ -1388,23 +1429,21 @@ int b200orb_area_hamming(int device, int f32_mode, int N, const float* kxy, cons
     };
     launch(1, nullptr, nullptr, nullptr);
     std::vector<int> cnt(M);
-    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpy(cnt.data(), d_cnt, (size_t)M * 4, cudaMemcpyDeviceToHost)) != cudaSuccess)
-        return done(fail(B200ORB_E_CUDA, std::string("k_area_hamming: ") + cudaGetErrorString(e)));
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(cnt.data(), d_cnt, (size_t)M * 4, cudaMemcpyDeviceToHost));
     long long sum = 0;
     for (int q = 0; q < M; ++q) { cand_start[q] = (int32_t)sum; sum += cnt[q]; }
-    if (sum > 0x7fffffffLL) return done(fail(B200ORB_E_RANGE, "too many candidates"));
+    if (sum > 0x7fffffffLL) return fail(B200ORB_E_RANGE, "too many candidates");
     cand_start[M] = (int32_t)sum; *total = (int32_t)sum;
-    if (sum > cap) return done(fail(B200ORB_E_RANGE, "candidate buffers too small (*total holds the size needed)"));
-    if (sum == 0) return done(0);
-    if (!cand_idx || !cand_dist) return done(fail(B200ORB_E_ARG, "NULL argument"));
-    if ((e = cudaMemcpy(d_cnt, cand_start, (size_t)(M + 1) * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&d_oi, (size_t)sum * 4)) != cudaSuccess || (e = cudaMalloc((void**)&d_od, (size_t)sum * 4)) != cudaSuccess)
-        return done(fail(B200ORB_E_CUDA, std::string("area_hamming buffers: ") + cudaGetErrorString(e)));
+    if (sum > cap) return fail(B200ORB_E_RANGE, "candidate buffers too small (*total holds the size needed)");
+    if (sum == 0) return 0;
+    if (!cand_idx || !cand_dist) return fail(B200ORB_E_ARG, "NULL argument");
+    CU_TRY(cudaMemcpy(d_cnt, cand_start, (size_t)(M + 1) * 4, cudaMemcpyHostToDevice));
     launch(0, d_cnt, d_oi, d_od);
-    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpy(cand_idx, d_oi, (size_t)sum * 4, cudaMemcpyDeviceToHost)) != cudaSuccess ||
-        (e = cudaMemcpy(cand_dist, d_od, (size_t)sum * 4, cudaMemcpyDeviceToHost)) != cudaSuccess)
-        return done(fail(B200ORB_E_CUDA, std::string("k_area_hamming: ") + cudaGetErrorString(e)));
-    return done(0);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(cand_idx, d_oi, (size_t)sum * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(cand_dist, d_od, (size_t)sum * 4, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 // The order-dependent part of the two projection searches, on the candidate lists b200orb_area_hamming produced (host code: every
