@@ -195,15 +195,30 @@ __global__ void __launch_bounds__(256, 5) k_resize(const __grid_constant__ Plan 
 // K5: GaussianBlur 7x7 sigma 2 of every level (ORBextractor.cpp:1084-1085), OpenCV fixed-point result:
 // kernel [18,34,48,56,48,34,18]/256 per axis, dst = (sum + 2^15) >> 16.
 // The bordered pyramid already holds the reflect-101 halo the blur needs.
-// Register-resident separable filter, no shared memory: a warp owns a 128-column strip (lane = 4 output
-// columns = one 32-bit store), walks BLUR_RB rows down and keeps the last 7 horizontally filtered rows in
-// registers.  Per input row every lane issues ONE aligned 32-bit load; the two neighbouring words come from
-// warp shuffles (the level ROI starts at buffer column 19, so output word k needs input words k+4 .. k+6).
+// Register-resident separable filter, no shared memory.  A warp owns a strip of 30 output words (120 columns; lane = one 32-bit
+// word of the bordered buffer, lanes 30 / 31 only feed their left neighbours) and walks BLUR_RB rows down.
+//   * VERTICAL pass first, on raw bytes: every four input rows are byte-transposed per lane (8 PRMT) into four registers that
+//     hold one column's four rows each, so a column's seven vertical taps are two or three 4-way dot products (DP4A) against
+//     constant coefficient words -- 2.5 per column and output row instead of the 4 instructions of a 16-bit formulation.
+//   * HORIZONTAL pass on the 16-bit column sums, packed in pairs: the level ROI starts at buffer column 19, so output word k needs
+//     the sums of words k+4 .. k+6, i.e. the lane's own two pairs, both pairs of lane + 1 and the first pair of lane + 2 (three
+//     shuffles); every output is four 2-way dot products (DP2A).  Integer sums are exact in either order, the result is OpenCV's.
 // ------------------------------------------------------------------------------------------------
-#define BLUR_TW 128
+#define BLUR_TW 120
 #define BLUR_RB 32
 #define BLUR_WARPS 4
 #define BLUR_TH (BLUR_RB * BLUR_WARPS)
+__device__ __forceinline__ u32 blur_out4(u32 m01, u32 m23, u32 r01, u32 r23, u32 q01) {
+    // taps 18 34 48 56 48 34 18 over the ten sums (m01 m23 r01 r23 q01) = columns 0..9; outputs at columns 0..3
+    const u32 K01 = 18u | (34u << 8), K23 = 48u | (56u << 8), K45 = 48u | (34u << 8), K6_ = 18u;
+    const u32 K_0 = 18u << 8, K12 = 34u | (48u << 8), K34 = 56u | (48u << 8), K56 = 34u | (18u << 8);
+    u32 a0 = __dp2a_lo(m01, K01, 32768u); a0 = __dp2a_lo(m23, K23, a0); a0 = __dp2a_lo(r01, K45, a0); a0 = __dp2a_lo(r23, K6_, a0);
+    u32 a1 = __dp2a_lo(m01, K_0, 32768u); a1 = __dp2a_lo(m23, K12, a1); a1 = __dp2a_lo(r01, K34, a1); a1 = __dp2a_lo(r23, K56, a1);
+    u32 a2 = __dp2a_lo(m23, K01, 32768u); a2 = __dp2a_lo(r01, K23, a2); a2 = __dp2a_lo(r23, K45, a2); a2 = __dp2a_lo(q01, K6_, a2);
+    u32 a3 = __dp2a_lo(m23, K_0, 32768u); a3 = __dp2a_lo(r01, K12, a3); a3 = __dp2a_lo(r23, K34, a3); a3 = __dp2a_lo(q01, K56, a3);
+    // every sum is < 2^24: the result bytes are byte 2 of each accumulator
+    return __byte_perm(__byte_perm(a0, a1, 0x0062), __byte_perm(a2, a3, 0x0062), 0x5410);
+}
 __global__ void __launch_bounds__(BLUR_WARPS * 32) k_blur(const __grid_constant__ Plan P, const u8* __restrict__ pyr, u8* __restrict__ blur) {
     const int slot = blockIdx.y, bid = (int)blockIdx.x;
     int l = 0;
@@ -217,62 +232,61 @@ __global__ void __launch_bounds__(BLUR_WARPS * 32) k_blur(const __grid_constant_
     if (y0 >= G.h) return;                                  // warp-uniform
     const u32* src = reinterpret_cast<const u32*>(pyr + (size_t)slot * P.pyr_bytes + G.pyr_ofs);
     const int wpr = G.pitch >> 2;                            // words per buffer row
-    // input bytes for outputs x0..x0+3: ROI x0-3 .. x0+6 = buffer columns x0+16 .. x0+25 -> words (x0+16)/4 + {0,1,2}
+    // input bytes for outputs x0..x0+3: ROI x0-3 .. x0+6 = buffer columns x0+16 .. x0+25: this lane's word is (x0+16)/4
     const int w0 = min((x0 + 16) >> 2, wpr - 1);
-    const int wx = min(((tx * BLUR_TW + 16) >> 2) + 32 + (lane & 1), wpr - 1);   // lanes 0/1 fetch the two words past the strip
     u8* dst = blur + (size_t)slot * P.blur_bytes + G.blur_ofs;
-    // ask for all BLUR_RB + 6 input rows of the strip at once (one line per row): the unrolled loop below then runs on L1 hits
-    // instead of serialising on DRAM latency a few rows at a time
-    for (int r = lane; r < BLUR_RB + 6; r += 32) {
+    // ask for all BLUR_RB + 8 input rows of the strip at once (one line per row): the unrolled loop below then runs on L1 hits
+    for (int r = lane; r < BLUR_RB + 8; r += 32) {
         const int by = min(y0 + r - 3 + ORB_EDGE, G.rows - 1);
         asm volatile("prefetch.global.L1 [%0];" ::"l"(src + (size_t)by * wpr + min(((tx * BLUR_TW + 16) >> 2) + 16, wpr - 1)));
     }
-    // Horizontal pass: the 7 taps of one output are two 4-byte dot products (DP4A) on byte windows cut out of the three
-    // source words with funnel shifts.  Vertical pass: consecutive filtered rows (16-bit values) are kept packed in pairs
-    // P[k] = (h[k], h[k+1]) so that 6 of the 7 taps are three 2-way dot products (DP2A) and the 7th one multiply-add.
-    const u32 KH0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);     // taps 0..3
-    const u32 KH1 = 48u | (34u << 8) | (18u << 16);                    // taps 4..6 (byte 3 = 0)
-    const u32 KV01 = 18u | (34u << 8), KV23 = 48u | (56u << 8), KV45 = 48u | (34u << 8);
-    u32 hp[7][4];      // ring of packed pairs: hp[k % 7][c] = h_k[c] | h_{k+1}[c] << 16
-    u32 hprev[4] = {0u, 0u, 0u, 0u};
+    // input row i (0 .. BLUR_RB + 7) is ROI row y0 + i - 3; output j uses inputs j .. j + 6; inputs come in groups of four
+    const u32 KA = 18u | (34u << 8) | (48u << 16) | (56u << 24);      // k0 k1 k2 k3
+    const u32 KB = 48u | (34u << 8) | (18u << 16);                     // k4 k5 k6 0
+    const u32 KC = (18u << 8) | (34u << 16) | (48u << 24);             // 0 k0 k1 k2
+    const u32 KD = 56u | (48u << 8) | (34u << 16) | (18u << 24);       // k3 k4 k5 k6
+    const u32 KE = (18u << 16) | (34u << 24);                          // 0 0 k0 k1
+    const u32 KF = 48u | (56u << 8) | (48u << 16) | (34u << 24);       // k2 k3 k4 k5
+    const u32 KG = 18u;                                                // k6 0 0 0
+    const u32 KH = 18u << 24;                                          // 0 0 0 k0
+    const u32 KI = 34u | (48u << 8) | (56u << 16) | (48u << 24);       // k1 k2 k3 k4
+    const u32 KJ = 34u | (18u << 8);                                   // k5 k6 0 0
+    u32 T[3][4];       // ring of byte-transposed groups: T[m % 3][c] = column c of inputs 4m .. 4m+3
 #pragma unroll
-    for (int r = 0; r < BLUR_RB + 6; ++r) {
-        const int by = min(y0 + r - 3 + ORB_EDGE, G.rows - 1);
-        const u32* row = src + (size_t)by * wpr;
-        const u32 A = row[w0];
-        const u32 X = lane < 2 ? row[wx] : 0u;
-        u32 B = __shfl_down_sync(0xffffffffu, A, 1);
-        u32 C = __shfl_down_sync(0xffffffffu, A, 2);
-        const u32 X0 = __shfl_sync(0xffffffffu, X, 0), X1 = __shfl_sync(0xffffffffu, X, 1);
-        if (lane == 31) { B = X0; C = X1; }
-        if (lane == 30) C = X0;
-        u32 hc[4];
+    for (int m = 0; m < BLUR_RB / 4 + 2; ++m) {
+        u32 A[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {   // output column c: source bytes c .. c+6 of the 12-byte window (A, B, C)
-            const u32 lo = c ? __funnelshift_r(A, B, 8 * c) : A;
-            const u32 hi = c ? __funnelshift_r(B, C, 8 * c) : B;
-            hc[c] = __dp4a(hi, KH1, __dp4a(lo, KH0, 0u));
+        for (int k = 0; k < 4; ++k) {
+            const int by = min(y0 + 4 * m + k - 3 + ORB_EDGE, G.rows - 1);
+            A[k] = src[(size_t)by * wpr + w0];
         }
-        if (r >= 1) {
+        const u32 t0 = __byte_perm(A[0], A[1], 0x5140), t1 = __byte_perm(A[2], A[3], 0x5140);     // (a.b0 b.b0 a.b1 b.b1)
+        const u32 t2 = __byte_perm(A[0], A[1], 0x7362), t3 = __byte_perm(A[2], A[3], 0x7362);     // (a.b2 b.b2 a.b3 b.b3)
+        T[m % 3][0] = __byte_perm(t0, t1, 0x5410); T[m % 3][1] = __byte_perm(t0, t1, 0x7632);
+        T[m % 3][2] = __byte_perm(t2, t3, 0x5410); T[m % 3][3] = __byte_perm(t2, t3, 0x7632);
+        if (m >= 2) {      // outputs 4(m-2) .. 4(m-2)+3 from groups m-2, m-1, m
+            const u32 (&G0)[4] = T[(m - 2) % 3];
+            const u32 (&G1)[4] = T[(m - 1) % 3];
+            const u32 (&G2)[4] = T[m % 3];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) hp[(r - 1) % 7][c] = hprev[c] | (hc[c] << 16);
-        }
-        if (r >= 6) {
-            const int y = y0 + r - 6;
-            u32 o = 0;
+            for (int p = 0; p < 4; ++p) {
+                u32 v[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {   // rows r-6 .. r: pairs (r-6,r-5), (r-4,r-3), (r-2,r-1) + row r
-                u32 acc = 18u * hc[c] + 32768u;
-                acc = __dp2a_lo(hp[(r - 6) % 7][c], KV01, acc);
-                acc = __dp2a_lo(hp[(r - 4) % 7][c], KV23, acc);
-                acc = __dp2a_lo(hp[(r - 2) % 7][c], KV45, acc);
-                o |= (acc >> 16) << (8 * c);
+                for (int c = 0; c < 4; ++c) {
+                    if (p == 0) v[c] = __dp4a(G1[c], KB, __dp4a(G0[c], KA, 0u));
+                    else if (p == 1) v[c] = __dp4a(G1[c], KD, __dp4a(G0[c], KC, 0u));
+                    else if (p == 2) v[c] = __dp4a(G2[c], KG, __dp4a(G1[c], KF, __dp4a(G0[c], KE, 0u)));
+                    else v[c] = __dp4a(G2[c], KJ, __dp4a(G1[c], KI, __dp4a(G0[c], KH, 0u)));
+                }
+                const u32 m01 = __byte_perm(v[0], v[1], 0x5410), m23 = __byte_perm(v[2], v[3], 0x5410);     // 16-bit sums in pairs
+                const u32 r01 = __shfl_down_sync(0xffffffffu, m01, 1), r23 = __shfl_down_sync(0xffffffffu, m23, 1);
+                const u32 q01 = __shfl_down_sync(0xffffffffu, m01, 2);
+                const u32 o = blur_out4(m01, m23, r01, r23, q01);
+                const int y = y0 + 4 * (m - 2) + p;
+                if (lane < 30 && y < G.h && x0 < G.w)   // blur pitch is a multiple of 64: the aligned 4-byte store may spill into padding only
+                    *reinterpret_cast<u32*>(dst + (size_t)y * G.blur_pitch + x0) = o;
             }
-            if (y < G.h && x0 < G.w)   // blur pitch is a multiple of 64: the aligned 4-byte store may spill into padding only
-                *reinterpret_cast<u32*>(dst + (size_t)y * G.blur_pitch + x0) = o;
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) hprev[c] = hc[c];
     }
 }
 
