@@ -552,11 +552,12 @@ def run_b200_arm(args):
         per_image["octree"] = 4 * ncand + 4 * nkp
         peak, peak_src = measured_peak()
         kernels = {}
-        launches_per_call = {"border0": 1, "resize_chain": ORB["nlevels"] - 1, "blur": 1, "fast_cells": 1, "octree": 1, "orient_describe": 1, "stereo": 2}
+        launches_per_call = fe.stage_launches()
         for k, tot in stage_ms.items():
             bytes_total = (stereo_pp * prof_pairs) if k == "stereo" else (per_image[k] * 2 * prof_pairs)
             gbs = bytes_total / (tot / 1e3) / 1e9 if tot > 0 else 0.0
-            kernels[k] = {"ms_total": tot, "share": tot / max(sum(stage_ms.values()), 1e-9), "avg_launch_ms": tot / max(prof_calls * launches_per_call[k], 1),
+            kernels[k] = {"ms_total": tot, "share": tot / max(sum(stage_ms.values()), 1e-9), "ms_per_chunk": tot / max(prof_calls, 1),
+                          "launches_per_chunk": launches_per_call[k], "avg_launch_ms": tot / max(prof_calls * launches_per_call[k], 1),
                           "algorithmic_bytes_per_launch": bytes_total / max(prof_calls * launches_per_call[k], 1), "achieved_gbs": gbs, "frac": gbs / peak}
         dom = max(stage_ms, key=stage_ms.get)
         try:       # static ncu figures of the same kernels (profiles/traffic.json, from the committed --set full capture)

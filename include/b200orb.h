@@ -184,6 +184,8 @@ int b200orb_batch_candidate_count(b200orb_batch* b, int n_images, long long* tot
 #define B200ORB_NSTAGE 7
 int b200orb_batch_profile(b200orb_batch* b, int enable, int max_calls);
 int b200orb_batch_profile_read(b200orb_batch* b, float* ms_per_stage, int* n_calls, long long* n_pairs);
+/* kernel launches per stage of one b200orb_batch_run_device call */
+int b200orb_batch_stage_launches(const b200orb_batch* b, int* launches_per_stage);
 
 /* ---------------------------------------------------------------------------------------------
  * BoW transform of the descriptors -- the tree descent of

@@ -61,6 +61,7 @@ def lib():
     l.b200orb_batch_status_host.argtypes = [vp, vp, i32]
     l.b200orb_batch_candidate_count.argtypes = [vp, i32, C.POINTER(C.c_longlong)]
     l.b200orb_batch_profile.argtypes = [vp, i32, i32]
+    l.b200orb_batch_stage_launches.argtypes = [vp, vp]
     l.b200orb_batch_profile_read.argtypes = [vp, vp, C.POINTER(i32), C.POINTER(C.c_longlong)]
     l.b200orb_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     l.b200orb_host_free.argtypes = [vp]

