@@ -419,34 +419,25 @@ def run_b200_arm(args):
     # ---- the host-copy ceiling of this box: the same bytes per chunk (pinned H2D of both views + D2H of every output array) with
     # no kernel at all, uploads and downloads on their own streams, all ranks at once.  e2e cannot exceed it; e2e / ceiling says how
     # much of what the host <-> device links deliver the pipeline uses ----
-    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    dbuf = [torch.empty((2, P, H, W), dtype=torch.uint8, device=dev) for _ in range(2)]
-    dout = fe.alloc_outputs(P)
-
-    def copy_only():
-        for k, c in enumerate(range(0, Be, P)):
-            n = min(P, Be - c)
-            with torch.cuda.stream(s_up):
-                dbuf[k & 1][0, :n].copy_(lh[c:c + n], non_blocking=True)
-                dbuf[k & 1][1, :n].copy_(rh[c:c + n], non_blocking=True)
-            with torch.cuda.stream(s_dn):
-                for key, v in oh.items():          # contiguous slices only: every copy is one cudaMemcpyAsync, like run_host's
-                    if key in ("kps", "desc", "nkp"):
-                        for side in (0, 1):
-                            v[side, c:c + n].copy_(dout[key][side, :n], non_blocking=True)
-                    else:
-                        v[c:c + n].copy_(dout[key][:n], non_blocking=True)
-    copy_only()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        copy_only()
-    torch.cuda.synchronize()
-    tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    fe.set_copy_only(True)                       # the very same C-ABI call: same copies, streams, events and buffers, no kernels
+    try:
+        fe.run_host(lh, rh, MBF, FX, out=oh)
+        barrier()
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                fe.run_host(lh, rh, MBF, FX, out=oh)
+            torch.cuda.synchronize()
+            tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            best = float(tc) if best is None else min(best, float(tc))
+            barrier()
+    finally:
+        fe.set_copy_only(False)
+    tc = best
     ceiling_value = world * Be * args.steps / float(tc)
-    del dbuf, dout
 
     # ---- latency of the reference-compatible single-frame API (config 2: what one Frame.__init__ costs) ----
     dropin = None

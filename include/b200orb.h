@@ -169,6 +169,10 @@ int b200orb_batch_run_host_shard(b200orb_batch* b, const uint8_t* h_left, const 
 int b200orb_batch_status_device(b200orb_batch* b, int n_pairs, void* stream, int32_t* pair_status);
 int b200orb_batch_status_host(const b200orb_batch* b, int32_t* pair_status, int n_pairs);
 
+/* measurement aid: with on != 0, b200orb_batch_run_host / _shard perform exactly their uploads, downloads, stream waits and events but
+ * launch no kernel -- the ceiling the host <-> device links of the box set for this traffic pattern (bench.py reports e2e against it) */
+int b200orb_batch_set_copy_only(b200orb_batch* b, int on);
+
 /* stereo options of the batched path (same flags as b200orb_stereo_ex; default 0 = the reference's behaviour) */
 int b200orb_batch_set_stereo_flags(b200orb_batch* b, int flags);
 

@@ -46,6 +46,7 @@ def lib():
     l.b200orb_stereo.argtypes = [vp, vp, f64, f32, vp, vp, vp]
     l.b200orb_stereo_ex.argtypes = [vp, vp, f64, f32, i32, vp, vp, vp, vp]
     l.b200orb_batch_set_stereo_flags.argtypes = [vp, i32]
+    l.b200orb_batch_set_copy_only.argtypes = [vp, i32]
     l.b200orb_stereo_host.argtypes = [i32, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, f64, f32, vp, vp, vp]
     l.b200orb_batch_create.argtypes = [i32, f32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(vp)]
     l.b200orb_batch_destroy.argtypes = [vp]

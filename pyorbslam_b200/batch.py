@@ -36,6 +36,10 @@ class StereoFrontend:
         """Opt-in upstream-ORB-SLAM2 behaviour (not the reference's): see B200ORB_STEREO_* in include/b200orb.h."""
         _lib.check(_lib.lib().b200orb_batch_set_stereo_flags(self._h, (1 if median_cull else 0) | (2 if dense_pyramid else 0)))
 
+    def set_copy_only(self, on=True):
+        """Measurement aid: run_host moves its bytes but launches no kernel (see b200orb_batch_set_copy_only)."""
+        _lib.check(_lib.lib().b200orb_batch_set_copy_only(self._h, int(bool(on))))
+
     def workspace_bytes(self):
         return int(_lib.lib().b200orb_batch_workspace_bytes(self._h))
 

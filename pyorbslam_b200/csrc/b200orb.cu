@@ -601,6 +601,7 @@ struct b200orb_batch {
     bool host_ready = false;
     long long host_bytes = 0;
     int* h_status = nullptr; int h_status_cap = 0, h_status_n = 0;   // pinned: per-pair range-error flags of the last run_host
+    int copy_only = 0;        // diagnostic: run_host moves its bytes but launches no kernel (host-link ceiling of the same traffic pattern)
     int status_bank = 0;      // which half of eng.d_status the next run_device uses (run_host: the chunk's slot, so that the
                               // previous chunk's flag download on the output stream never races with the next chunk's clear)
     int stereo_flags = 0;
@@ -1111,6 +1112,12 @@ int b200orb_batch_status_host(const b200orb_batch* b, int32_t* pair_status, int 
     return 0;
 }
 
+int b200orb_batch_set_copy_only(b200orb_batch* b, int on) {
+    if (!b) return fail(B200ORB_E_ARG, "NULL batch");
+    b->copy_only = on ? 1 : 0;
+    return 0;
+}
+
 int b200orb_batch_set_stereo_flags(b200orb_batch* b, int flags) {
     if (!b) return fail(B200ORB_E_ARG, "NULL batch");
     if (flags & ~(B200ORB_STEREO_MEDIAN_CULL | B200ORB_STEREO_DENSE_PYRAMID)) return fail(B200ORB_E_ARG, "unknown stereo flag");
@@ -1256,7 +1263,7 @@ int b200orb_batch_run_host_shard(b200orb_batch* b, const uint8_t* h_left, const 
         CU_TRY(cudaStreamWaitEvent(b->s_comp, b->ev_in[s], 0));
         if (k >= 2) CU_TRY(cudaStreamWaitEvent(b->s_comp, b->ev_out[s], 0));   // outputs of chunk k-2 downloaded
         b->status_bank = s;
-        const int rrc = b200orb_batch_run_device(b, b->d_in[s], b->d_in[s] + np * HW, (int)np, mbf, fx, b->d_kps[s], b->d_desc[s], b->d_nkp[s],
+        const int rrc = b->copy_only ? 0 : b200orb_batch_run_device(b, b->d_in[s], b->d_in[s] + np * HW, (int)np, mbf, fx, b->d_kps[s], b->d_desc[s], b->d_nkp[s],
                                                  b->d_uR[s], b->d_dep[s], b->d_mi[s], b->s_comp);
         b->status_bank = 0;
         if (rrc) return rrc;
