@@ -378,21 +378,41 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 8) k_stereo(const __grid_consta
                     const int pc = lin - pr * SG.plog[oL];
                     const u8* src = (left ? bl : br) + SG.base[oL] + (size_t)pr * SG.pitch[oL] + pc;
                     unsigned char* dst = left ? wl + r * 12 : wr + r * 24;
-                    if (pc + n <= SG.plog[oL] || SG.pitch[oL] == SG.plog[oL]) {
-                        const size_t addr = reinterpret_cast<size_t>(src);
-                        const u32* wp = reinterpret_cast<const u32*>(addr & ~(size_t)3);
-                        const int sh = 8 * (int)(addr & 3);
-                        u32* dw = reinterpret_cast<u32*>(dst);
-                        u32 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
-                        dw[0] = __funnelshift_r(w0, w1, sh); dw[1] = __funnelshift_r(w1, w2, sh); dw[2] = __funnelshift_r(w2, w3, sh);
+                    const size_t addr = reinterpret_cast<size_t>(src);
+                    const u32* wp = reinterpret_cast<const u32*>(addr & ~(size_t)3);
+                    const int sh = 8 * (int)(addr & 3);
+                    u32 v[6];
+                    {
+                        const u32 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+                        v[0] = __funnelshift_r(w0, w1, sh); v[1] = __funnelshift_r(w1, w2, sh); v[2] = __funnelshift_r(w2, w3, sh);
                         if (!left) {
-                            w0 = wp[4]; w1 = wp[5]; w2 = wp[6];
-                            dw[3] = __funnelshift_r(w3, w0, sh); dw[4] = __funnelshift_r(w0, w1, sh); dw[5] = __funnelshift_r(w1, w2, sh);
+                            const u32 w4 = wp[4], w5 = wp[5], w6 = wp[6];
+                            v[3] = __funnelshift_r(w3, w4, sh); v[4] = __funnelshift_r(w4, w5, sh); v[5] = __funnelshift_r(w5, w6, sh);
                         }
-                    } else {
-                        const int wrap = SG.pitch[oL] - SG.plog[oL];
-                        for (int k = 0; k < n; ++k) dst[k] = src[k + (pc + k >= SG.plog[oL] ? wrap : 0)];
                     }
+                    const int nfirst = SG.plog[oL] - pc, wrap = SG.pitch[oL] - SG.plog[oL];
+                    if (nfirst < n && wrap != 0) {
+                        // the row crosses the logical pitch: its bytes from nfirst on continue at the start of the next padded row, i.e.
+                        // `wrap` bytes further; fetch that stream the same way and take bytes >= nfirst from it
+                        const size_t addr2 = addr + (size_t)wrap;
+                        const u32* wq = reinterpret_cast<const u32*>(addr2 & ~(size_t)3);
+                        const int sh2 = 8 * (int)(addr2 & 3);
+                        const int nw = left ? 3 : 6;
+                        u32 prev = wq[0];
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            if (j >= nw) break;
+                            const u32 nxt = wq[j + 1];
+                            const u32 b = __funnelshift_r(prev, nxt, sh2);
+                            prev = nxt;
+                            const int keep = min(max(nfirst - 4 * j, 0), 4);              // bytes of word j that come before the wrap
+                            const u32 mask = keep >= 4 ? 0xffffffffu : ((1u << (8 * keep)) - 1u);
+                            v[j] = (v[j] & mask) | (b & ~mask);
+                        }
+                    }
+                    u32* dw = reinterpret_cast<u32*>(dst);
+                    dw[0] = v[0]; dw[1] = v[1]; dw[2] = v[2];
+                    if (!left) { dw[3] = v[3]; dw[4] = v[4]; dw[5] = v[5]; }
                 }
                 __syncwarp();
                 const int lc = wl[5 * 12 + 5];
