@@ -282,7 +282,7 @@ struct Engine {
     u8 *d_pyr = nullptr, *d_blur = nullptr;
     u32 *d_cand = nullptr, *d_scratch = nullptr, *d_lvlkp = nullptr;
     int *d_cellcnt = nullptr, *d_lvlcnt = nullptr, *d_status = nullptr, *d_rowstart = nullptr;
-    int4* d_rmeta = nullptr;
+    uint2* d_rmeta = nullptr;     // row-band index entries of the right keypoints: band_rows() x kp_total per pair
     unsigned char* d_octnodes = nullptr;     // node arrays of k_octree when they do not fit in shared memory
     unsigned char* d_roottab = nullptr;
     int* d_fastctr = nullptr;                // k_fast_cells: next unclaimed cell
@@ -368,7 +368,7 @@ struct Engine {
         TRY(alloc(&d_lvlcnt, (size_t)S * P.nlevels));
         TRY(alloc(&d_status, (size_t)2 * std::max(S, 1)));     // one range-error flag word per pair, two banks (run_host alternates them per chunk)
         TRY(alloc(&d_rowstart, (size_t)S * (P.lv[0].h + 1)));
-        TRY(alloc(&d_rmeta, (size_t)S * P.kp_total));
+        TRY(alloc(&d_rmeta, (size_t)std::max(S / 2, 1) * P.kp_total * band_rows()));
         if (hp.oct_global_nodes) TRY(alloc(&d_octnodes, (size_t)S * P.nlevels * hp.oct_node_stride));
         TRY(alloc(&d_fastctr, 1));
         TRY(alloc(&d_roottab, hp.roottab.size() + 16));
@@ -471,6 +471,12 @@ struct Engine {
         CU_TRY(cudaGetLastError());
         return 0;
     }
+    // upper bound of the rows one right keypoint is entered into: floor(y - 2s) .. ceil(y + 2s) at the coarsest level
+    int band_rows() const {
+        float smax = 1.f;
+        for (float v : prm.sf) smax = std::max(smax, v);
+        return 2 * (int)ceil(2.0 * smax) + 2;
+    }
     // flags: B200ORB_STEREO_DENSE_PYRAMID -> SAD windows on the true level image instead of the reference's sheared view
     void stereo_geom(StereoGeom& SG, int flags = 0) const {
         const Plan& P = hp.P;
@@ -501,12 +507,9 @@ void fill_stereo_consts(StereoArgs& A, double mbf, float fx) {
 // (nRows + 1) and idx_stride ints per pair of scratch.
 int launch_stereo(const StereoGeom& SG, StereoArgs A, int max_left, int pairs, cudaStream_t st, int flags = 0) {
     if (pairs < 1 || max_left < 1) return 0;
-    float smax = 1.f;
-    for (int l = 0; l < SG.nlevels; ++l) smax = std::max(smax, SG.sf[l]);
-    A.reach = (int)ceil(2.0 * smax) + 2;
     const size_t smem = (size_t)(2 * SG.nRows + 1) * sizeof(int);
     k_rowindex<<<pairs, RI_THREADS, smem, st>>>(A.kpsR, A.nR, A.kp_stride, A.n_stride, A.kp_row, A.oct_idx, SG, (int*)A.rowStart,
-                                                (int4*)A.rmeta, A.idx_stride, A.status, A.status_stride);
+                                                (uint2*)A.rmeta, A.idx_stride, A.status, A.status_stride);
     ++g_launches;
     dim3 grid((max_left + ST_WARPS - 1) / ST_WARPS, pairs);
     k_stereo<<<grid, ST_WARPS * 32, 0, st>>>(SG, A);
@@ -906,7 +909,7 @@ int b200orb_stereo_ex(b200orb_extractor* L, b200orb_extractor* R, double mbf, fl
     A.pyrL = L->eng.d_pyr; A.pyrR = R->eng.d_pyr;
     A.kp_row = 6; A.oct_idx = 5; A.out_stride = PL.kp_total;
     A.uRight = L->d_uR; A.depth = L->d_depth; A.matchIdx = L->d_match; A.status = L->d_sstatus; A.sadDist = L->d_sad;
-    A.rowStart = L->eng.d_rowstart; A.rmeta = L->eng.d_rmeta; A.idx_stride = PL.kp_total;
+    A.rowStart = L->eng.d_rowstart; A.rmeta = L->eng.d_rmeta; A.idx_stride = (long long)PL.kp_total * L->eng.band_rows();
     fill_stereo_consts(A, mbf, fx);
     const size_t C = (size_t)PL.kp_total;
     CU_TRY(cudaMemsetAsync(L->d_sstatus, 0, 4, L->st));
@@ -964,9 +967,12 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     HostStereoWS& ws = ws_map[device];
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t nR1 = (size_t)std::max(nRight, 1);
+    float smax_h = 1.f;
+    for (int l = 0; l < nlevels; ++l) smax_h = std::max(smax_h, sf[l]);
+    const size_t band = (size_t)(2 * (int)ceil(2.0 * smax_h) + 2);
     const size_t o_blob = 0, o_kL = o_blob + al((size_t)total * 2), o_dL = o_kL + al((size_t)nLeft * 12), o_kR = o_dL + al((size_t)nLeft * 32),
                  o_dR = o_kR + al(nR1 * 12), o_out = o_dR + al(nR1 * 32), o_n = o_out + al((size_t)nLeft * 12), o_rs = o_n + 256,
-                 o_rm = o_rs + al((size_t)(lh[0] + 1) * 4), need = o_rm + al(nR1 * 16);
+                 o_rm = o_rs + al((size_t)(lh[0] + 1) * 4), need = o_rm + al(nR1 * band * 8);
     if (need > ws.cap) {
         if (ws.base) cudaFree(ws.base);
         ws.base = nullptr; ws.cap = 0;
@@ -979,7 +985,7 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     float* d_kL = (float*)(ws.base + o_kL); u8* d_dL = ws.base + o_dL;
     float* d_kR = (float*)(ws.base + o_kR); u8* d_dR = ws.base + o_dR;
     float* d_u = (float*)(ws.base + o_out); float* d_d = d_u + nLeft; int* d_m = (int*)(d_d + nLeft);
-    int* d_n = (int*)(ws.base + o_n); int* d_rs = (int*)(ws.base + o_rs); int4* d_rm = (int4*)(ws.base + o_rm);
+    int* d_n = (int*)(ws.base + o_n); int* d_rs = (int*)(ws.base + o_rs); uint2* d_rm = (uint2*)(ws.base + o_rm);
     for (int l = 0; l < nlevels; ++l) {
         CU_TRY(cudaMemcpyAsync(d_blob + SG.base[l], pyrL[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemcpyAsync(d_blob + total + SG.base[l], pyrR[l], (size_t)lw[l] * lh[l], cudaMemcpyHostToDevice, st));
@@ -998,7 +1004,7 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     A.pyrL = d_blob; A.pyrR = d_blob + total;
     A.kp_row = 3; A.oct_idx = 2; A.out_stride = nLeft;
     A.uRight = d_u; A.depth = d_d; A.matchIdx = d_m; A.status = d_n + 2;
-    A.rowStart = d_rs; A.rmeta = d_rm; A.idx_stride = std::max(nRight, 1);
+    A.rowStart = d_rs; A.rmeta = d_rm; A.idx_stride = (long long)(nR1 * band);
     fill_stereo_consts(A, mbf, fx);
     TRY(launch_stereo(SG, A, nLeft, 1, st));
     int status = 0;
@@ -1079,7 +1085,7 @@ int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint
     A.uRight = d_uRight; A.depth = d_depth; A.matchIdx = d_matchIdx;
     A.status = b->eng.d_status + (size_t)b->status_bank * b->eng.S; A.status_stride = 1;   // flag word per pair, cleared here, read by b200orb_batch_status_device / run_host
     CU_TRY(cudaMemsetAsync(A.status, 0, (size_t)n_pairs * sizeof(int), st));
-    A.rowStart = b->eng.d_rowstart; A.rmeta = b->eng.d_rmeta; A.idx_stride = (int)C;
+    A.rowStart = b->eng.d_rowstart; A.rmeta = b->eng.d_rmeta; A.idx_stride = (long long)C * b->eng.band_rows();
     fill_stereo_consts(A, mbf, fx);
     if (b->stereo_flags & B200ORB_STEREO_MEDIAN_CULL) {
         if (!b->d_sad) CU_TRY(cudaMalloc((void**)&b->d_sad, (size_t)b->P * C * 4));

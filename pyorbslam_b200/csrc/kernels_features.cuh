@@ -203,20 +203,19 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
-// K7a: row index of the RIGHT keypoints (the GPU form of vRowIndices, Frame.py:170-179): counting sort of the
-// right keypoints by integer row into rowStart[nRows + 1] / rmeta[nR] (sorted order).  A left keypoint at row v then only
-// visits the bins v - R .. v + R (R = ceil(2 * max scale) + 2 covers every band) and applies the exact
-// floor(y - 2s) <= v <= ceil(y + 2s) test per candidate.  Order inside a bin is irrelevant: the winner is the
-// minimum of (dist << 20 | right index), which equals the reference's first strict minimum in ascending index.
-// One CTA per right image.
+// K7a: row index of the RIGHT keypoints -- the GPU form of vRowIndices (Frame.py:170-179), built like the reference builds it:
+// a right keypoint is entered into EVERY row of its band floor(y - 2s) .. ceil(y + 2s) (evaluated in double exactly like
+// Frame.py:173-176), so a left keypoint at row v reads one bin, rowStart[v] .. rowStart[v + 1], and every entry it finds already
+// passed the row test (visiting the +-10 neighbouring bins of a one-entry-per-keypoint index cost 2.3x more candidates, most of them
+// low-octave keypoints whose band is only 5 rows).  Counting sort over the bands: histogram, block scan, scatter; 8 bytes per
+// entry (uR, octave << 24 | index).  Order inside a bin is irrelevant: the winner is the minimum of (dist << 20 | right index),
+// which equals the reference's first strict minimum in ascending index.  One CTA per right image.
 // ------------------------------------------------------------------------------------------------
 #define RI_THREADS 256
-// It also writes, per SORTED position, the 16 bytes the matcher needs: uR, minr | maxr << 12 | octave << 24 and the keypoint index, where
-// minr = floor(y - 2s), maxr = ceil(y + 2s) are evaluated in double exactly like Frame.py:173-176.
 __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict__ kpsR, const int* __restrict__ nR, long long kp_stride,
                                                          int n_stride, int kp_row, int oct_idx, const __grid_constant__ StereoGeom SG,
-                                                         int* __restrict__ rowStart, int4* __restrict__ rmeta,
-                                                         int idx_stride, int* __restrict__ status, int status_stride) {
+                                                         int* __restrict__ rowStart, uint2* __restrict__ rmeta,
+                                                         long long idx_stride, int* __restrict__ status, int status_stride) {
     const int nRows = SG.nRows;
     extern __shared__ int ri_hist[];     // nRows + 1 counters, then nRows cursors
     __shared__ int ri_tmp[RI_THREADS / 32 + 1];
@@ -225,14 +224,20 @@ __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict
     const int n = nR[(size_t)pair * n_stride];
     const float* k = kpsR + (size_t)pair * kp_stride;
     int* rs = rowStart + (size_t)pair * (nRows + 1);
-    int4* rm = rmeta + (size_t)pair * idx_stride;
+    uint2* rm = rmeta + (size_t)pair * idx_stride;
     int* cursor = ri_hist + nRows + 1;
     for (int i = threadIdx.x; i <= nRows; i += RI_THREADS) ri_hist[i] = 0;
     __syncthreads();
+    auto band = [&](const float* r, int& minr, int& maxr, int& o) {
+        o = min(max((int)r[oct_idx], 0), SG.nlevels - 1);
+        const double y = (double)r[1], reach = 2.0 * (double)SG.sf[o];
+        minr = (int)floor(y - reach); maxr = (int)ceil(y + reach);
+    };
     for (int j = threadIdx.x; j < n; j += RI_THREADS) {
-        const int row = (int)k[(size_t)j * kp_row + 1];
-        if (row < 0 || row >= nRows) { atomicOr(status, 2); continue; }
-        atomicAdd(&ri_hist[row], 1);
+        int minr, maxr, o;
+        band(k + (size_t)j * kp_row, minr, maxr, o);
+        if (minr < 0 || maxr >= nRows) atomicOr(status, 2);      // vRowIndices[yi] leaves the list (the reference raises / wraps around)
+        for (int row = max(minr, 0); row <= min(maxr, nRows - 1); ++row) atomicAdd(&ri_hist[row], 1);
     }
     __syncthreads();
     // exclusive scan over nRows + 1 entries (the last one becomes the total)
@@ -256,13 +261,10 @@ __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict
     __syncthreads();
     for (int j = threadIdx.x; j < n; j += RI_THREADS) {
         const float* r = k + (size_t)j * kp_row;
-        const int row = (int)r[1];
-        const int o = min(max((int)r[oct_idx], 0), SG.nlevels - 1);
-        const double y = (double)r[1], reach = 2.0 * (double)SG.sf[o];
-        const int minr = min(max((int)floor(y - reach), 0), 4095), maxr = min(max((int)ceil(y + reach), 0), 4095);
-        if (row < 0 || row >= nRows) continue;
-        const int pos = atomicAdd(&cursor[row], 1);
-        rm[pos] = make_int4(__float_as_int(r[0]), minr | (maxr << 12) | (o << 24), j, 0);   // stored in SORTED order: one load per candidate
+        int minr, maxr, o;
+        band(r, minr, maxr, o);
+        const uint2 ent = make_uint2(__float_as_uint(r[0]), ((unsigned)o << 24) | (unsigned)j);
+        for (int row = max(minr, 0); row <= min(maxr, nRows - 1); ++row) rm[atomicAdd(&cursor[row], 1)] = ent;
     }
 }
 
@@ -287,8 +289,7 @@ struct StereoArgs {
     int n_stride;                                           // stride of nL / nR between pairs (ints)
     int kp_row, oct_idx;                                    // floats per keypoint row, index of the octave
     int out_stride;                                         // rows per pair in the outputs
-    const int* rowStart; const int4* rmeta; int idx_stride;   // row index + sorted metadata of the right keypoints (k_rowindex)
-    int reach;                                              // bins to visit on each side of the left keypoint's row
+    const int* rowStart; const uint2* rmeta; long long idx_stride;   // row index of the right keypoints (k_rowindex): bins + entries per pair
     float mbf32, mb, maxD;
     double mbf;
     float* uRight; float* depth; int* matchIdx;
@@ -326,14 +327,14 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 8) k_stereo(const __grid_consta
         const float minU = uL - A.maxD;
         const uint4* dl = reinterpret_cast<const uint4*>(dL + (size_t)iL * 32);
         const uint4 l0 = dl[0], l1 = dl[1];
-        const int c0 = rs[max(row - A.reach, 0)], c1 = rs[min(row + A.reach + 1, SG.nRows)];
-        const int4* rm = A.rmeta + (size_t)pair * A.idx_stride;
+        const int c0 = rs[row], c1 = rs[row + 1];                     // vRowIndices[int(vL)], Frame.py:192-194
+        const uint2* rm = A.rmeta + (size_t)pair * A.idx_stride;
         for (int c = c0 + lane; c < c1; c += 32) {
-            const int4 m = rm[c];
-            const int j = m.z;
-            const float uR = __int_as_float(m.x);
-            const int oR = m.y >> 24, minr = m.y & 0xfff, maxr = (m.y >> 12) & 0xfff;
-            if (row < minr || row > maxr || oR < oL - 1 || oR > oL + 1 || !(minU <= uR) || !(uR <= uL)) continue;
+            const uint2 m = rm[c];
+            const int j = (int)(m.y & 0xffffffu);
+            const float uR = __uint_as_float(m.x);
+            const int oR = (int)(m.y >> 24);
+            if (oR < oL - 1 || oR > oL + 1 || !(minU <= uR) || !(uR <= uL)) continue;      // Frame.py:209-215
             const uint4* dr = reinterpret_cast<const uint4*>(dR + (size_t)j * 32);
             const uint4 r0 = __ldg(dr), r1 = __ldg(dr + 1);
             const unsigned d = __popc(l0.x ^ r0.x) + __popc(l0.y ^ r0.y) + __popc(l0.z ^ r0.z) + __popc(l0.w ^ r0.w) +
