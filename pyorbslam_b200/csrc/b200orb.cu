@@ -366,7 +366,7 @@ struct Engine {
         TRY(alloc(&d_lvlkp, (size_t)S * P.kp_total));
         TRY(alloc(&d_cellcnt, (size_t)S * P.ncells));
         TRY(alloc(&d_lvlcnt, (size_t)S * P.nlevels));
-        TRY(alloc(&d_status, (size_t)2 * std::max(S, 1)));     // one range-error flag word per pair, two banks (run_host alternates them per chunk)
+        TRY(alloc(&d_status, (size_t)3 * std::max(S, 1)));     // one range-error flag word per pair, three banks (run_host: one per chunk in flight)
         TRY(alloc(&d_rowstart, (size_t)S * (P.lv[0].h + 1)));
         TRY(alloc(&d_rmeta, (size_t)std::max(S / 2, 1) * P.kp_total * band_rows()));
         if (hp.oct_global_nodes) TRY(alloc(&d_octnodes, (size_t)S * P.nlevels * hp.oct_node_stride));
@@ -380,7 +380,7 @@ struct Engine {
         TRY(alloc(&d_ytab, hp.ytab.size()));
         CU_TRY(cudaMemset(d_pyr, 0, (size_t)S * P.pyr_bytes));
         CU_TRY(cudaMemset(d_blur, 0, (size_t)S * P.blur_bytes));
-        CU_TRY(cudaMemset(d_status, 0, sizeof(int) * (size_t)2 * std::max(S, 1)));
+        CU_TRY(cudaMemset(d_status, 0, sizeof(int) * (size_t)3 * std::max(S, 1)));
         if (!hp.xtab.empty()) CU_TRY(cudaMemcpy(d_xtab, hp.xtab.data(), hp.xtab.size() * sizeof(XTab), cudaMemcpyHostToDevice));
         if (!hp.xgrp.empty()) CU_TRY(cudaMemcpy(d_xgrp, hp.xgrp.data(), hp.xgrp.size() * sizeof(XGroup), cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(d_mtab, hp.mtab.data(), hp.mtab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
@@ -597,10 +597,13 @@ struct b200orb_batch {
     int P = 0, H = 0, W = 0;
     // run_host pipeline state
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    u8* d_in[2] = {nullptr, nullptr};
-    float* d_kps[2] = {nullptr, nullptr}; u8* d_desc[2] = {nullptr, nullptr}; int* d_nkp[2] = {nullptr, nullptr};
-    float* d_uR[2] = {nullptr, nullptr}; float* d_dep[2] = {nullptr, nullptr}; int* d_mi[2] = {nullptr, nullptr};
+    // run_host keeps NBUF chunks in flight (upload k+2 | compute k+1 | download k): with upload and compute times about equal, a third
+    // buffer keeps the upload stream from waiting for the kernels of two chunks ago
+    static constexpr int NBUF = 3;
+    cudaEvent_t ev_in[NBUF] = {}, ev_comp[NBUF] = {}, ev_out[NBUF] = {};
+    u8* d_in[NBUF] = {};
+    float* d_kps[NBUF] = {}; u8* d_desc[NBUF] = {}; int* d_nkp[NBUF] = {};
+    float* d_uR[NBUF] = {}; float* d_dep[NBUF] = {}; int* d_mi[NBUF] = {};
     bool host_ready = false;
     long long host_bytes = 0;
     int* h_status = nullptr; int h_status_cap = 0, h_status_n = 0;   // pinned: per-pair range-error flags of the last run_host
@@ -1037,7 +1040,7 @@ void b200orb_batch_destroy(b200orb_batch* b) {
     b->eng.release();
     for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
     cudaFree(b->d_sad);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < b200orb_batch::NBUF; ++i) {
         cudaFree(b->d_in[i]); cudaFree(b->d_kps[i]); cudaFree(b->d_desc[i]); cudaFree(b->d_nkp[i]);
         cudaFree(b->d_uR[i]); cudaFree(b->d_dep[i]); cudaFree(b->d_mi[i]);
         if (b->ev_in[i]) cudaEventDestroy(b->ev_in[i]);
@@ -1200,7 +1203,7 @@ static int batch_host_setup(b200orb_batch* b) {
     CU_TRY(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&b->s_comp, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < b200orb_batch::NBUF; ++i) {
         CU_TRY(cudaEventCreateWithFlags(&b->ev_in[i], cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&b->ev_comp[i], cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&b->ev_out[i], cudaEventDisableTiming));
@@ -1260,14 +1263,14 @@ int b200orb_batch_run_host_shard(b200orb_batch* b, const uint8_t* h_left, const 
     }
     int p0 = 0;
     for (int k = 0; k < (int)sizes.size(); p0 += sizes[k], ++k) {
-        const int s = k & 1;
+        const int s = k % b200orb_batch::NBUF;
         const size_t np = (size_t)sizes[k];
-        if (k >= 2) CU_TRY(cudaStreamWaitEvent(b->s_in, b->ev_comp[s], 0));     // inputs of chunk k-2 consumed
+        if (k >= b200orb_batch::NBUF) CU_TRY(cudaStreamWaitEvent(b->s_in, b->ev_comp[s], 0));     // inputs of chunk k-NBUF consumed
         CU_TRY(cudaMemcpyAsync(b->d_in[s], h_left + (size_t)p0 * HW, np * HW, cudaMemcpyHostToDevice, b->s_in));
         CU_TRY(cudaMemcpyAsync(b->d_in[s] + np * HW, h_right + (size_t)p0 * HW, np * HW, cudaMemcpyHostToDevice, b->s_in));
         CU_TRY(cudaEventRecord(b->ev_in[s], b->s_in));
         CU_TRY(cudaStreamWaitEvent(b->s_comp, b->ev_in[s], 0));
-        if (k >= 2) CU_TRY(cudaStreamWaitEvent(b->s_comp, b->ev_out[s], 0));   // outputs of chunk k-2 downloaded
+        if (k >= b200orb_batch::NBUF) CU_TRY(cudaStreamWaitEvent(b->s_comp, b->ev_out[s], 0));   // outputs of chunk k-NBUF downloaded
         b->status_bank = s;
         const int rrc = b->copy_only ? 0 : b200orb_batch_run_device(b, b->d_in[s], b->d_in[s] + np * HW, (int)np, mbf, fx, b->d_kps[s], b->d_desc[s], b->d_nkp[s],
                                                  b->d_uR[s], b->d_dep[s], b->d_mi[s], b->s_comp);
