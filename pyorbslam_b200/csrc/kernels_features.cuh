@@ -76,8 +76,11 @@ __device__ __forceinline__ void glibc_sincosf(float y, float* sp, float* cp) {
 // ------------------------------------------------------------------------------------------------
 #define DESC_WARPS 8
 #define DESC_KPW 8     // keypoints per warp
-#define DESC_PP 64     // pitch of the staged descriptor window = width of its TMA box (37 columns + up to 15 bytes of alignment shift)
-#define DESC_WIN (19 * 128)   // bytes per warp: 37 rows x 64, rounded up to the 128-byte alignment a TMA destination needs
+// pitch of the staged descriptor window = width of its TMA box: 37 columns + up to 15 bytes of alignment shift need 52; 80 rather
+// than 64 because with 16-word rows the samples of a warp (clustered around the window centre, ~10 words wide) only ever touch ~20 of the
+// 32 banks (ncu: 4.75 wavefronts per sample load); 20-word rows walk through all banks with a period of 8 rows
+#define DESC_PP 80
+#define DESC_WIN (24 * 128)   // bytes per warp: 37 rows x 80, rounded up to the 128-byte alignment a TMA destination needs
 __device__ __forceinline__ int dp4a_us(u32 a_u8x4, u32 b_s8x4, int c) {     // unsigned bytes x signed bytes
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
