@@ -160,6 +160,28 @@ def _elem_float_dtype(values):
     return dt
 
 
+def _frame_arrays(frame):
+    """Array views of a frame's immutable-after-construction data (undistorted keypoints, grid, mvuRight), built once per frame and
+    kept on the frame object: TrackWithMotionModel and SearchLocalPoints query the same current frame several times.  The key is the
+    identity of the three list objects (Frame.__init__ assigns them once, Frame.py:57-70)."""
+    key = (id(frame.mvKeysUn), id(frame.mGrid), id(frame.mvuRight), frame.N)
+    c = getattr(frame, "_b200orb_arrays", None)
+    if c is None or c["key"] != key:
+        cs, ci = _grid_csr(frame)
+        ur_list = frame.mvuRight
+        c = {"key": key,
+             "kxy": np.array([k.pt for k in frame.mvKeysUn], np.float32).reshape(-1, 2),
+             "koct": np.array([k.octave for k in frame.mvKeysUn], np.int32),
+             "cs": cs, "ci": ci,
+             "ur_el": _elem_float_dtype(ur_list),
+             "ur": np.array([float(v) for v in ur_list], np.float64)}
+        try:
+            frame._b200orb_arrays = c
+        except AttributeError:      # frames with __slots__: no cache
+            pass
+    return c
+
+
 def _grid_csr(frame):
     """frame.mGrid (Frame.assign_features_to_grid, Frame.py:153-159) as CSR over cell ix * rows + iy."""
     cols, rows = frame.FRAME_GRID_COLS, frame.FRAME_GRID_ROWS
@@ -202,10 +224,9 @@ def _area_hamming(frame, qx, qy, qr, qlvl, qdesc, device=0):
     start = np.zeros(M + 1, np.int32)
     if M == 0 or frame.N == 0:
         return start, np.zeros(0, np.int32), np.zeros(0, np.int32)
-    kxy = np.array([k.pt for k in frame.mvKeysUn], np.float32).reshape(-1, 2)
-    koct = np.array([k.octave for k in frame.mvKeysUn], np.int32)
+    fa = _frame_arrays(frame)
+    kxy, koct, cs, ci = fa["kxy"], fa["koct"], fa["cs"], fa["ci"]
     kdesc = np.ascontiguousarray(frame.mDescriptors, np.uint8).reshape(-1, 32)
-    cs, ci = _grid_csr(frame)
     f32 = qx.dtype == np.float32
     qcell = _cell_ranges(frame, qx, qy, qr)
     qxyr = np.ascontiguousarray(np.stack([qx.astype(np.float64), qy.astype(np.float64),
@@ -237,10 +258,9 @@ def _right_ok(frame, start, idx, q_xr, q_rad):
     n = len(idx)
     if n == 0:
         return np.ones(0, np.uint8)
-    ur_list = frame.mvuRight
-    el = _elem_float_dtype(ur_list)
+    fa = _frame_arrays(frame)
+    el, ur = fa["ur_el"], fa["ur"]
     dt = q_xr.dtype if el is None else np.result_type(q_xr.dtype, el)
-    ur = np.array([float(v) for v in ur_list], np.float64)
     has_r = ur[idx] > 0
     per_q = np.repeat(np.arange(len(start) - 1), np.diff(start))
     er = np.abs(q_xr.astype(dt)[per_q] - ur.astype(dt)[idx])
@@ -259,8 +279,9 @@ def _homogeneous(vals):
 
 def search_by_projection_f_f(self, current_frame, last_frame, th):
     """ORBMatcher.search_by_projection_f_f, ORBMatcher.py:291-393 (TrackWithMotionModel).
-    The projections run exactly as in the reference (same scalar NumPy expressions); all window queries and descriptor distances
-    are one GPU call (b200orb_area_hamming), the order-dependent selection one host call (b200orb_greedy_project_ff)."""
+    The projections of all map points are one stacked 3x3 @ 3x1 matmul plus elementwise expressions of the same dtype as the
+    reference's scalar ones (bit-identical, self-checked per call); all window queries and descriptor distances are one GPU call
+    (b200orb_area_hamming), the order-dependent selection one host call (b200orb_greedy_project_ff)."""
     Rcw = current_frame.mTcw[:3, :3]
     tcw = current_frame.mTcw[:3, 3:4]
     twc = -Rcw.T @ tcw
@@ -269,38 +290,40 @@ def search_by_projection_f_f(self, current_frame, last_frame, th):
     tlc = Rlw @ twc + tlw
     b_forward = tlc[2] > current_frame.mb
     b_backward = -tlc[2] > current_frame.mb
-    qi, qu, qv, qrad, qlvl, qxr, qmp = [], [], [], [], [], [], []
     fx, fy, cx, cy, mbf = current_frame.fx, current_frame.fy, current_frame.cx, current_frame.cy, current_frame.mbf
     x0, x1, y0, y1 = current_frame.mnMinX, current_frame.mnMaxX, current_frame.mnMinY, current_frame.mnMaxY
     sf = current_frame.mvScaleFactors
-    for i in range(last_frame.N):
-        pMP = last_frame.mvpMapPoints[i]
-        if not pMP or last_frame.mvbOutlier[i]:
-            continue
-        x3Dc = Rcw @ pMP.get_world_pos() + tcw
-        xc, yc, zc = x3Dc[0][0], x3Dc[1][0], x3Dc[2][0]
-        invzc = 1.0 / zc
-        if invzc < 0:
-            continue
+    cand = [i for i in range(last_frame.N) if last_frame.mvpMapPoints[i] and not last_frame.mvbOutlier[i]]      # ORBMatcher.py:299-303
+    if not cand or current_frame.N == 0:
+        return 0
+    mps = [last_frame.mvpMapPoints[i] for i in cand]
+    Pw = np.stack([np.asarray(mp.get_world_pos()) for mp in mps])             # [n, 3, 1]
+    # x3Dc = Rcw @ pos + tcw for all points as ONE stacked matmul: NumPy runs the same 3x3 @ 3x1 routine per slice, so the results
+    # are the per-point ones bit for bit (an einsum or a hand-written sum is NOT: different association / contraction).  Checked on
+    # the first points of every call; if this NumPy build ever disagrees, the per-point expression of the reference is used.
+    X = np.matmul(Rcw[None], Pw) + tcw[None]
+    nchk = min(len(cand), 4)
+    if not all(np.array_equal(X[j], Rcw @ Pw[j] + tcw) for j in range(nchk)):
+        X = np.stack([Rcw @ p + tcw for p in Pw])
+    xc, yc, zc = X[:, 0, 0], X[:, 1, 0], X[:, 2, 0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        invzc = 1.0 / zc                                                       # ORBMatcher.py:313
         u = fx * xc * invzc + cx
         v = fy * yc * invzc + cy
-        if u < x0 or u > x1:
-            continue
-        if v < y0 or v > y1:
-            continue
-        octave = last_frame.mvKeys[i].octave
-        qi.append(i); qu.append(u); qv.append(v); qrad.append(th * sf[octave]); qmp.append(pMP)
-        qlvl.append((octave, -1) if b_forward else ((0, octave) if b_backward else (octave - 1, octave + 1)))
-        qxr.append(u - mbf * invzc)
-    M = len(qi)
-    if M == 0 or current_frame.N == 0:
+        keep = ~(invzc < 0) & ~((u < x0) | (u > x1)) & ~((v < y0) | (v > y1))  # the three `continue`s, ORBMatcher.py:314-323
+    sel = np.nonzero(keep)[0]
+    M = len(sel)
+    if M == 0:
         return 0
-    if not (_homogeneous(qu) and _homogeneous(qv) and _homogeneous(qxr)):
-        raise TypeError("projected coordinates of mixed scalar types")
-    qu, qv, qxr = np.array(qu), np.array(qv), np.array(qxr)
+    qi = [cand[j] for j in sel.tolist()]
+    qmp = [mps[j] for j in sel.tolist()]
+    octs = [last_frame.mvKeys[i].octave for i in qi]
+    qu, qv = np.ascontiguousarray(u[sel]), np.ascontiguousarray(v[sel])
+    qxr = qu - mbf * invzc[sel]                                                # ORBMatcher.py:347 (same dtype as the scalar expression)
+    qrad = np.array([th * sf[o] for o in octs], np.float64)
+    qlvl = [(o, -1) if b_forward else ((0, o) if b_backward else (o - 1, o + 1)) for o in octs]
     if qu.dtype != qv.dtype or qu.dtype not in (np.float32, np.float64):
-        raise TypeError("projected coordinates must be float32 or float64 scalars")
-    qrad = np.array(qrad, np.float64)
+        raise TypeError("projected coordinates must be float32 or float64")
     qdesc = np.stack([np.asarray(mp.get_descriptor(), np.uint8).reshape(32) for mp in qmp])
     start, idx, dist = _area_hamming(current_frame, qu, qv, qrad, np.array(qlvl, np.int32), qdesc)
     ok = _right_ok(current_frame, start, idx, qxr, qrad)
@@ -362,7 +385,7 @@ def search_by_projection_f_p(self, frame, vp_map_points, th):
     ok = _right_ok(frame, start, idx, qxr, qrad)
     occ = _occupied(frame)
     marks = np.array([1 if mp.observations() > 0 else 0 for mp in qmp], np.uint8)
-    koct = np.array([k.octave for k in frame.mvKeysUn], np.int32)
+    koct = _frame_arrays(frame)["koct"]
     best = np.empty(M, np.int32)
     l = _lib.lib()
     l.b200orb_greedy_project_fp.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
