@@ -114,7 +114,7 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
     P.nlevels = prm.nlevels; P.H = H; P.W = W; P.iniTh = prm.iniTh; P.minTh = prm.minTh;
     for (int v = 0; v < 16; ++v) P.umax[v] = prm.umax[v];
     hp.xtab.clear(); hp.ytab.clear(); hp.xgrp.clear(); hp.roottab.clear();
-    int pyr = 0, blr = 0, cells = 0, cand = 0, kpt = 0, fctas = 0, bctas = 0, maxw = 0, maxh = 0, maxcap = 0, maxcells = 0;
+    int pyr = 0, blr = 0, cells = 0, cand = 0, kpt = 0, bctas = 0, maxw = 0, maxh = 0, maxcap = 0, maxcells = 0;
     for (int l = 0; l < prm.nlevels; ++l) {
         LevelGeom& G = P.lv[l];
         G.w = cv_round_f((float)W * prm.isf[l]);       // ORBextractor.cpp:1110-1111
@@ -138,8 +138,6 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
         G.cell_ofs = cells; cells += nRows * nCols;
         G.cell_cap = nRows ? ((G.wCell + 1) / 2) * ((G.hCell + 1) / 2) : 0;   // strict 8-neighbour maxima: <= 1 per 2x2 block
         G.cand_ofs = cand; cand += round_up(nRows * nCols * G.cell_cap, 4);
-        G.fast_groups = (nCols + FAST_WARPS - 1) / FAST_WARPS;
-        G.fast_cta_ofs = fctas; fctas += nRows * G.fast_groups;
         G.blur_tiles_x = (G.w + BLUR_TW - 1) / BLUR_TW;
         G.blur_cta_ofs = bctas; bctas += G.blur_tiles_x * ((G.h + BLUR_TH - 1) / BLUR_TH);
         G.quota = prm.quota[l];
@@ -239,7 +237,7 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
                 hp.mtab[(al * MOM_STEPS + i) * 32 + lane] = make_uint2(cu, cv);
             }
     P.pyr_bytes = pyr; P.blur_bytes = blr; P.ncells = std::max(cells, 1); P.cand_entries = std::max(cand, 4);
-    P.kp_total = std::max(kpt, 1); P.fast_ctas = fctas; P.blur_ctas = bctas; P.max_cells_level = maxcells;
+    P.kp_total = std::max(kpt, 1); P.blur_ctas = bctas; P.max_cells_level = maxcells;
     hp.fast_SP = round_up(15 + maxw + 6, 16);  // TMA box: starts at the 16-byte boundary below the window, width a multiple of 16
     hp.fast_SR = maxh + 6;
     hp.fast_TP = round_up(maxw + 2, 4);

@@ -17,7 +17,6 @@ struct LevelGeom {
     int cell_ofs;           // first cell of this level in the slot's cell-count array
     int cell_cap;           // candidate capacity of one cell
     int cand_ofs;           // u32 index of the level's candidate storage in the slot's candidate blob
-    int fast_cta_ofs, fast_groups;    // first FAST CTA of the level; CTAs per cell row
     int blur_cta_ofs, blur_tiles_x;
     int quota;              // mnFeaturesPerLevel
     int kp_ofs, kp_cap;     // level segment in the slot's level-keypoint array
@@ -34,7 +33,7 @@ struct Plan {
     int pyr_bytes, blur_bytes;   // per slot
     int ncells, cand_entries;    // per slot
     int kp_total;                // per slot: sum of kp_cap == row capacity of the output arrays
-    int fast_ctas, blur_ctas;
+    int blur_ctas;
     int max_cells_level;         // largest cell count of one level
     int umax[16];
     LevelGeom lv[ORB_MAX_LEVELS];

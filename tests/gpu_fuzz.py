@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle as O  # noqa: E402
 from pyorbslam_b200 import ORBextractor  # noqa: E402
 from pyorbslam_b200.stereo import stereo_resident  # noqa: E402
-from pyorbslam_b200.synthetic import make_stereo_pair  # noqa: E402
+from pyorbslam_b200.synthetic import make_kitti_like_pair, make_stereo_pair  # noqa: E402
 
 
 def run(seed=0, ncase=100, verbose=True):
@@ -25,8 +25,10 @@ def run(seed=0, ncase=100, verbose=True):
         nlev = int(rng.integers(1, 9)); sf = float(rng.choice([1.1, 1.2, 1.2, 1.25, 1.3, 1.41, 1.5, 1.8, 2.0]))
         while min(H, W) / sf ** (nlev - 1) < 70: nlev -= 1
         nf = int(rng.choice([50, 300, 1000, 2000, 4000])); ini = int(rng.choice([20, 20, 12, 30, 7])); mn = int(rng.choice([7, 7, 5, 3, 12]))
-        kind = rng.integers(0, 4)
-        if kind == 0:
+        kind = rng.integers(0, 5)
+        if kind == 4:
+            L, R = make_kitti_like_pair(int(rng.integers(0, 10 ** 6)), H, W)      # the bench's scenes
+        elif kind == 0:
             L, R = make_stereo_pair(int(rng.integers(0, 10 ** 6)), H, W)
         elif kind == 1:
             L = rng.integers(0, 256, (H, W), dtype=np.uint8); R = np.roll(L, -int(rng.integers(1, 40)), axis=1)
@@ -89,7 +91,8 @@ def run_batch(seed=0, ncase=10, pairs=9, verbose=True):
             eL, eR = ORBextractor(*params, reuse_identical_input=False), ORBextractor(*params, reuse_identical_input=False)
         except ValueError:
             continue
-        ps = [make_stereo_pair(int(rng.integers(0, 10 ** 6)), H, W) for _ in range(pairs)]
+        gen = make_kitti_like_pair if c % 2 else make_stereo_pair
+        ps = [gen(int(rng.integers(0, 10 ** 6)), H, W) for _ in range(pairs)]
         out = fe.run(torch.from_numpy(np.stack([p[0] for p in ps])).cuda(), torch.from_numpy(np.stack([p[1] for p in ps])).cuda(), 386.1448, 718.856)
         torch.cuda.synchronize()
         nk = out["nkp"].cpu().numpy()
