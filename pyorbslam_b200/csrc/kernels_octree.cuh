@@ -174,9 +174,11 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
         keys[0] = base; keys[1] = base + (size_t)nCells * G.cell_cap;
     }
     const u32* csrc = cand + (size_t)slot * P.cand_entries + G.cand_ofs;
-    for (int c = warp; c < nCells; c += OCT_WARPS) {
-        const int n = ccnt[c], o = cellOfs[c];
-        for (int k = lane; k < n; k += 32) keys[1][o + k] = csrc[(size_t)c * G.cell_cap + k];
+    // eight lanes per cell (a cell holds ~7 candidates on average, its segment up to cell_cap): four cells per warp step, their loads
+    // independent; a cell's count is the difference of its scanned offsets, not another global read
+    for (int c = warp * 4 + (lane >> 3); c < nCells; c += OCT_WARPS * 4) {
+        const int o = cellOfs[c], n = (c + 1 < nCells ? cellOfs[c + 1] : K) - o;
+        for (int k = lane & 7; k < n; k += 8) keys[1][o + k] = csrc[(size_t)c * G.cell_cap + k];
     }
     __syncthreads();
 
