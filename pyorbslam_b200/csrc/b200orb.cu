@@ -961,11 +961,13 @@ int b200orb_stereo_host(int device, int nLeft, const float* kpsL, const uint8_t*
     // Device scratch of this entry point is cached per device and only grows (the first version paid eleven cudaMalloc / cudaFree
     // pairs per call -- ~10 ms before any work).  One arena, carved into 256-byte aligned pieces; the uploads are plain copies of the
     // caller's (pageable) arrays.
-    struct HostStereoWS { u8* base = nullptr; size_t cap = 0; cudaStream_t st = nullptr; };
+    struct HostStereoWS { std::mutex mu; u8* base = nullptr; size_t cap = 0; cudaStream_t st = nullptr; };
     static std::mutex ws_mutex;
     static std::map<int, HostStereoWS> ws_map;
-    std::lock_guard<std::mutex> guard(ws_mutex);
-    HostStereoWS& ws = ws_map[device];
+    HostStereoWS* wsp;
+    { std::lock_guard<std::mutex> g(ws_mutex); wsp = &ws_map[device]; }      // std::map nodes are stable
+    HostStereoWS& ws = *wsp;
+    std::lock_guard<std::mutex> guard(ws.mu);                                 // calls on one device are serialised, devices run side by side
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t nR1 = (size_t)std::max(nRight, 1);
     float smax_h = 1.f;
