@@ -379,6 +379,31 @@ def run_b200_arm(args):
     fe.set_stereo_options()
     del od
 
+    # ---- checker leg: a few frames of the timed batch itself against the CPU oracle (bit-exact keypoints, descriptors, matches) ----
+    oracle_check = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle as O                    # the oracle is the checker here, never the thing measured
+        prm = (ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"])
+        picked, same_all = [0, B // 2 + 3, B - 1], True
+        for i in picked:
+            ci, k = i // P, i % P
+            o = outs[ci]
+            Li, Ri = left[i].cpu().numpy(), right[i].cpu().numpy()
+            oL, oR = O.OracleExtractor(*prm), O.OracleExtractor(*prm)
+            kL, dL = oL.extract_arrays(Li)
+            kR, dR = oR.extract_arrays(Ri)
+            nl, nr = int(o["nkp"][0, k]), int(o["nkp"][1, k])
+            ok = (nl, nr) == (len(kL), len(kR))
+            if ok:
+                ok = (np.array_equal(o["kps"][0, k, :nl].cpu().numpy().view(np.uint32), kL.view(np.uint32)) and np.array_equal(o["desc"][0, k, :nl].cpu().numpy(), dL)
+                      and np.array_equal(o["kps"][1, k, :nr].cpu().numpy().view(np.uint32), kR.view(np.uint32)) and np.array_equal(o["desc"][1, k, :nr].cpu().numpy(), dR))
+            if ok:
+                ou, od, oi, _ = O.stereo(kL[:, [0, 1, 5]], dL, kR[:, [0, 1, 5]], dR, oL.sf, oL.isf, oL.GetImagePyramid(), oR.GetImagePyramid(), MBF, FX)
+                ok = (np.array_equal(o["uRight"][k, :nl].cpu().numpy().view(np.uint32), ou.view(np.uint32)) and np.array_equal(o["depth"][k, :nl].cpu().numpy().view(np.uint32), od.view(np.uint32))
+                      and np.array_equal(o["matchIdx"][k, :nl].cpu().numpy(), oi))
+            same_all = same_all and bool(ok)
+        oracle_check = {"frames_of_the_timed_batch": picked, "bit_exact_vs_oracle": same_all}
+
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -596,6 +621,7 @@ def run_b200_arm(args):
                                        "scenes match like upstream ORB-SLAM2 on KITTI",
                                "workspace_bytes": sum(f.workspace_bytes() for f in fes), "rank0_cpu_affinity": numa if isinstance(numa, str) else f"{len(numa)} cpus: {numa[0]}-{numa[-1]}"},
         }
+        line["oracle_check"] = oracle_check
         line["dropin_single_frame_latency"] = dropin
         line["other_baseline_configs"] = other_configs
         line["bow_transform_8f_rank2"] = bow_extra
