@@ -349,22 +349,23 @@ def run_b200_arm(args):
     ms = e0.elapsed_time(e1)
     launches = _lib.kernel_launches() - l0
     clk = clocks.stop()
-    # ---- per-stage pass (not part of `value`): the same steps again with CUDA events recorded between the stages on the launching
-    # stream ----
-    for f in fes:
-        f.profile(True, max_calls=args.steps * len(chunks))
+    # ---- per-stage pass (not part of `value`): the same chunks again, one at a time on ONE stream, with CUDA events recorded between
+    # the stages on the launching stream -- with `--streams` > 1 the timed region above overlaps consecutive chunks, so the stage
+    # times below add up to more than ms_per_step / chunks ----
+    fe.profile(True, max_calls=args.steps * len(chunks))
     for _ in range(args.steps):
-        step()
+        for (c, n), o in zip(chunks, outs):
+            fe.run(left[c:c + n], right[c:c + n], MBF, FX, out=o)
     barrier()
     stage_ms, prof_calls, prof_pairs = {}, 0, 0
-    for f in fes:
+    for f in fes[:1]:
         sm_, pc_, pp_ = f.profile_read()
         f.profile(False)
         for k_, v_ in sm_.items():
             stage_ms[k_] = stage_ms.get(k_, 0.0) + v_
         prof_calls += pc_
         prof_pairs += pp_
-    last_fe = fes[(len(chunks) - 1) % NS]
+    last_fe = fe
     ncand = last_fe.candidate_count(2 * chunks[-1][1]) / (2 * chunks[-1][1])
     nkp = float(torch.cat([o["nkp"].float().flatten() for o in outs]).mean())
     valid = [torch.arange(fe.capacity, device=dev)[None, :] < o["nkp"][0][:, None] for o in outs]
@@ -805,7 +806,7 @@ def main():
     ap.add_argument("--base-pairs", type=int, default=16, help="distinct synthetic scenes per rank")
     ap.add_argument("--e2e-pairs", type=int, default=2048, help="pairs per end-to-end step, capped at --pairs; the same at every --gpus "
                     "(pinned host memory: 0.93 MB in + 0.25 MB out per pair and rank)")
-    ap.add_argument("--streams", type=int, default=1, help="front-ends running consecutive chunks concurrently (own workspace + stream each)")
+    ap.add_argument("--streams", type=int, default=2, help="front-ends running consecutive chunks concurrently (own workspace + stream each)")
     ap.add_argument("--scenes", default="kitti_like", choices=["kitti_like", "layered"], help="synthetic scene generator (pyorbslam_b200/synthetic.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-other-configs", action="store_true", help="skip the config 1 / 4 / 5 side measurements (fixture image, hires, stereo-only sweep)")

@@ -13,6 +13,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200orb.h"
@@ -36,6 +37,22 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define TRY(expr) do { int _r = (expr); if (_r != 0) return _r; } while (0)
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Launch with programmatic stream serialization (see pdl_enter() in kernels_image.cuh): the kernel may start placing CTAs while the
+// previous kernel of the stream drains; it blocks in griddepcontrol.wait until that kernel has completed.
+// B200ORB_PDL: bit mask of the kernels launched that way (1 border0, 2 resize, 4 blur, 8 FAST, 16 octree, 32 describe, 64 row index, 128 stereo)
+int g_pdl = [] { const char* v = getenv("B200ORB_PDL"); return v ? atoi(v) : 2; }();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_seq(int pdl_bit, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (g_pdl & pdl_bit) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 inline int cv_round_f(float v) { return (int)lrintf(v); }
 
 // ------------------------------------------------------------------------------------------------
@@ -94,6 +111,7 @@ struct HostPlan {
     std::vector<uint2> mtab;      // IC_Angle coefficient table, see k_describe
     std::vector<YTab> ytab;
     std::vector<unsigned char> roottab;   // k_octree: root index of every candidate column, per level
+    std::vector<uint4> celltab;           // k_fast_cells: geometry of every cell of one image (see fast_cell_geom)
     int rs_gA_lo[ORB_MAX_LEVELS] = {0}, rs_gA_n[ORB_MAX_LEVELS] = {0}, rs_gB_n[ORB_MAX_LEVELS] = {0};   // k_resize: interior / border column groups
     int fast_SP = 0, fast_SR = 0, fast_TP = 0, fast_TR = 0, fast_LC = 0, fast_RQ = 0, fast_cells = 0, fast_WS = 0;
     LevelMaps maps;               // TMA tensor maps of the pyramid levels (k_fast_cells), rebuilt by Engine::plan
@@ -238,13 +256,32 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
             }
     P.pyr_bytes = pyr; P.blur_bytes = blr; P.ncells = std::max(cells, 1); P.cand_entries = std::max(cand, 4);
     P.kp_total = std::max(kpt, 1); P.blur_ctas = bctas; P.max_cells_level = maxcells;
+    // the FAST kernel counts columns from the 4-byte boundary at or below the window's first pixel: up to 3 more than the cell is wide
+    const int maxwa = maxw + 3;
     hp.fast_SP = round_up(15 + maxw + 6, 16);  // TMA box: starts at the 16-byte boundary below the window, width a multiple of 16
     hp.fast_SR = maxh + 6;
-    hp.fast_TP = round_up(maxw + 2, 4);
+    hp.fast_TP = round_up(maxwa + 2, 4);
     hp.fast_TR = round_up(maxh + 2, 4);       // TP * TR is a multiple of 16: the tiles are cleared with 128-bit stores
-    if (maxw > 63 || maxh > 63) return fail(B200ORB_E_ARG, "FAST cell larger than 63 px (level narrower than 62 px after the border?)");
+    // wCell = ceil(width / floor(width / 30)) <= 59 whenever the level has cells at all
+    if (maxwa > 64 || maxh > 63) return fail(B200ORB_E_ARG, "FAST cell larger than 61 x 63 px");
     hp.fast_LC = round_up(std::max(maxw * maxh, 2), 8);            // 16-byte multiple
-    hp.fast_RQ = 2 * round_up(std::max(maxh, 1), 4) * (maxw > 32 ? 16 : 8);   // per warp: rows x quads x (min | ini nibble pair)
+    hp.fast_RQ = 2 * round_up(std::max(maxh, 1), 4) * (maxwa > 32 ? 16 : 8);   // per warp: rows x quads x (min | ini nibble pair)
+    // cell table (ORBextractor.cpp:783-806): window origin, detection size, level and candidate offset of every cell of an image
+    hp.celltab.assign(std::max(cells, 1), make_uint4(0u, 0u, 0u, 0u));
+    for (int l = 0; l < P.nlevels; ++l) {
+        const LevelGeom& G = P.lv[l];
+        for (int ci = 0; ci < G.nRows; ++ci)
+            for (int j = 0; j < G.nCols; ++j) {
+                const int local = ci * G.nCols + j;
+                const int iniY = ORB_DET_ORIGIN + ci * G.hCell, iniX = ORB_DET_ORIGIN + j * G.wCell;
+                const int maxY = std::min(iniY + G.hCell + 6, G.maxBY), maxX = std::min(iniX + G.wCell + 6, G.maxBX);
+                int cw = maxX - iniX - 6, ch = maxY - iniY - 6;              // detection window (FAST skips a 3-px rim)
+                if (iniY >= G.maxBY - 3 || iniX >= G.maxBX - 6 || ch <= 0 || cw <= 0) { cw = 0; ch = 0; }   // :793,801 / image < 7 px
+                if (iniX > 0xffff || iniY > 0xffff) return fail(B200ORB_E_ARG, "image too large for the FAST cell table");
+                hp.celltab[G.cell_ofs + local] = make_uint4((unsigned)iniX | ((unsigned)iniY << 16), (unsigned)cw | ((unsigned)ch << 8) | ((unsigned)l << 16),
+                                                            (unsigned)(G.cand_ofs + local * G.cell_cap), 0u);
+            }
+    }
     hp.fast_WS = round_up(hp.fast_SP * hp.fast_SR + hp.fast_TP * hp.fast_TR + hp.fast_LC * 2 + hp.fast_RQ + 16, 128);   // +16: phase 1 reads whole words past the last row
     hp.fast_smem = (size_t)FAST_WARPS * hp.fast_WS;
     if (hp.fast_smem > 200 * 1024) return fail(B200ORB_E_ARG, "cell size too large for the FAST kernel's shared memory");
@@ -272,6 +309,7 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
 // ------------------------------------------------------------------------------------------------
 // Engine: workspace for S image slots + the kernel sequence
 // ------------------------------------------------------------------------------------------------
+constexpr int kStatusBanks = 4;      // = b200orb_batch::NBUF
 struct Engine {
     Params prm;
     HostPlan hp;
@@ -283,6 +321,7 @@ struct Engine {
     uint2* d_rmeta = nullptr;     // row-band index entries of the right keypoints: band_rows() x kp_total per pair
     unsigned char* d_octnodes = nullptr;     // node arrays of k_octree when they do not fit in shared memory
     unsigned char* d_roottab = nullptr;
+    uint4* d_celltab = nullptr;
     int* d_fastctr = nullptr;                // k_fast_cells: next unclaimed cell
     XTab* d_xtab = nullptr;
     XGroup* d_xgrp = nullptr;
@@ -302,7 +341,7 @@ struct Engine {
     }
     void release() {
         cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_cand); cudaFree(d_scratch); cudaFree(d_lvlkp);
-        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_xgrp); d_xgrp = nullptr; cudaFree(d_mtab); d_mtab = nullptr; cudaFree(d_fpat); d_fpat = nullptr; cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr; cudaFree(d_roottab); d_roottab = nullptr; cudaFree(d_fastctr); d_fastctr = nullptr;
+        cudaFree(d_cellcnt); cudaFree(d_lvlcnt); cudaFree(d_status); cudaFree(d_xtab); cudaFree(d_xgrp); d_xgrp = nullptr; cudaFree(d_mtab); d_mtab = nullptr; cudaFree(d_fpat); d_fpat = nullptr; cudaFree(d_ytab); cudaFree(d_rowstart); cudaFree(d_rmeta); d_rmeta = nullptr; cudaFree(d_octnodes); d_octnodes = nullptr; cudaFree(d_roottab); d_roottab = nullptr; cudaFree(d_celltab); d_celltab = nullptr; cudaFree(d_fastctr); d_fastctr = nullptr;
         d_pyr = d_blur = nullptr; d_cand = d_scratch = d_lvlkp = nullptr; d_cellcnt = d_lvlcnt = d_status = d_rowstart = nullptr;
         d_xtab = nullptr; d_ytab = nullptr; planned = false; bytes = 0;
     }
@@ -364,13 +403,15 @@ struct Engine {
         TRY(alloc(&d_lvlkp, (size_t)S * P.kp_total));
         TRY(alloc(&d_cellcnt, (size_t)S * P.ncells));
         TRY(alloc(&d_lvlcnt, (size_t)S * P.nlevels));
-        TRY(alloc(&d_status, (size_t)3 * std::max(S, 1)));     // one range-error flag word per pair, three banks (run_host: one per chunk in flight)
+        TRY(alloc(&d_status, (size_t)kStatusBanks * std::max(S, 1)));     // one range-error flag word per pair, one bank per run_host chunk in flight
         TRY(alloc(&d_rowstart, (size_t)S * (P.lv[0].h + 1)));
         TRY(alloc(&d_rmeta, (size_t)std::max(S / 2, 1) * P.kp_total * band_rows()));
         if (hp.oct_global_nodes) TRY(alloc(&d_octnodes, (size_t)S * P.nlevels * hp.oct_node_stride));
         TRY(alloc(&d_fastctr, 1));
         TRY(alloc(&d_roottab, hp.roottab.size() + 16));
         if (!hp.roottab.empty()) CU_TRY(cudaMemcpy(d_roottab, hp.roottab.data(), hp.roottab.size(), cudaMemcpyHostToDevice));
+        TRY(alloc(&d_celltab, hp.celltab.size()));
+        CU_TRY(cudaMemcpy(d_celltab, hp.celltab.data(), hp.celltab.size() * sizeof(uint4), cudaMemcpyHostToDevice));
         TRY(alloc(&d_xtab, hp.xtab.size()));
         TRY(alloc(&d_xgrp, hp.xgrp.size()));
         TRY(alloc(&d_mtab, hp.mtab.size()));
@@ -378,7 +419,7 @@ struct Engine {
         TRY(alloc(&d_ytab, hp.ytab.size()));
         CU_TRY(cudaMemset(d_pyr, 0, (size_t)S * P.pyr_bytes));
         CU_TRY(cudaMemset(d_blur, 0, (size_t)S * P.blur_bytes));
-        CU_TRY(cudaMemset(d_status, 0, sizeof(int) * (size_t)3 * std::max(S, 1)));
+        CU_TRY(cudaMemset(d_status, 0, sizeof(int) * (size_t)kStatusBanks * std::max(S, 1)));
         if (!hp.xtab.empty()) CU_TRY(cudaMemcpy(d_xtab, hp.xtab.data(), hp.xtab.size() * sizeof(XTab), cudaMemcpyHostToDevice));
         if (!hp.xgrp.empty()) CU_TRY(cudaMemcpy(d_xgrp, hp.xgrp.data(), hp.xgrp.size() * sizeof(XGroup), cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(d_mtab, hp.mtab.data(), hp.mtab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
@@ -414,7 +455,7 @@ struct Engine {
             const int nv = (G.w + 2 * ORB_EDGE + 15) / 16;
             const int vA_lo = 2, vA_n = std::max(0, (P.W + 15) / 16 - vA_lo), vB_n = nv - vA_n;
             const int blkA = (vA_n * G.rows + 255) / 256, blkB = (vB_n * G.rows + 255) / 256;
-            k_border0<<<dim3(blkA + blkB, n), 256, 0, st>>>(P, imgA, imgB, splitA, d_pyr, blkA, vA_lo, vA_n, magic_of(vA_n), vB_n, magic_of(vB_n));
+            CU_TRY(launch_seq(1, k_border0, dim3(blkA + blkB, n), dim3(256), 0, st, P, imgA, imgB, splitA, d_pyr, blkA, vA_lo, vA_n, magic_of(vA_n), vB_n, magic_of(vB_n), d_fastctr));
             ++g_launches;
             if (evs) cudaEventRecord(evs[1], st);
         }
@@ -424,8 +465,8 @@ struct Engine {
             const LevelGeom& G = P.lv[l];
             const int rgroups = (G.rows + RS_ROWS - 1) / RS_ROWS;
             const int blkA = (hp.rs_gA_n[l] * rgroups + 255) / 256, blkB = (hp.rs_gB_n[l] * rgroups + 255) / 256;
-            k_resize<<<dim3(blkA + blkB, n), 256, 0, st>>>(P, l, blkA, hp.rs_gA_lo[l], hp.rs_gA_n[l], magic_of(hp.rs_gA_n[l]), hp.rs_gB_n[l],
-                                                          magic_of(hp.rs_gB_n[l]), d_pyr, d_xtab, d_xgrp, d_ytab);
+            CU_TRY(launch_seq(2, k_resize, dim3(blkA + blkB, n), dim3(256), 0, st, P, l, blkA, hp.rs_gA_lo[l], hp.rs_gA_n[l], magic_of(hp.rs_gA_n[l]), hp.rs_gB_n[l],
+                              magic_of(hp.rs_gB_n[l]), d_pyr, (const XTab*)d_xtab, (const XGroup*)d_xgrp, (const YTab*)d_ytab));
             ++g_launches;
         }
         if (evs) cudaEventRecord(evs[2], st);
@@ -440,7 +481,7 @@ struct Engine {
         }
         auto launch_blur = [&]() {
             if (fork) { cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(side, ev_fork, 0); }
-            k_blur<<<dim3(P.blur_ctas, n), BLUR_WARPS * 32, 0, fork ? side : st>>>(P, d_pyr, d_blur);
+            launch_seq(4, k_blur, dim3(P.blur_ctas, n), dim3(BLUR_WARPS * 32), 0, fork ? side : st, P, (const u8*)d_pyr, d_blur);
             ++g_launches;
             if (fork) cudaEventRecord(ev_join, side);
         };
@@ -450,20 +491,20 @@ struct Engine {
             // persistent: every warp walks cells of the whole launch; 8 CTAs of FAST_WARPS warps per SM are resident
             const int total = n * hp.fast_cells;
             const int ctas = std::min((total + FAST_WARPS - 1) / FAST_WARPS, sm_count * 8);
-            CU_TRY(cudaMemsetAsync(d_fastctr, 0, sizeof(int), st));
-            k_fast_cells<<<ctas, FAST_WARPS * 32, hp.fast_smem, st>>>(P, hp.maps, d_cand, d_cellcnt, total, hp.fast_cells, d_fastctr, hp.fast_SP, hp.fast_SR,
-                                                                      hp.fast_TP, hp.fast_TR, hp.fast_LC, hp.fast_RQ, hp.fast_WS);
+            // the cell counter was zeroed by this sequence's k_border0
+            CU_TRY(launch_seq(8, k_fast_cells, dim3(ctas), dim3(FAST_WARPS * 32), hp.fast_smem, st, P, hp.maps, (const uint4*)d_celltab, d_cand, d_cellcnt, total, hp.fast_cells, magic_of(hp.fast_cells), d_fastctr,
+                              hp.fast_SP, hp.fast_SR, hp.fast_TP, hp.fast_TR, hp.fast_LC, hp.fast_RQ, hp.fast_WS));
             ++g_launches;
         }
         if (fork && fork_blur >= 2) launch_blur();
         if (evs) cudaEventRecord(evs[4], st);
-        k_octree<<<dim3(n, P.nlevels), OCT_THREADS, hp.oct_smem, st>>>(P, d_cand, d_cellcnt, d_scratch, d_lvlkp, d_lvlcnt, hp.oct_capN,
-                                                                      hp.oct_capK, hp.oct_capC, d_octnodes, hp.oct_node_stride, d_roottab);
+        CU_TRY(launch_seq(16, k_octree, dim3(n, P.nlevels), dim3(OCT_THREADS), hp.oct_smem, st, P, (const u32*)d_cand, (const int*)d_cellcnt, d_scratch, d_lvlkp,
+                          d_lvlcnt, hp.oct_capN, hp.oct_capK, hp.oct_capC, d_octnodes, hp.oct_node_stride, (const unsigned char*)d_roottab));
         ++g_launches;
         if (evs) cudaEventRecord(evs[5], st);
         if (fork) CU_TRY(cudaStreamWaitEvent(st, ev_join, 0));
-        k_describe<<<dim3((P.kp_total + DESC_WARPS * DESC_KPW - 1) / (DESC_WARPS * DESC_KPW), n), DESC_WARPS * 32, 0, st>>>(P, hp.bmaps, d_pyr, d_lvlkp, d_lvlcnt, d_mtab,
-                                                                                                    d_fpat, d_kps, d_desc, d_nkp);
+        CU_TRY(launch_seq(32, k_describe, dim3((P.kp_total + DESC_WARPS * DESC_KPW - 1) / (DESC_WARPS * DESC_KPW), n), dim3(DESC_WARPS * 32), 0, st, P, hp.bmaps,
+                          (const u8*)d_pyr, (const u32*)d_lvlkp, (const int*)d_lvlcnt, (const uint2*)d_mtab, (const float4*)d_fpat, d_kps, d_desc, d_nkp));
         ++g_launches;
         if (evs) cudaEventRecord(evs[6], st);
         CU_TRY(cudaGetLastError());
@@ -506,15 +547,15 @@ void fill_stereo_consts(StereoArgs& A, double mbf, float fx) {
 int launch_stereo(const StereoGeom& SG, StereoArgs A, int max_left, int pairs, cudaStream_t st, int flags = 0) {
     if (pairs < 1 || max_left < 1) return 0;
     const size_t smem = (size_t)(2 * SG.nRows + 1) * sizeof(int);
-    k_rowindex<<<pairs, RI_THREADS, smem, st>>>(A.kpsR, A.nR, A.kp_stride, A.n_stride, A.kp_row, A.oct_idx, SG, (int*)A.rowStart,
-                                                (uint2*)A.rmeta, A.idx_stride, A.status, A.status_stride);
+    CU_TRY(launch_seq(64, k_rowindex, dim3(pairs), dim3(RI_THREADS), smem, st, A.kpsR, A.nR, A.kp_stride, A.n_stride, A.kp_row, A.oct_idx, SG, (int*)A.rowStart,
+                      (uint2*)A.rmeta, A.idx_stride, A.status, A.status_stride));
     ++g_launches;
     dim3 grid((max_left + ST_WARPS - 1) / ST_WARPS, pairs);
-    k_stereo<<<grid, ST_WARPS * 32, 0, st>>>(SG, A);
+    CU_TRY(launch_seq(128, k_stereo, grid, dim3(ST_WARPS * 32), 0, st, SG, A));
     ++g_launches;
     if (flags & B200ORB_STEREO_MEDIAN_CULL) {
         if (!A.sadDist) return fail(B200ORB_E_ARG, "median cull needs a sadDist buffer");
-        k_median_cull<<<pairs, MC_THREADS, 0, st>>>(A.nL, A.n_stride, A.out_stride, A.sadDist, A.uRight, A.depth);
+        CU_TRY(launch_seq(128, k_median_cull, dim3(pairs), dim3(MC_THREADS), 0, st, A.nL, A.n_stride, A.out_stride, (const int*)A.sadDist, A.uRight, A.depth));
         ++g_launches;
     }
     CU_TRY(cudaGetLastError());
@@ -594,10 +635,13 @@ struct b200orb_batch {
     Engine eng;
     int P = 0, H = 0, W = 0;
     // run_host pipeline state
-    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
-    // run_host keeps NBUF chunks in flight (upload k+2 | compute k+1 | download k): with upload and compute times about equal, a third
-    // buffer keeps the upload stream from waiting for the kernels of two chunks ago
-    static constexpr int NBUF = 3;
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_comp2 = nullptr, s_out = nullptr;
+    // run_host keeps NBUF chunks in flight (upload k+3 | compute k+2 and k+1 | download k).  Consecutive chunks alternate between two
+    // compute lanes -- each its own stream and Engine workspace -- so that one chunk's latency-bound launches (octree rounds, the small
+    // pyramid levels, kernel tails) run under the other chunk's kernels; B200ORB_HOST_LANES=1 keeps one lane
+    static constexpr int NBUF = kStatusBanks;
+    Engine* eng2 = nullptr;
+    int lanes = 1;
     cudaEvent_t ev_in[NBUF] = {}, ev_comp[NBUF] = {}, ev_out[NBUF] = {};
     u8* d_in[NBUF] = {};
     float* d_kps[NBUF] = {}; u8* d_desc[NBUF] = {}; int* d_nkp[NBUF] = {};
@@ -609,7 +653,7 @@ struct b200orb_batch {
     int status_bank = 0;      // which half of eng.d_status the next run_device uses (run_host: the chunk's slot, so that the
                               // previous chunk's flag download on the output stream never races with the next chunk's clear)
     int stereo_flags = 0;
-    int* d_sad = nullptr;     // [P][C], only with the median cull
+    int* d_sad[2] = {nullptr, nullptr};     // [P][C] per compute lane, only with the median cull
     // per-kernel timing (b200orb_batch_profile): a pool of event sets, one set per run_device call
     std::vector<cudaEvent_t> prof_ev;
     std::vector<int> prof_pairs;
@@ -1038,8 +1082,10 @@ void b200orb_batch_destroy(b200orb_batch* b) {
     if (!b) return;
     cudaSetDevice(b->eng.device);
     b->eng.release();
+    if (b->eng2) { b->eng2->release(); delete b->eng2; }
+    if (b->s_comp2) cudaStreamDestroy(b->s_comp2);
     for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
-    cudaFree(b->d_sad);
+    cudaFree(b->d_sad[0]); cudaFree(b->d_sad[1]);
     for (int i = 0; i < b200orb_batch::NBUF; ++i) {
         cudaFree(b->d_in[i]); cudaFree(b->d_kps[i]); cudaFree(b->d_desc[i]); cudaFree(b->d_nkp[i]);
         cudaFree(b->d_uR[i]); cudaFree(b->d_dep[i]); cudaFree(b->d_mi[i]);
@@ -1056,16 +1102,16 @@ void b200orb_batch_destroy(b200orb_batch* b) {
 
 int b200orb_batch_max_pairs(const b200orb_batch* b) { return b ? b->P : 0; }
 int b200orb_batch_kp_capacity(const b200orb_batch* b) { return b ? b->eng.hp.P.kp_total : 0; }
-long long b200orb_batch_workspace_bytes(const b200orb_batch* b) { return b ? b->eng.bytes + b->host_bytes : 0; }
+long long b200orb_batch_workspace_bytes(const b200orb_batch* b) { return b ? b->eng.bytes + (b->eng2 ? b->eng2->bytes : 0) + b->host_bytes : 0; }
 
-int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint8_t* d_right, int n_pairs, double mbf, float fx,
-                             float* d_kps, uint8_t* d_desc, int32_t* d_nkp, float* d_uRight, float* d_depth, int32_t* d_matchIdx,
-                             void* stream) {
+static int batch_run_on(b200orb_batch* b, Engine& E, const uint8_t* d_left, const uint8_t* d_right, int n_pairs, double mbf, float fx,
+                        float* d_kps, uint8_t* d_desc, int32_t* d_nkp, float* d_uRight, float* d_depth, int32_t* d_matchIdx,
+                        void* stream) {
     if (!b || !d_left || !d_right || !d_kps || !d_desc || !d_nkp || !d_uRight || !d_depth) return fail(B200ORB_E_ARG, "NULL argument");
     if (n_pairs < 1 || n_pairs > b->P) return fail(B200ORB_E_ARG, "n_pairs must be in [1, max_pairs]");
-    CU_TRY(cudaSetDevice(b->eng.device));
+    CU_TRY(cudaSetDevice(E.device));
     cudaStream_t st = (cudaStream_t)stream;
-    const Plan& P = b->eng.hp.P;
+    const Plan& P = E.hp.P;
     const size_t C = P.kp_total;
     cudaEvent_t* evs = nullptr;
     if (b->prof_on && b->prof_used < b->prof_cap) {
@@ -1074,29 +1120,36 @@ int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint
         ++b->prof_used;
         CU_TRY(cudaEventRecord(evs[0], st));
     }
-    TRY(b->eng.extract(d_left, d_right, n_pairs, 2 * n_pairs, d_kps, d_desc, d_nkp, st, evs));
+    TRY(E.extract(d_left, d_right, n_pairs, 2 * n_pairs, d_kps, d_desc, d_nkp, st, evs));
     StereoGeom SG;
-    b->eng.stereo_geom(SG, b->stereo_flags);
+    E.stereo_geom(SG, b->stereo_flags);
     StereoArgs A;
     memset(&A, 0, sizeof(A));
     A.kpsL = d_kps; A.kpsR = d_kps + (size_t)n_pairs * C * 6;
     A.descL = d_desc; A.descR = d_desc + (size_t)n_pairs * C * 32;
     A.nL = d_nkp; A.nR = d_nkp + n_pairs; A.n_stride = 1;
-    A.pyrL = b->eng.d_pyr; A.pyrR = b->eng.d_pyr + (size_t)n_pairs * P.pyr_bytes;
+    A.pyrL = E.d_pyr; A.pyrR = E.d_pyr + (size_t)n_pairs * P.pyr_bytes;
     A.kp_stride = (long long)C * 6; A.desc_stride = (long long)C * 32; A.pyr_stride = P.pyr_bytes;
     A.kp_row = 6; A.oct_idx = 5; A.out_stride = (int)C;
     A.uRight = d_uRight; A.depth = d_depth; A.matchIdx = d_matchIdx;
-    A.status = b->eng.d_status + (size_t)b->status_bank * b->eng.S; A.status_stride = 1;   // flag word per pair, cleared here, read by b200orb_batch_status_device / run_host
-    CU_TRY(cudaMemsetAsync(A.status, 0, (size_t)n_pairs * sizeof(int), st));
-    A.rowStart = b->eng.d_rowstart; A.rmeta = b->eng.d_rmeta; A.idx_stride = (long long)C * b->eng.band_rows();
+    A.status = E.d_status + (size_t)b->status_bank * E.S; A.status_stride = 1;   // flag word per pair, cleared by k_rowindex, read by b200orb_batch_status_device / run_host
+    A.rowStart = E.d_rowstart; A.rmeta = E.d_rmeta; A.idx_stride = (long long)C * E.band_rows();
     fill_stereo_consts(A, mbf, fx);
     if (b->stereo_flags & B200ORB_STEREO_MEDIAN_CULL) {
-        if (!b->d_sad) CU_TRY(cudaMalloc((void**)&b->d_sad, (size_t)b->P * C * 4));
-        A.sadDist = b->d_sad;
+        int*& sad = b->d_sad[&E == b->eng2 ? 1 : 0];
+        if (!sad) CU_TRY(cudaMalloc((void**)&sad, (size_t)b->P * C * 4));
+        A.sadDist = sad;
     }
     TRY(launch_stereo(SG, A, (int)C, n_pairs, st, b->stereo_flags));
     if (evs) CU_TRY(cudaEventRecord(evs[B200ORB_NSTAGE], st));
     return 0;
+}
+
+int b200orb_batch_run_device(b200orb_batch* b, const uint8_t* d_left, const uint8_t* d_right, int n_pairs, double mbf, float fx,
+                             float* d_kps, uint8_t* d_desc, int32_t* d_nkp, float* d_uRight, float* d_depth, int32_t* d_matchIdx,
+                             void* stream) {
+    if (!b) return fail(B200ORB_E_ARG, "NULL argument");
+    return batch_run_on(b, b->eng, d_left, d_right, n_pairs, mbf, fx, d_kps, d_desc, d_nkp, d_uRight, d_depth, d_matchIdx, stream);
 }
 
 static const char* kRangeMsg = "a SAD window or row band leaves the pyramid view in at least one pair (the reference raises IndexError/ValueError "
@@ -1203,6 +1256,14 @@ static int batch_host_setup(b200orb_batch* b) {
     CU_TRY(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&b->s_comp, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
+    const char* lv = getenv("B200ORB_HOST_LANES");
+    b->lanes = lv ? std::max(1, std::min(2, atoi(lv))) : 2;
+    if (b->lanes == 2) {
+        CU_TRY(cudaStreamCreateWithFlags(&b->s_comp2, cudaStreamNonBlocking));
+        b->eng2 = new Engine;
+        b->eng2->prm = b->eng.prm; b->eng2->device = b->eng.device;
+        TRY(b->eng2->plan(b->H, b->W, 2 * b->P));
+    }
     for (int i = 0; i < b200orb_batch::NBUF; ++i) {
         CU_TRY(cudaEventCreateWithFlags(&b->ev_in[i], cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&b->ev_comp[i], cudaEventDisableTiming));
@@ -1254,12 +1315,22 @@ int b200orb_batch_run_host_shard(b200orb_batch* b, const uint8_t* h_left, const 
         int left = n_pairs;
         std::vector<int> tail;
         if (n_pairs >= 4 * P && P >= 8) {
+            static const int min_tail = [] { const char* v = getenv("B200ORB_HOST_MIN_TAIL"); return v ? std::max(1, atoi(v)) : 0; }();
             sizes.push_back(P / 4); sizes.push_back(P / 2);
-            tail.push_back(P / 2); tail.push_back(P / 4);
-            left -= 2 * (P / 4 + P / 2);
+            left -= P / 4 + P / 2;
+            // the job ends one chunk latency after its last upload: taper the last chunks down to min_tail pairs (default P/4)
+            for (int c = P / 2; c >= std::max(min_tail ? min_tail : P / 4, 1) && c >= 4; c /= 2) { tail.push_back(c); left -= c; }
         }
         while (left > 0) { const int c = std::min(P, left); sizes.push_back(c); left -= c; }
         sizes.insert(sizes.end(), tail.begin(), tail.end());
+    }
+    // B200ORB_HOST_TRACE=1: per-chunk completion times of upload / kernels / download on stderr (diagnostic; extra timing events)
+    static const bool trace = [] { const char* v = getenv("B200ORB_HOST_TRACE"); return v && atoi(v) != 0; }();
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize(3 * sizes.size() + 1);
+        for (auto& e : tev) CU_TRY(cudaEventCreate(&e));
+        CU_TRY(cudaEventRecord(tev[0], b->s_in));
     }
     int p0 = 0;
     for (int k = 0; k < (int)sizes.size(); p0 += sizes[k], ++k) {
@@ -1269,17 +1340,22 @@ int b200orb_batch_run_host_shard(b200orb_batch* b, const uint8_t* h_left, const 
         CU_TRY(cudaMemcpyAsync(b->d_in[s], h_left + (size_t)p0 * HW, np * HW, cudaMemcpyHostToDevice, b->s_in));
         CU_TRY(cudaMemcpyAsync(b->d_in[s] + np * HW, h_right + (size_t)p0 * HW, np * HW, cudaMemcpyHostToDevice, b->s_in));
         CU_TRY(cudaEventRecord(b->ev_in[s], b->s_in));
-        CU_TRY(cudaStreamWaitEvent(b->s_comp, b->ev_in[s], 0));
-        if (k >= b200orb_batch::NBUF) CU_TRY(cudaStreamWaitEvent(b->s_comp, b->ev_out[s], 0));   // outputs of chunk k-NBUF downloaded
+        if (trace) CU_TRY(cudaEventRecord(tev[1 + 3 * k], b->s_in));
+        const bool lane2 = b->lanes == 2 && (k & 1);
+        Engine& E = lane2 ? *b->eng2 : b->eng;
+        cudaStream_t sc = lane2 ? b->s_comp2 : b->s_comp;
+        CU_TRY(cudaStreamWaitEvent(sc, b->ev_in[s], 0));
+        if (k >= b200orb_batch::NBUF) CU_TRY(cudaStreamWaitEvent(sc, b->ev_out[s], 0));   // outputs of chunk k-NBUF downloaded
         b->status_bank = s;
-        const int rrc = b->copy_only ? 0 : b200orb_batch_run_device(b, b->d_in[s], b->d_in[s] + np * HW, (int)np, mbf, fx, b->d_kps[s], b->d_desc[s], b->d_nkp[s],
-                                                 b->d_uR[s], b->d_dep[s], b->d_mi[s], b->s_comp);
+        const int rrc = b->copy_only ? 0 : batch_run_on(b, E, b->d_in[s], b->d_in[s] + np * HW, (int)np, mbf, fx, b->d_kps[s], b->d_desc[s], b->d_nkp[s],
+                                                         b->d_uR[s], b->d_dep[s], b->d_mi[s], sc);
         b->status_bank = 0;
         if (rrc) return rrc;
-        CU_TRY(cudaEventRecord(b->ev_comp[s], b->s_comp));
+        CU_TRY(cudaEventRecord(b->ev_comp[s], sc));
+        if (trace) CU_TRY(cudaEventRecord(tev[2 + 3 * k], sc));
         CU_TRY(cudaStreamWaitEvent(b->s_out, b->ev_comp[s], 0));
-        // the chunk's range-error flags travel with its outputs (bank s is cleared again by chunk k + 2, which waits for ev_out[s])
-        CU_TRY(cudaMemcpyAsync(b->h_status + p0, b->eng.d_status + (size_t)s * b->eng.S, np * sizeof(int), cudaMemcpyDeviceToHost, b->s_out));
+        // the chunk's range-error flags travel with its outputs (bank s is cleared again by chunk k + NBUF, which waits for ev_out[s])
+        CU_TRY(cudaMemcpyAsync(b->h_status + p0, E.d_status + (size_t)s * E.S, np * sizeof(int), cudaMemcpyDeviceToHost, b->s_out));
         for (int side = 0; side < 2; ++side) {
             CU_TRY(cudaMemcpyAsync(h_kps + (side * NT + p0) * C * 6, b->d_kps[s] + side * np * C * 6, np * C * 24, cudaMemcpyDeviceToHost, b->s_out));
             CU_TRY(cudaMemcpyAsync(h_desc + (side * NT + p0) * C * 32, b->d_desc[s] + side * np * C * 32, np * C * 32, cudaMemcpyDeviceToHost, b->s_out));
@@ -1289,9 +1365,19 @@ int b200orb_batch_run_host_shard(b200orb_batch* b, const uint8_t* h_left, const 
         CU_TRY(cudaMemcpyAsync(h_depth + (size_t)p0 * C, b->d_dep[s], np * C * 4, cudaMemcpyDeviceToHost, b->s_out));
         if (h_matchIdx) CU_TRY(cudaMemcpyAsync(h_matchIdx + (size_t)p0 * C, b->d_mi[s], np * C * 4, cudaMemcpyDeviceToHost, b->s_out));
         CU_TRY(cudaEventRecord(b->ev_out[s], b->s_out));
+        if (trace) CU_TRY(cudaEventRecord(tev[3 + 3 * k], b->s_out));
     }
     CU_TRY(cudaStreamSynchronize(b->s_out));
     CU_TRY(cudaStreamSynchronize(b->s_comp));
+    if (b->s_comp2) CU_TRY(cudaStreamSynchronize(b->s_comp2));
+    if (trace) {
+        for (size_t k = 0; k < sizes.size(); ++k) {
+            float t[3] = {0.f, 0.f, 0.f};
+            for (int j = 0; j < 3; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[1 + 3 * k + j]);
+            fprintf(stderr, "[b200orb trace] chunk %2d pairs %4d  uploaded %7.3f  computed %7.3f  downloaded %7.3f ms\n", (int)k, sizes[k], t[0], t[1], t[2]);
+        }
+        for (auto& e : tev) cudaEventDestroy(e);
+    }
     for (int i = 0; i < n_pairs; ++i)
         if (b->h_status[i]) return fail(B200ORB_E_RANGE, kRangeMsg);     // every output is in host memory; flagged pairs hold -1 at the offending keypoints
     return 0;

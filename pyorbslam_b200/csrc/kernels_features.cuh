@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_co
                                                               const int* __restrict__ lvl_cnt, const uint2* __restrict__ mtab,
                                                               const float4* __restrict__ fpat, float* __restrict__ kps,
                                                               u8* __restrict__ desc, int* __restrict__ nkp) {
+    pdl_enter();
     const int slot = blockIdx.y, lane = threadIdx.x & 31;
     // the moment table goes to shared memory once per CTA, the float pattern into registers once per warp; every warp then
     // walks DESC_KPW consecutive keypoints
@@ -219,11 +220,14 @@ __global__ void __launch_bounds__(RI_THREADS) k_rowindex(const float* __restrict
                                                          int n_stride, int kp_row, int oct_idx, const __grid_constant__ StereoGeom SG,
                                                          int* __restrict__ rowStart, uint2* __restrict__ rmeta,
                                                          long long idx_stride, int* __restrict__ status, int status_stride) {
+    pdl_enter();
     const int nRows = SG.nRows;
     extern __shared__ int ri_hist[];     // nRows + 1 counters, then nRows cursors
     __shared__ int ri_tmp[RI_THREADS / 32 + 1];
     const int pair = blockIdx.x;
     status += (size_t)pair * status_stride;          // one flag word per pair in the batch API (stride 0: one word in all)
+    if (threadIdx.x == 0) *status = 0;               // cleared here (no memset between the kernels: they are chained programmatically);
+    __syncthreads();                                 // k_stereo of the same pair ORs its own flags in afterwards
     const int n = nR[(size_t)pair * n_stride];
     const float* k = kpsR + (size_t)pair * kp_stride;
     int* rs = rowStart + (size_t)pair * (nRows + 1);
@@ -308,6 +312,7 @@ __device__ __forceinline__ const u8* view_ptr(const u8* base, const StereoGeom& 
 }
 
 __global__ void __launch_bounds__(ST_WARPS * 32, 8) k_stereo(const __grid_constant__ StereoGeom SG, const StereoArgs A) {
+    pdl_enter();
     __shared__ __align__(16) unsigned char s_win[ST_WARPS][11 * 12 + 11 * 24 + 4];     // 400 bytes per warp: word-aligned window rows
     const int pair = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nL = A.nL[(size_t)pair * A.n_stride];
@@ -485,6 +490,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 8) k_stereo(const __grid_consta
 __global__ void __launch_bounds__(MC_THREADS) k_median_cull(const int* __restrict__ nL, int n_stride, int out_stride,
                                                             const int* __restrict__ sadDist, float* __restrict__ uRight,
                                                             float* __restrict__ depth) {
+    pdl_enter();
     __shared__ int hist[256];
     __shared__ int sel[3];     // [0] matches, [1] selected high byte, [2] rank inside it
     const int pair = blockIdx.x, n = nL[(size_t)pair * n_stride];

@@ -7,6 +7,16 @@
 typedef unsigned char u8;
 typedef unsigned int u32;
 
+// Programmatic dependent launch (every kernel of the launch sequence is launched with cudaLaunchAttributeProgrammaticStreamSerialization):
+// `launch_dependents` at the top of a CTA lets the NEXT kernel of the stream start placing its CTAs as soon as every CTA of this grid
+// has started, i.e. into the slots the last, partially filled wave leaves free; `wait` blocks until the previous kernel has completed
+// and flushed, so nothing of its output is read early.  The launch latency and ramp-up of a kernel then overlap the tail of its
+// predecessor (14 kernel boundaries per chunk).
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ int reflect101(int p, int len) {
     // OpenCV borderInterpolate(BORDER_REFLECT_101); loops only when the border is wider than the image
     if ((unsigned)p < (unsigned)len) return p;
@@ -27,7 +37,9 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 // instruction on average).
 __global__ void __launch_bounds__(256) k_border0(const __grid_constant__ Plan P, const u8* __restrict__ imgA,
                                                  const u8* __restrict__ imgB, int splitA, u8* __restrict__ pyr,
-                                                 int blkA, int vA_lo, int vA_n, u32 magicA, int vB_n, u32 magicB) {
+                                                 int blkA, int vA_lo, int vA_n, u32 magicA, int vB_n, u32 magicB, int* __restrict__ fast_counter) {
+    pdl_enter();
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *fast_counter = 0;     // k_fast_cells' cell counter of this launch sequence
     const LevelGeom& G = P.lv[0];
     const int slot = blockIdx.y;
     const bool interior = (int)blockIdx.x < blkA;
@@ -186,6 +198,7 @@ __global__ void __launch_bounds__(256, 5) k_resize(const __grid_constant__ Plan 
                                                 int gB_n, u32 magicB, u8* __restrict__ pyr,
                                                 const XTab* __restrict__ xtab, const XGroup* __restrict__ xgrp,
                                                 const YTab* __restrict__ ytab) {
+    pdl_enter();
     const bool interior = (int)blockIdx.x < blkA;
     const int idx = (interior ? (int)blockIdx.x : (int)blockIdx.x - blkA) * (int)blockDim.x + (int)threadIdx.x;
     const int per_row = interior ? gA_n : gB_n;
@@ -225,6 +238,7 @@ __device__ __forceinline__ u32 blur_out4(u32 m01, u32 m23, u32 r01, u32 r23, u32
     return __byte_perm(__byte_perm(a0, a1, 0x0062), __byte_perm(a2, a3, 0x0062), 0x5410);
 }
 __global__ void __launch_bounds__(BLUR_WARPS * 32) k_blur(const __grid_constant__ Plan P, const u8* __restrict__ pyr, u8* __restrict__ blur) {
+    pdl_enter();
     const int slot = blockIdx.y, bid = (int)blockIdx.x;
     int l = 0;
     while (l + 1 < P.nlevels && bid >= P.lv[l + 1].blur_cta_ofs) ++l;
@@ -382,25 +396,16 @@ __device__ __forceinline__ void fast_quick2(u32 v, u32 a, u32 b, u32 c, u32 d, u
     rm = ((A - Tm) | (B - Tm)) & 0x80008000u;
 }
 // -> min-threshold nibble in bits 0..3, ini-threshold nibble in bits 8..11 (bit k = pixel k passes).
-// o = address of the first of the four pixels; al = o & 3 is loop-invariant per cell, so the word offsets / funnel-shift
-// amounts of the five operands are plain registers (one code path for all four alignments: the kernel used to carry four
-// template copies of this loop and stalled on instruction fetch).
-struct FastCut { int wL, wR, shL, shC, shR; };     // word index of L / R relative to the centre-row base, byte shifts * 8
-__device__ __forceinline__ FastCut fast_cut_setup(int al) {
-    FastCut c;
-    c.wL = (al + 1) >> 2; c.wR = (al + 7) >> 2;
-    c.shL = 8 * ((al + 1) & 3); c.shC = 8 * (al & 3); c.shR = 8 * ((al + 7) & 3);
-    return c;
-}
-__device__ __forceinline__ u32 fast_quick4(const u8* o, int al, const FastCut& fc, int SP, u32 Ti, u32 Tm) {
-    const u32* wc = reinterpret_cast<const u32*>(o - al - 4);            // centre row: bytes -al-4 .. of the pixel group
-    const u32* wt = reinterpret_cast<const u32*>(o - al + 3 * SP);
-    const u32* wb = reinterpret_cast<const u32*>(o - al - 3 * SP);
-    const u32 c0 = wc[0], c1 = wc[1], c2 = wc[2], c3 = wc[3];            // bytes -al-4 .. -al+11 (the strip rows carry 16 bytes of slack)
-    const u32 L = __funnelshift_r(fc.wL ? c1 : c0, fc.wL ? c2 : c1, fc.shL);
-    const u32 C = __funnelshift_r(c1, c2, fc.shC);
-    const u32 R = __funnelshift_r(fc.wR == 1 ? c1 : c2, fc.wR == 1 ? c2 : c3, fc.shR);
-    const u32 T = __funnelshift_r(wt[0], wt[1], fc.shC), B = __funnelshift_r(wb[0], wb[1], fc.shC);
+// o = address of the first of the four pixels, a multiple of 4: the groups are laid on the shared-memory word grid (the window's
+// first column sits up to 3 px into its first group; those leading bits are masked off by fast_expand), so centre, y-3 and y+3
+// are single aligned words and x-3 / x+3 one constant funnel shift each.  (The kernel used to lay the groups on the window's own
+// columns: eight loads, five variable shifts and four selects per group instead of five loads and two shifts.)
+__device__ __forceinline__ u32 fast_quick4(const u8* o, int SP, u32 Ti, u32 Tm) {
+    const u32* wc = reinterpret_cast<const u32*>(o);
+    const u32 cl = wc[-1], C = wc[0], cr = wc[1];
+    const u32 T = *reinterpret_cast<const u32*>(o + 3 * SP), B = *reinterpret_cast<const u32*>(o - 3 * SP);
+    const u32 L = __funnelshift_r(cl, C, 8);           // bytes -3 .. 0
+    const u32 R = __funnelshift_r(C, cr, 24);          // bytes  3 .. 6
     u32 ei, em, oi, om;
     fast_quick2(__byte_perm(C, 0, 0x4240), __byte_perm(T, 0, 0x4240), __byte_perm(B, 0, 0x4240),
                 __byte_perm(R, 0, 0x4240), __byte_perm(L, 0, 0x4240), Ti, Tm, ei, em);            // pixels 0 | 2
@@ -411,48 +416,51 @@ __device__ __forceinline__ u32 fast_quick4(const u8* o, int al, const FastCut& f
     return (x | (x >> 14)) & 0x0f0fu;
 }
 
-// Phase 1 of a cell (detection window up to 63 x 63): a lane tests 4 consecutive pixels of a row -- 8 lanes per row and 4 rows
-// per step for windows up to 32 px wide, 16 lanes per row and 2 rows per step beyond -- and drops the two nibbles (one 16-bit
-// store) into a per-row table: rowq[row][quad], 8 or 16 quads per row.
-__device__ __forceinline__ void fast_phase1_bits(const u8* s0, int SP, int cw, int ch, int Ti, int Tm, unsigned short* rowq, int lane) {
-    const bool wide = cw > 32;
-    const int sh = wide ? 4 : 3, r = lane >> sh, q = lane & ((1 << sh) - 1), rstep = 32 >> sh;
+// Phase 1 of a cell.  sa = the word-aligned address at or below the window's first detection pixel, cwa = columns from there to
+// the window's right edge (<= 64).  A lane tests 4 consecutive pixels of a row and drops the two nibbles (one 16-bit store) into
+// a per-row table rowq[row][quad] (8 quads per row for up to 32 columns, 16 beyond).  The Q = ceil(cwa / 4) quads of all rows are
+// dealt to the lanes as one sequence (item = row * Q + quad, lane + 32 * step): no lane idles whatever Q is.
+__device__ __forceinline__ void fast_phase1_bits(const u8* sa, int SP, int cwa, int ch, int Ti, int Tm, unsigned short* rowq, int lane) {
+    const int sh = cwa > 32 ? 4 : 3;
     const u32 ti = (u32)Ti * 0x00010001u, tm = (u32)Tm * 0x00010001u;
-    const int al = (int)(reinterpret_cast<size_t>(s0) & 3);              // rows are SP apart (multiple of 16), groups 4 apart
-    const FastCut fc = fast_cut_setup(al);
-    if (4 * q < cw) {
-        const u8* o = s0 + r * SP + 4 * q;
-        unsigned short* rb = rowq + (r << sh) + q;
+    const int Q = (cwa + 3) >> 2;                        // 1 .. 16
+    const u32 rcp = (65536u + (u32)Q - 1u) / (u32)Q;     // n / Q == (n * rcp) >> 16 for n <= 32
+    int row = (int)(((u32)lane * rcp) >> 16), quad = lane - row * Q;
+    const int dr = (int)((32u * rcp) >> 16), dq = 32 - dr * Q;
+    const u8* o = sa + row * SP + 4 * quad;
+    unsigned short* rb = rowq + (row << sh) + quad;
+    const int stepO = dr * SP + 4 * dq, stepR = (dr << sh) + dq, wrapO = SP - 4 * Q, wrapR = (1 << sh) - Q;
 #pragma unroll 2
-        for (int y = r; y < ch; y += rstep, o += rstep * SP, rb += 32) *rb = (unsigned short)fast_quick4(o, al, fc, SP, ti, tm);
+    while (row < ch) {
+        *rb = (unsigned short)fast_quick4(o, SP, ti, tm);
+        quad += dq; row += dr; o += stepO; rb += stepR;
+        if (quad >= Q) { quad -= Q; ++row; o += wrapO; rb += wrapR; }
     }
     __syncwarp();
 }
 
 // Row-major work list of a cell from the phase-1 table: lane r turns the masks of rows r and r + 32 into list entries (y << 6 | x)
 // at the offsets an exclusive warp scan of the row counts gives -- row-major order by construction, no per-pixel ballot.
-// which = 0: pixels passing at iniThFAST;  1: pixels passing at minThFAST but not at iniThFAST;  2: all passing at minThFAST.
-__device__ __forceinline__ int fast_expand(const unsigned short* rowq, int cw, int ch, int which, unsigned short* list, int lane) {
-    const bool wide = cw > 32;
+// x counts from the aligned origin (see fast_phase1_bits): colmask keeps columns [a, cwa).
+// useMin = false: pixels passing at iniThFAST;  true: pixels passing at minThFAST.
+__device__ __forceinline__ int fast_expand(const unsigned short* rowq, int cwa, int ch, unsigned long long colmask, bool useMin,
+                                           unsigned short* list, int lane) {
+    const bool wide = cwa > 32;
     // a 32-bit word holds two quads: min nibbles at bits 0..3 / 16..19, ini nibbles at bits 8..11 / 24..27
-    auto nib_min = [](u32 w) { return (w & 0xfu) | ((w >> 12) & 0xf0u); };
-    auto nib_ini = [](u32 w) { return ((w >> 8) & 0xfu) | ((w >> 20) & 0xf0u); };
-    const unsigned long long colmask = (1ull << cw) - 1ull;
+    const int nsh = useMin ? 0 : 8;
+    auto nib = [nsh](u32 w) { w >>= nsh; return (w & 0xfu) | ((w >> 12) & 0xf0u); };
     unsigned long long m[2] = {0ull, 0ull};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int row = lane + 32 * h;
         if (row < ch) {
-            unsigned long long mi, mm;
             const uint4 w = *reinterpret_cast<const uint4*>(rowq + row * (wide ? 16 : 8));
-            mi = nib_ini(w.x) | (nib_ini(w.y) << 8) | (nib_ini(w.z) << 16) | (nib_ini(w.w) << 24);
-            mm = nib_min(w.x) | (nib_min(w.y) << 8) | (nib_min(w.z) << 16) | (nib_min(w.w) << 24);
+            unsigned long long mm = nib(w.x) | (nib(w.y) << 8) | (nib(w.z) << 16) | (nib(w.w) << 24);
             if (wide) {
                 const uint4 w2 = *reinterpret_cast<const uint4*>(rowq + row * 16 + 8);
-                mi |= (unsigned long long)(nib_ini(w2.x) | (nib_ini(w2.y) << 8) | (nib_ini(w2.z) << 16) | (nib_ini(w2.w) << 24)) << 32;
-                mm |= (unsigned long long)(nib_min(w2.x) | (nib_min(w2.y) << 8) | (nib_min(w2.z) << 16) | (nib_min(w2.w) << 24)) << 32;
+                mm |= (unsigned long long)(nib(w2.x) | (nib(w2.y) << 8) | (nib(w2.z) << 16) | (nib(w2.w) << 24)) << 32;
             }
-            m[h] = (which == 0 ? mi : which == 1 ? (mm & ~mi) : mm) & colmask;
+            m[h] = mm & colmask;
         }
     }
     int base = 0;
@@ -548,37 +556,37 @@ __device__ __forceinline__ int fast_score(const u8* p, int SP, int t) {
 //   2+3 exact corner strength (packed 3-input min/max) of the pixels passing at iniThFAST -> score tile (every score >= 1);
 //       entries with score >= iniThFAST stay in the list (in place)
 //   4   strict 8-neighbour NMS on that list
-//   R   only if nothing survived (ORBextractor.cpp:811): score the pixels passing at minThFAST but not at iniThFAST, rebuild the
-//       list from the minThFAST bits, keep score >= minThFAST, NMS again
+//   R   only if nothing survived (ORBextractor.cpp:811): the same two steps on the pixels passing at minThFAST, kept at
+//       score >= minThFAST (the few that had passed at iniThFAST are scored a second time: same values, no second list)
 //   5   ordered emission of the survivors
 // Survivors at T are exactly the strict local maxima among the pixels with score >= T: a neighbour with a lower score never
 // suppresses, so scores below T left in the tile are harmless and nothing is cleared between the two attempts.
 struct FastCell {            // geometry of one cell (warp-uniform)
-    int slot, level, cell;   // cell = index inside the level
+    int slot, level, rem;    // rem = cell index inside the slot (all levels)
     int iniX, iniY, cw, ch;  // window origin (incl. the 3-px rim, level coordinates) and detection size; cw <= 0: the reference skips the cell
+    int cand_ofs;            // u32 index of the cell's candidate storage inside the slot's blob
 };
-__device__ __forceinline__ void fast_cell_geom(const Plan& P, int c, int cells_per_slot, FastCell& g) {
-    const int slot = c / cells_per_slot, rem = c - slot * cells_per_slot;
-    int l = 0;
-    while (l + 1 < P.nlevels && rem >= P.lv[l + 1].cell_ofs) ++l;      // levels without cells share their successor's offset
-    const LevelGeom& G = P.lv[l];
-    const int local = rem - G.cell_ofs;
-    const int ci = local / G.nCols, j = local - ci * G.nCols;
-    g.slot = slot; g.level = l; g.cell = local;
-    g.iniY = ORB_DET_ORIGIN + ci * G.hCell;
-    const int maxY = min(g.iniY + G.hCell + 6, G.maxBY);
-    g.iniX = ORB_DET_ORIGIN + j * G.wCell;
-    const int maxX = min(g.iniX + G.wCell + 6, G.maxBX);
-    g.cw = maxX - g.iniX - 6; g.ch = maxY - g.iniY - 6;                  // detection window (FAST skips a 3-px rim)
-    if (g.iniY >= G.maxBY - 3 || g.iniX >= G.maxBX - 6 || g.ch <= 0) g.cw = 0;   // ORBextractor.cpp:793,801 / image < 7 px
+// One table entry per cell of an image (built by the host from ORBextractor.cpp:783-806, see HostPlan::celltab):
+//   x = iniX | iniY << 16,  y = cw | ch << 8 | level << 16 (cw = 0: skipped cell),  z = candidate offset
+__device__ __forceinline__ void fast_cell_geom(const uint4* __restrict__ celltab, int c, int cells_per_slot, u32 slot_magic, FastCell& g) {
+    int slot = (int)__umulhi((u32)c, slot_magic);             // c / cells_per_slot via ceil(2^32 / d); may overshoot by one
+    if (slot * cells_per_slot > c) --slot;
+    const int rem = c - slot * cells_per_slot;
+    const uint4 t = __ldg(celltab + rem);
+    g.slot = slot; g.rem = rem; g.level = (int)(t.y >> 16);
+    g.iniX = (int)(t.x & 0xffffu); g.iniY = (int)(t.x >> 16);
+    g.cw = (int)(t.y & 0xffu); g.ch = (int)((t.y >> 8) & 0xffu);
+    g.cand_ofs = (int)t.z;
 }
 
 __global__ void __launch_bounds__(FAST_WARPS * 32, 8) k_fast_cells(const __grid_constant__ Plan P, const __grid_constant__ LevelMaps M,
+                                                                   const uint4* __restrict__ celltab,
                                                                    u32* __restrict__ cand, int* __restrict__ cellcnt,
-                                                                   int total_cells, int cells_per_slot, int* __restrict__ next_cell,
+                                                                   int total_cells, int cells_per_slot, u32 slot_magic, int* __restrict__ next_cell,
                                                                    int SP /*window pitch = box width*/, int SR /*window rows = box height*/,
                                                                    int TP /*tile pitch*/, int TR /*tile rows*/,
                                                                    int LC /*list capacity*/, int RQ /*bytes of the row table*/, int WS /*bytes per warp*/) {
+    pdl_enter();
     extern __shared__ __align__(128) u8 smem[];
     __shared__ unsigned long long win_bar[FAST_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -591,7 +599,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 8) k_fast_cells(const __grid_
     unsigned long long* bar = &win_bar[warp];
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
-    // dynamic work distribution: a warp takes the next unclaimed cell (global counter, zeroed by the host before the launch), so the
+    // dynamic work distribution: a warp takes the next unclaimed cell (global counter, zeroed by this sequence's k_border0), so the
     // launch ends when the cells run out, not when the unluckiest static share does
     auto claim = [&]() { int v = 0; if (lane == 0) v = atomicAdd(next_cell, 1); return __shfl_sync(0xffffffffu, v, 0); };
     int c = claim();
@@ -604,18 +612,17 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 8) k_fast_cells(const __grid_
         mbar_expect_tx(bar, box_bytes);
         tma_box_g2s(win, maps + g.level, (g.iniX + ORB_EDGE) & ~15, g.iniY + ORB_EDGE, g.slot, bar);   // the box must start 16-byte aligned
     };
-    if (c < total_cells) { fast_cell_geom(P, c, cells_per_slot, cur); stage(cur); }
+    if (c < total_cells) { fast_cell_geom(celltab, c, cells_per_slot, slot_magic, cur); stage(cur); }
     const int iniTh = max(0, min(P.iniTh, 255)), minTh = max(0, min(P.minTh, 255));
     u32 parity = 0;
 #pragma unroll 1
     while (c < total_cells) {
-    const LevelGeom& G = P.lv[cur.level];
-    int* cnt_out = cellcnt + (size_t)cur.slot * P.ncells + G.cell_ofs + cur.cell;
+    int* cnt_out = cellcnt + (size_t)cur.slot * P.ncells + cur.rem;
     const int cw = cur.cw, ch = cur.ch;
     FastCell nxt;
     const int cn = claim();
     const bool more = cn < total_cells;
-    if (more) fast_cell_geom(P, cn, cells_per_slot, nxt);
+    if (more) fast_cell_geom(celltab, cn, cells_per_slot, slot_magic, nxt);
     if (cw <= 0) {                                          // cell the reference skips: nothing was staged for it
         if (lane == 0) *cnt_out = 0;
         if (more) stage(nxt);
@@ -627,10 +634,14 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 8) k_fast_cells(const __grid_
     mbar_wait(bar, parity);
     parity ^= 1u;
     __syncwarp();
-    const u8* s0 = win + 3 * SP + ((cur.iniX + ORB_EDGE) & 15) + 3;     // first detection pixel (the box starts at the 16-byte boundary below the window)
+    // first detection pixel = box column xo (the box starts at the 16-byte boundary below the window); everything below counts
+    // columns from the word boundary at or below it: s0 = that address, the window's columns are [xa, cwa)
+    const int xo = ((cur.iniX + ORB_EDGE) & 15) + 3, xa = xo & 3, cwa = cw + xa;
+    const u8* s0 = win + 3 * SP + (xo - xa);
+    const unsigned long long colmask = (~0ull >> (64 - cw)) << xa;          // 1 <= cw, cwa <= 64
 
     // ---- phase 1, both thresholds ----
-    fast_phase1_bits(s0, SP, cw, ch, iniTh, minTh, rowq, lane);     // four pixels per lane
+    fast_phase1_bits(s0, SP, cwa, ch, iniTh, minTh, rowq, lane);     // four pixels per lane
     // exact corner strength of list[0, n): every score >= 1 goes to the tile (a score of 0 can never win the strict NMS, so it is
     // dropped like a non-corner); entries with score >= tKeep are kept, compacted in place.  corner at T <=> best > T <=> score >= T
     auto score_list = [&](int n, int tKeep) {
@@ -664,45 +675,23 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 8) k_fast_cells(const __grid_
         __syncwarp();
         return __any_sync(0xffffffffu, any);
     };
-    // One loop body for the three list passes (a single copy of the expansion / scoring / NMS code: the kernel is sensitive to
+    // One loop body for the two attempts (a single copy of the expansion / scoring / NMS code: the kernel is sensitive to
     // instruction-cache misses):
     //   pass 0  pixels passing at iniThFAST: score, keep score >= iniThFAST, NMS (ORBextractor.cpp:808-809); done if anything survives
-    //   pass 1  vKeysCell.empty() (:811): pixels passing at minThFAST but not at iniThFAST: score only (the others are in the tile)
-    //   pass 2  all pixels passing at minThFAST: keep tile score >= minThFAST, NMS (:813-815)
+    //   pass 1  vKeysCell.empty() (:811): pixels passing at minThFAST: score, keep score >= minThFAST, NMS (:813-815)
     int nB = 0;
-    bool staged = false;
 #pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-        const int n = fast_expand(rowq, cw, ch, pass, list, lane);
-        if (pass < 2) {
-            nB = score_list(n, pass == 0 ? max(iniTh, 1) : 256);
-            if (pass == 1) {      // last pass that reads the window: the next cell's copy may start now
-                __syncwarp();
-                if (more) stage(nxt);
-                staged = true;
-                continue;
-            }
-        } else {
-            const int tKeep = max(minTh, 1);
-            nB = 0;
-            for (int b0 = 0; b0 < n; b0 += 32) {
-                const int i = b0 + lane;
-                const int e = i < n ? list[i] : 0;
-                const bool cc = i < n && tile[((e >> 6) + 1) * TP + (e & 63) + 1] >= tKeep;
-                const u32 m = __ballot_sync(0xffffffffu, cc);
-                __syncwarp();
-                if (cc) list[nB + __popc(m & lt)] = (unsigned short)e;
-                nB += __popc(m);
-            }
-            __syncwarp();
-        }
+    for (int pass = 0; pass < 2; ++pass) {
+        const int n = fast_expand(rowq, cwa, ch, colmask, pass != 0, list, lane);
+        nB = score_list(n, max(pass == 0 ? iniTh : minTh, 1));
         if (nms_list(nB) || minTh >= iniTh) break;
     }
-    if (!staged && more) { __syncwarp(); stage(nxt); }
+    __syncwarp();
+    if (more) stage(nxt);        // nothing reads the window any more: the next cell's copy may start now
     // ---- phase 5 ----
-    u32* out = cand + (size_t)cur.slot * P.cand_entries + G.cand_ofs + (size_t)cur.cell * G.cell_cap;
+    u32* out = cand + (size_t)cur.slot * P.cand_entries + cur.cand_ofs;
     int count = 0;
-    const int xrel0 = cur.iniX - ORB_DET_ORIGIN + 3, yrel0 = cur.iniY - ORB_DET_ORIGIN + 3;
+    const int xrel0 = cur.iniX - ORB_DET_ORIGIN + 3 - xa, yrel0 = cur.iniY - ORB_DET_ORIGIN + 3;
     for (int b0 = 0; b0 < nB; b0 += 32) {
         const int i = b0 + lane;
         const int e = i < nB ? list[i] : 0;

@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
                                                         u32* __restrict__ lvl_kp, int* __restrict__ lvl_cnt,
                                                         int capN, int capK, int capC, unsigned char* gnodes, size_t gnode_stride,
                                                         const unsigned char* __restrict__ roottab) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char oct_smem[];
     const int l = blockIdx.y, slot = blockIdx.x;     // slots fastest: the long level-0 CTAs of all images start first, the short top levels fill the tail
     const LevelGeom& G = P.lv[l];
