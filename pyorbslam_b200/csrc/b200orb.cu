@@ -278,8 +278,11 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
                 int cw = maxX - iniX - 6, ch = maxY - iniY - 6;              // detection window (FAST skips a 3-px rim)
                 if (iniY >= G.maxBY - 3 || iniX >= G.maxBX - 6 || ch <= 0 || cw <= 0) { cw = 0; ch = 0; }   // :793,801 / image < 7 px
                 if (iniX > 0xffff || iniY > 0xffff) return fail(B200ORB_E_ARG, "image too large for the FAST cell table");
+                // phase 1 counts columns from the word boundary at or below the first detection pixel (box column ((iniX + ORB_EDGE) & 15) + 3)
+                const int xa = (((iniX + ORB_EDGE) & 15) + 3) & 3, Q = std::max((cw + xa + 3) >> 2, 1);
+                const unsigned rcp = (65536u + Q - 1) / Q, dr = 32u / Q;
                 hp.celltab[G.cell_ofs + local] = make_uint4((unsigned)iniX | ((unsigned)iniY << 16), (unsigned)cw | ((unsigned)ch << 8) | ((unsigned)l << 16),
-                                                            (unsigned)(G.cand_ofs + local * G.cell_cap), 0u);
+                                                            (unsigned)(G.cand_ofs + local * G.cell_cap), rcp | (dr << 17) | ((unsigned)Q << 23));
             }
     }
     hp.fast_WS = round_up(hp.fast_SP * hp.fast_SR + hp.fast_TP * hp.fast_TR + hp.fast_LC * 2 + hp.fast_RQ + 16, 128);   // +16: phase 1 reads whole words past the last row

@@ -400,10 +400,10 @@ __device__ __forceinline__ void fast_quick2(u32 v, u32 a, u32 b, u32 c, u32 d, u
 // first column sits up to 3 px into its first group; those leading bits are masked off by fast_expand), so centre, y-3 and y+3
 // are single aligned words and x-3 / x+3 one constant funnel shift each.  (The kernel used to lay the groups on the window's own
 // columns: eight loads, five variable shifts and four selects per group instead of five loads and two shifts.)
-__device__ __forceinline__ u32 fast_quick4(const u8* o, int SP, u32 Ti, u32 Tm) {
-    const u32* wc = reinterpret_cast<const u32*>(o);
+__device__ __forceinline__ u32 fast_quick4(const u8* ob /* the group's address 3 rows up */, int SP3, int SP6, u32 Ti, u32 Tm) {
+    const u32* wc = reinterpret_cast<const u32*>(ob + SP3);
     const u32 cl = wc[-1], C = wc[0], cr = wc[1];
-    const u32 T = *reinterpret_cast<const u32*>(o + 3 * SP), B = *reinterpret_cast<const u32*>(o - 3 * SP);
+    const u32 T = *reinterpret_cast<const u32*>(ob + SP6), B = *reinterpret_cast<const u32*>(ob);
     const u32 L = __funnelshift_r(cl, C, 8);           // bytes -3 .. 0
     const u32 R = __funnelshift_r(C, cr, 24);          // bytes  3 .. 6
     u32 ei, em, oi, om;
@@ -420,21 +420,23 @@ __device__ __forceinline__ u32 fast_quick4(const u8* o, int SP, u32 Ti, u32 Tm) 
 // the window's right edge (<= 64).  A lane tests 4 consecutive pixels of a row and drops the two nibbles (one 16-bit store) into
 // a per-row table rowq[row][quad] (8 quads per row for up to 32 columns, 16 beyond).  The Q = ceil(cwa / 4) quads of all rows are
 // dealt to the lanes as one sequence (item = row * Q + quad, lane + 32 * step): no lane idles whatever Q is.
-__device__ __forceinline__ void fast_phase1_bits(const u8* sa, int SP, int cwa, int ch, int Ti, int Tm, unsigned short* rowq, int lane) {
+__device__ __forceinline__ void fast_phase1_bits(const u8* sa, int SP, int cwa, int ch, int Q, u32 rcp, int dr, int Ti, int Tm,
+                                                 unsigned short* rowq, int lane) {
     const int sh = cwa > 32 ? 4 : 3;
     const u32 ti = (u32)Ti * 0x00010001u, tm = (u32)Tm * 0x00010001u;
-    const int Q = (cwa + 3) >> 2;                        // 1 .. 16
-    const u32 rcp = (65536u + (u32)Q - 1u) / (u32)Q;     // n / Q == (n * rcp) >> 16 for n <= 32
-    int row = (int)(((u32)lane * rcp) >> 16), quad = lane - row * Q;
-    const int dr = (int)((32u * rcp) >> 16), dq = 32 - dr * Q;
-    const u8* o = sa + row * SP + 4 * quad;
+    // Q = ceil(cwa / 4) in 1 .. 16, rcp = ceil(65536 / Q): n / Q == (n * rcp) >> 16 for n <= 32, dr = 32 / Q (all from the cell table)
+    const int row = (int)(((u32)lane * rcp) >> 16), dq = 32 - dr * Q, SP3 = 3 * SP, SP6 = 6 * SP;
+    int quad = lane - row * Q;
+    const u8* ob = sa - SP3 + row * SP + 4 * quad;         // the lane's group, 3 rows up (the y-3 operand)
+    const u8* const oend = sa - SP3 + ch * SP;
     unsigned short* rb = rowq + (row << sh) + quad;
-    const int stepO = dr * SP + 4 * dq, stepR = (dr << sh) + dq, wrapO = SP - 4 * Q, wrapR = (1 << sh) - Q;
+    const int stepO = dr * SP + 4 * dq, stepR = (dr << sh) + dq, stepOw = stepO + SP - 4 * Q, stepRw = stepR + (1 << sh) - Q;
 #pragma unroll 2
-    while (row < ch) {
-        *rb = (unsigned short)fast_quick4(o, SP, ti, tm);
-        quad += dq; row += dr; o += stepO; rb += stepR;
-        if (quad >= Q) { quad -= Q; ++row; o += wrapO; rb += wrapR; }
+    while (ob < oend) {
+        *rb = (unsigned short)fast_quick4(ob, SP3, SP6, ti, tm);
+        quad += dq;
+        const bool wrap = quad >= Q;
+        ob += wrap ? stepOw : stepO; rb += wrap ? stepRw : stepR; quad -= wrap ? Q : 0;
     }
     __syncwarp();
 }
@@ -565,9 +567,10 @@ struct FastCell {            // geometry of one cell (warp-uniform)
     int slot, level, rem;    // rem = cell index inside the slot (all levels)
     int iniX, iniY, cw, ch;  // window origin (incl. the 3-px rim, level coordinates) and detection size; cw <= 0: the reference skips the cell
     int cand_ofs;            // u32 index of the cell's candidate storage inside the slot's blob
+    u32 deal;                // phase-1 lane dealing: rcp | dr << 17 | Q << 23 (see fast_phase1_bits)
 };
 // One table entry per cell of an image (built by the host from ORBextractor.cpp:783-806, see HostPlan::celltab):
-//   x = iniX | iniY << 16,  y = cw | ch << 8 | level << 16 (cw = 0: skipped cell),  z = candidate offset
+//   x = iniX | iniY << 16,  y = cw | ch << 8 | level << 16 (cw = 0: skipped cell),  z = candidate offset,  w = lane dealing of phase 1
 __device__ __forceinline__ void fast_cell_geom(const uint4* __restrict__ celltab, int c, int cells_per_slot, u32 slot_magic, FastCell& g) {
     int slot = (int)__umulhi((u32)c, slot_magic);             // c / cells_per_slot via ceil(2^32 / d); may overshoot by one
     if (slot * cells_per_slot > c) --slot;
@@ -576,7 +579,7 @@ __device__ __forceinline__ void fast_cell_geom(const uint4* __restrict__ celltab
     g.slot = slot; g.rem = rem; g.level = (int)(t.y >> 16);
     g.iniX = (int)(t.x & 0xffffu); g.iniY = (int)(t.x >> 16);
     g.cw = (int)(t.y & 0xffu); g.ch = (int)((t.y >> 8) & 0xffu);
-    g.cand_ofs = (int)t.z;
+    g.cand_ofs = (int)t.z; g.deal = t.w;
 }
 
 __global__ void __launch_bounds__(FAST_WARPS * 32, 8) k_fast_cells(const __grid_constant__ Plan P, const __grid_constant__ LevelMaps M,
@@ -641,7 +644,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 8) k_fast_cells(const __grid_
     const unsigned long long colmask = (~0ull >> (64 - cw)) << xa;          // 1 <= cw, cwa <= 64
 
     // ---- phase 1, both thresholds ----
-    fast_phase1_bits(s0, SP, cwa, ch, iniTh, minTh, rowq, lane);     // four pixels per lane
+    fast_phase1_bits(s0, SP, cwa, ch, (int)(cur.deal >> 23), cur.deal & 0x1ffffu, (int)((cur.deal >> 17) & 63u), iniTh, minTh, rowq, lane);     // four pixels per lane
     // exact corner strength of list[0, n): every score >= 1 goes to the tile (a score of 0 can never win the strict NMS, so it is
     // dropped like a non-corner); entries with score >= tKeep are kept, compacted in place.  corner at T <=> best > T <=> score >= T
     auto score_list = [&](int n, int tKeep) {
