@@ -495,7 +495,7 @@ struct Engine {
             const int total = n * hp.fast_cells;
             const int ctas = std::min((total + FAST_WARPS - 1) / FAST_WARPS, sm_count * 8);
             // the cell counter was zeroed by this sequence's k_border0
-            CU_TRY(launch_seq(8, k_fast_cells, dim3(ctas), dim3(FAST_WARPS * 32), hp.fast_smem, st, P, hp.maps, (const uint4*)d_celltab, d_cand, d_cellcnt, total, hp.fast_cells, magic_of(hp.fast_cells), d_fastctr,
+            CU_TRY(launch_seq(8, k_fast_cells, dim3(ctas), dim3(FAST_WARPS * 32), hp.fast_smem, st, P, hp.maps, (const uint4*)d_celltab, d_cand, d_cellcnt, total, hp.fast_cells, magic_of(hp.fast_cells), d_fastctr, 1u,
                               hp.fast_SP, hp.fast_SR, hp.fast_TP, hp.fast_TR, hp.fast_LC, hp.fast_RQ, hp.fast_WS));
             ++g_launches;
         }

@@ -388,19 +388,27 @@ __device__ __forceinline__ bool fast_quick(const u8* p, int SP, int t) {
 //   bright at t <=> min(max(a,b), max(c,d)) - v > t,   dark at t <=> v - max(min(a,b), min(c,d)) > t
 // With A = mn + 0x7fff - v and B = v + 0x7fff - mx per lane (both inside [0x7f00, 0x80fe]: no carry, no borrow),
 // (A - t) | (B - t) has bit 15 of a lane set <=> the pixel passes at t.  ri / rm: bit 15 / 31 = pixel of the low / high lane.
-__device__ __forceinline__ void fast_quick2(u32 v, u32 a, u32 b, u32 c, u32 d, u32 Ti, u32 Tm, u32& ri, u32& rm) {
+// The adds run as multiply-adds (x * one + y, `one` an opaque register holding 1) and the flag bits are gathered with
+// multiply-high: this loop is bound by the ALU pipe (min/max, byte permutes, logic), the FMA pipe that executes IMAD idles.
+// Ki / Km = 0x7fff7fff - t * 0x10001.
+__device__ __forceinline__ u32 mad_lo(u32 a, u32 b, u32 c) {
+    u32 d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ void fast_quick2(u32 v, u32 a, u32 b, u32 c, u32 d, u32 Ki, u32 Km, u32 one, u32 mone, u32& ri, u32& rm) {
     const u32 mn = __vminu2(__vmaxu2(a, b), __vmaxu2(c, d));
     const u32 mx = __vmaxu2(__vminu2(a, b), __vminu2(c, d));
-    const u32 A = mn + (0x7fff7fffu - v), B = (v + 0x7fff7fffu) - mx;
-    ri = ((A - Ti) | (B - Ti)) & 0x80008000u;
-    rm = ((A - Tm) | (B - Tm)) & 0x80008000u;
+    const u32 X = mad_lo(v, mone, mn), Y = mad_lo(mx, mone, v);          // mn - v, v - mx per 16-bit lane (borrows cancel against K)
+    ri = (mad_lo(X, one, Ki) | mad_lo(Y, one, Ki)) & 0x80008000u;
+    rm = (mad_lo(X, one, Km) | mad_lo(Y, one, Km)) & 0x80008000u;
 }
 // -> min-threshold nibble in bits 0..3, ini-threshold nibble in bits 8..11 (bit k = pixel k passes).
-// o = address of the first of the four pixels, a multiple of 4: the groups are laid on the shared-memory word grid (the window's
-// first column sits up to 3 px into its first group; those leading bits are masked off by fast_expand), so centre, y-3 and y+3
-// are single aligned words and x-3 / x+3 one constant funnel shift each.  (The kernel used to lay the groups on the window's own
-// columns: eight loads, five variable shifts and four selects per group instead of five loads and two shifts.)
-__device__ __forceinline__ u32 fast_quick4(const u8* ob /* the group's address 3 rows up */, int SP3, int SP6, u32 Ti, u32 Tm) {
+// ob = address of the first of the four pixels, 3 rows up; a multiple of 4: the groups are laid on the shared-memory word grid
+// (the window's first column sits up to 3 px into its first group; those leading bits are masked off by fast_expand), so centre,
+// y-3 and y+3 are single aligned words and x-3 / x+3 one constant funnel shift each.  (The kernel used to lay the groups on the
+// window's own columns: eight loads, five variable shifts and four selects per group instead of five loads and two shifts.)
+__device__ __forceinline__ u32 fast_quick4(const u8* ob, int SP3, int SP6, u32 Ki, u32 Km, u32 one, u32 mone) {
     const u32* wc = reinterpret_cast<const u32*>(ob + SP3);
     const u32 cl = wc[-1], C = wc[0], cr = wc[1];
     const u32 T = *reinterpret_cast<const u32*>(ob + SP6), B = *reinterpret_cast<const u32*>(ob);
@@ -408,22 +416,26 @@ __device__ __forceinline__ u32 fast_quick4(const u8* ob /* the group's address 3
     const u32 R = __funnelshift_r(C, cr, 24);          // bytes  3 .. 6
     u32 ei, em, oi, om;
     fast_quick2(__byte_perm(C, 0, 0x4240), __byte_perm(T, 0, 0x4240), __byte_perm(B, 0, 0x4240),
-                __byte_perm(R, 0, 0x4240), __byte_perm(L, 0, 0x4240), Ti, Tm, ei, em);            // pixels 0 | 2
+                __byte_perm(R, 0, 0x4240), __byte_perm(L, 0, 0x4240), Ki, Km, one, mone, ei, em);            // pixels 0 | 2
     fast_quick2(__byte_perm(C, 0, 0x4341), __byte_perm(T, 0, 0x4341), __byte_perm(B, 0, 0x4341),
-                __byte_perm(R, 0, 0x4341), __byte_perm(L, 0, 0x4341), Ti, Tm, oi, om);            // pixels 1 | 3
-    const u32 e = ei | (em >> 8), o2 = oi | (om >> 8);      // bits 15 / 31 = ini, bits 7 / 23 = min
-    const u32 x = (e >> 7) | (o2 >> 6);                     // min: bits 0,1,16,17   ini: bits 8,9,24,25
-    return (x | (x >> 14)) & 0x0f0fu;
+                __byte_perm(R, 0, 0x4341), __byte_perm(L, 0, 0x4341), Ki, Km, one, mone, oi, om);            // pixels 1 | 3
+    // a word holds its two flags at bits 15 and 31; the high half of word * (2^(17+t) + 2^(3+t)) has them at bits t and t + 2
+    // (plus a stray copy at bit 16 + t): t = 0 / 1 for the min flags of pixels 0|2 / 1|3, t = 8 / 9 for the ini flags
+    u32 r = __umulhi(em, (1u << 17) + (1u << 3));
+    r += __umulhi(om, (1u << 18) + (1u << 4));
+    r += __umulhi(ei, (1u << 25) + (1u << 11));
+    r += __umulhi(oi, (1u << 26) + (1u << 12));
+    return r & 0x0f0fu;
 }
 
 // Phase 1 of a cell.  sa = the word-aligned address at or below the window's first detection pixel, cwa = columns from there to
 // the window's right edge (<= 64).  A lane tests 4 consecutive pixels of a row and drops the two nibbles (one 16-bit store) into
 // a per-row table rowq[row][quad] (8 quads per row for up to 32 columns, 16 beyond).  The Q = ceil(cwa / 4) quads of all rows are
 // dealt to the lanes as one sequence (item = row * Q + quad, lane + 32 * step): no lane idles whatever Q is.
-__device__ __forceinline__ void fast_phase1_bits(const u8* sa, int SP, int cwa, int ch, int Q, u32 rcp, int dr, int Ti, int Tm,
+__device__ __forceinline__ void fast_phase1_bits(const u8* sa, int SP, int cwa, int ch, int Q, u32 rcp, int dr, int Ti, int Tm, u32 one,
                                                  unsigned short* rowq, int lane) {
     const int sh = cwa > 32 ? 4 : 3;
-    const u32 ti = (u32)Ti * 0x00010001u, tm = (u32)Tm * 0x00010001u;
+    const u32 ki = 0x7fff7fffu - (u32)Ti * 0x00010001u, km = 0x7fff7fffu - (u32)Tm * 0x00010001u, mone = 0u - one;
     // Q = ceil(cwa / 4) in 1 .. 16, rcp = ceil(65536 / Q): n / Q == (n * rcp) >> 16 for n <= 32, dr = 32 / Q (all from the cell table)
     const int row = (int)(((u32)lane * rcp) >> 16), dq = 32 - dr * Q, SP3 = 3 * SP, SP6 = 6 * SP;
     int quad = lane - row * Q;
@@ -433,7 +445,7 @@ __device__ __forceinline__ void fast_phase1_bits(const u8* sa, int SP, int cwa, 
     const int stepO = dr * SP + 4 * dq, stepR = (dr << sh) + dq, stepOw = stepO + SP - 4 * Q, stepRw = stepR + (1 << sh) - Q;
 #pragma unroll 2
     while (ob < oend) {
-        *rb = (unsigned short)fast_quick4(ob, SP3, SP6, ti, tm);
+        *rb = (unsigned short)fast_quick4(ob, SP3, SP6, ki, km, one, mone);
         quad += dq;
         const bool wrap = quad >= Q;
         ob += wrap ? stepOw : stepO; rb += wrap ? stepRw : stepR; quad -= wrap ? Q : 0;
@@ -586,6 +598,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 8) k_fast_cells(const __grid_
                                                                    const uint4* __restrict__ celltab,
                                                                    u32* __restrict__ cand, int* __restrict__ cellcnt,
                                                                    int total_cells, int cells_per_slot, u32 slot_magic, int* __restrict__ next_cell,
+                                                                   u32 one /* = 1, opaque to the compiler: see fast_quick2 */,
                                                                    int SP /*window pitch = box width*/, int SR /*window rows = box height*/,
                                                                    int TP /*tile pitch*/, int TR /*tile rows*/,
                                                                    int LC /*list capacity*/, int RQ /*bytes of the row table*/, int WS /*bytes per warp*/) {
@@ -644,7 +657,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 8) k_fast_cells(const __grid_
     const unsigned long long colmask = (~0ull >> (64 - cw)) << xa;          // 1 <= cw, cwa <= 64
 
     // ---- phase 1, both thresholds ----
-    fast_phase1_bits(s0, SP, cwa, ch, (int)(cur.deal >> 23), cur.deal & 0x1ffffu, (int)((cur.deal >> 17) & 63u), iniTh, minTh, rowq, lane);     // four pixels per lane
+    fast_phase1_bits(s0, SP, cwa, ch, (int)(cur.deal >> 23), cur.deal & 0x1ffffu, (int)((cur.deal >> 17) & 63u), iniTh, minTh, one, rowq, lane);     // four pixels per lane
     // exact corner strength of list[0, n): every score >= 1 goes to the tile (a score of 0 can never win the strict NMS, so it is
     // dropped like a non-corner); entries with score >= tKeep are kept, compacted in place.  corner at T <=> best > T <=> score >= T
     auto score_list = [&](int n, int tKeep) {
