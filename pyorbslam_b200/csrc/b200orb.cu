@@ -1312,9 +1312,12 @@ int b200orb_batch_run_host_shard(b200orb_batch* b, const uint8_t* h_left, const 
     b->h_status_n = n_pairs;
     // chunk schedule: full chunks of max_pairs, with a short ramp at both ends of a long job (P/4, P/2, P ... P, P/2, P/4) so that the
     // first kernels start after a quarter-chunk upload and only a quarter-chunk download is left when the last kernels finish
+    // With two compute lanes the chunks are half the engine's capacity: a chunk's kernels then take longer than the next chunk's
+    // upload, so consecutive chunks do overlap on the GPU (with full chunks the next upload ends just as the kernels do), and the
+    // job ends half as long after its last upload.
     std::vector<int> sizes;
     {
-        const int P = b->P;
+        const int P = (b->lanes == 2 && b->P >= 16) ? b->P / 2 : b->P;
         int left = n_pairs;
         std::vector<int> tail;
         if (n_pairs >= 4 * P && P >= 8) {
