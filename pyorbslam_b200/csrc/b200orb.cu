@@ -264,8 +264,10 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
     hp.fast_TR = round_up(maxh + 2, 4);       // TP * TR is a multiple of 16: the tiles are cleared with 128-bit stores
     // wCell = ceil(width / floor(width / 30)) <= 59 whenever the level has cells at all
     if (maxwa > 64 || maxh > 63) return fail(B200ORB_E_ARG, "FAST cell larger than 61 x 63 px");
-    hp.fast_LC = round_up(std::max(maxw * maxh, 2), 8);            // 16-byte multiple
-    hp.fast_RQ = 2 * round_up(std::max(maxh, 1), 4) * (maxwa > 32 ? 16 : 8);   // per warp: rows x quads x (min | ini nibble pair)
+    // work list: half the window's pixels (a cell with more passing pixels is walked in row bands), at least one 64-pixel row
+    static const int lc_env = [] { const char* v = getenv("B200ORB_FAST_LC"); return v ? atoi(v) : 0; }();     // tests: force the banded path
+    hp.fast_LC = round_up(std::max(lc_env > 0 ? lc_env : maxw * maxh / 2, 64), 8);            // 16-byte multiple
+    hp.fast_RQ = round_up(std::max(maxh, 1), 4) * (maxwa > 32 ? 16 : 8);   // per warp: rows x quads x (min | ini nibble pair in a byte)
     // cell table (ORBextractor.cpp:783-806): window origin, detection size, level and candidate offset of every cell of an image
     hp.celltab.assign(std::max(cells, 1), make_uint4(0u, 0u, 0u, 0u));
     for (int l = 0; l < P.nlevels; ++l) {

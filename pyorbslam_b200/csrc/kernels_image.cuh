@@ -403,7 +403,7 @@ __device__ __forceinline__ void fast_quick2(u32 v, u32 a, u32 b, u32 c, u32 d, u
     ri = (mad_lo(X, one, Ki) | mad_lo(Y, one, Ki)) & 0x80008000u;
     rm = (mad_lo(X, one, Km) | mad_lo(Y, one, Km)) & 0x80008000u;
 }
-// -> min-threshold nibble in bits 0..3, ini-threshold nibble in bits 8..11 (bit k = pixel k passes).
+// -> min-threshold nibble in bits 0..3, ini-threshold nibble in bits 4..7 (bit k = pixel k passes); bits above 7 are scrap.
 // ob = address of the first of the four pixels, 3 rows up; a multiple of 4: the groups are laid on the shared-memory word grid
 // (the window's first column sits up to 3 px into its first group; those leading bits are masked off by fast_expand), so centre,
 // y-3 and y+3 are single aligned words and x-3 / x+3 one constant funnel shift each.  (The kernel used to lay the groups on the
@@ -420,20 +420,20 @@ __device__ __forceinline__ u32 fast_quick4(const u8* ob, int SP3, int SP6, u32 K
     fast_quick2(__byte_perm(C, 0, 0x4341), __byte_perm(T, 0, 0x4341), __byte_perm(B, 0, 0x4341),
                 __byte_perm(R, 0, 0x4341), __byte_perm(L, 0, 0x4341), Ki, Km, one, mone, oi, om);            // pixels 1 | 3
     // a word holds its two flags at bits 15 and 31; the high half of word * (2^(17+t) + 2^(3+t)) has them at bits t and t + 2
-    // (plus a stray copy at bit 16 + t): t = 0 / 1 for the min flags of pixels 0|2 / 1|3, t = 8 / 9 for the ini flags
+    // (plus a stray copy at bit 16 + t): t = 0 / 1 for the min flags of pixels 0|2 / 1|3, t = 4 / 5 for the ini flags
     u32 r = __umulhi(em, (1u << 17) + (1u << 3));
     r += __umulhi(om, (1u << 18) + (1u << 4));
-    r += __umulhi(ei, (1u << 25) + (1u << 11));
-    r += __umulhi(oi, (1u << 26) + (1u << 12));
-    return r & 0x0f0fu;
+    r += __umulhi(ei, (1u << 21) + (1u << 7));
+    r += __umulhi(oi, (1u << 22) + (1u << 8));
+    return r;        // the caller stores the low byte
 }
 
 // Phase 1 of a cell.  sa = the word-aligned address at or below the window's first detection pixel, cwa = columns from there to
 // the window's right edge (<= 64).  A lane tests 4 consecutive pixels of a row and drops the two nibbles (one 16-bit store) into
-// a per-row table rowq[row][quad] (8 quads per row for up to 32 columns, 16 beyond).  The Q = ceil(cwa / 4) quads of all rows are
+// a per-row byte table rowq[row][quad] (8 quads per row for up to 32 columns, 16 beyond).  The Q = ceil(cwa / 4) quads of all rows are
 // dealt to the lanes as one sequence (item = row * Q + quad, lane + 32 * step): no lane idles whatever Q is.
 __device__ __forceinline__ void fast_phase1_bits(const u8* sa, int SP, int cwa, int ch, int Q, u32 rcp, int dr, int Ti, int Tm, u32 one,
-                                                 unsigned short* rowq, int lane) {
+                                                 u8* rowq, int lane) {
     const int sh = cwa > 32 ? 4 : 3;
     const u32 ki = 0x7fff7fffu - (u32)Ti * 0x00010001u, km = 0x7fff7fffu - (u32)Tm * 0x00010001u, mone = 0u - one;
     // Q = ceil(cwa / 4) in 1 .. 16, rcp = ceil(65536 / Q): n / Q == (n * rcp) >> 16 for n <= 32, dr = 32 / Q (all from the cell table)
@@ -441,11 +441,11 @@ __device__ __forceinline__ void fast_phase1_bits(const u8* sa, int SP, int cwa, 
     int quad = lane - row * Q;
     const u8* ob = sa - SP3 + row * SP + 4 * quad;         // the lane's group, 3 rows up (the y-3 operand)
     const u8* const oend = sa - SP3 + ch * SP;
-    unsigned short* rb = rowq + (row << sh) + quad;
+    u8* rb = rowq + (row << sh) + quad;
     const int stepO = dr * SP + 4 * dq, stepR = (dr << sh) + dq, stepOw = stepO + SP - 4 * Q, stepRw = stepR + (1 << sh) - Q;
 #pragma unroll 2
     while (ob < oend) {
-        *rb = (unsigned short)fast_quick4(ob, SP3, SP6, ki, km, one, mone);
+        *rb = (u8)fast_quick4(ob, SP3, SP6, ki, km, one, mone);
         quad += dq;
         const bool wrap = quad >= Q;
         ob += wrap ? stepOw : stepO; rb += wrap ? stepRw : stepR; quad -= wrap ? Q : 0;
@@ -455,48 +455,54 @@ __device__ __forceinline__ void fast_phase1_bits(const u8* sa, int SP, int cwa, 
 
 // Row-major work list of a cell from the phase-1 table: lane r turns the masks of rows r and r + 32 into list entries (y << 6 | x)
 // at the offsets an exclusive warp scan of the row counts gives -- row-major order by construction, no per-pixel ballot.
-// x counts from the aligned origin (see fast_phase1_bits): colmask keeps columns [a, cwa).
+// x counts from the aligned origin (see fast_phase1_bits): colmask keeps columns [a, cwa).  Only rows [r0, r1) are listed.
 // useMin = false: pixels passing at iniThFAST;  true: pixels passing at minThFAST.
-__device__ __forceinline__ int fast_expand(const unsigned short* rowq, int cwa, int ch, unsigned long long colmask, bool useMin,
-                                           unsigned short* list, int lane) {
+// Returns the number of entries; when that exceeds the list capacity LC nothing is written (the caller then walks row bands).
+__device__ __forceinline__ int fast_expand(const u8* rowq, int cwa, int ch, unsigned long long colmask, bool useMin, int r0, int r1,
+                                           unsigned short* list, int LC, int lane) {
     const bool wide = cwa > 32;
-    // a 32-bit word holds two quads: min nibbles at bits 0..3 / 16..19, ini nibbles at bits 8..11 / 24..27
-    const int nsh = useMin ? 0 : 8;
-    auto nib = [nsh](u32 w) { w >>= nsh; return (w & 0xfu) | ((w >> 12) & 0xf0u); };
+    const int nsh = useMin ? 0 : 4;
+    // a byte holds one quad: min nibble | ini nibble << 4; squeeze the chosen nibbles of a word's four quads into 16 bits
+    auto nib4 = [nsh](u32 w) { w = (w >> nsh) & 0x0f0f0f0fu; w = (w | (w >> 4)) & 0x00ff00ffu; return (w | (w >> 8)) & 0xffffu; };
     unsigned long long m[2] = {0ull, 0ull};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int row = lane + 32 * h;
-        if (row < ch) {
-            const uint4 w = *reinterpret_cast<const uint4*>(rowq + row * (wide ? 16 : 8));
-            unsigned long long mm = nib(w.x) | (nib(w.y) << 8) | (nib(w.z) << 16) | (nib(w.w) << 24);
+        if (row < min(ch, r1) && row >= r0) {
+            unsigned long long mm;
             if (wide) {
-                const uint4 w2 = *reinterpret_cast<const uint4*>(rowq + row * 16 + 8);
-                mm |= (unsigned long long)(nib(w2.x) | (nib(w2.y) << 8) | (nib(w2.z) << 16) | (nib(w2.w) << 24)) << 32;
+                const uint4 w = *reinterpret_cast<const uint4*>(rowq + row * 16);
+                mm = (unsigned long long)(nib4(w.x) | (nib4(w.y) << 16)) | ((unsigned long long)(nib4(w.z) | (nib4(w.w) << 16)) << 32);
+            } else {
+                const uint2 w = *reinterpret_cast<const uint2*>(rowq + row * 8);
+                mm = nib4(w.x) | (nib4(w.y) << 16);
             }
             m[h] = mm & colmask;
         }
     }
-    int base = 0;
+    const int c0 = __popcll(m[0]), c1 = __popcll(m[1]);
+    // one inclusive scan for both halves: rows 0..31 in the low 16 bits, rows 32..63 in the high ones (a row has at most 64 entries,
+    // 32 rows at most 2048: no carry between the halves)
+    int incl = c0 | (c1 << 16);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    const int n0 = tot & 0xffff, n = n0 + (tot >> 16);
+    if (n > LC) return n;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         if (h == 1 && ch <= 32) break;
-        const int c = __popcll(m[h]);
-        int incl = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += up;
-        }
-        unsigned short* w = list + base + (incl - c);
+        unsigned short* w = list + (h ? n0 + (incl >> 16) - c1 : (incl & 0xffff) - c0);
         const int ybits = (lane + 32 * h) << 6;
         u32 lo = (u32)m[h], hi = (u32)(m[h] >> 32);
         while (lo) { *w++ = (unsigned short)(ybits | (__ffs(lo) - 1)); lo &= lo - 1; }
         while (hi) { *w++ = (unsigned short)(ybits | (__ffs(hi) + 31)); hi &= hi - 1; }
-        base += __shfl_sync(0xffffffffu, incl, 31);
     }
     __syncwarp();
-    return base;
+    return n;
 }
 
 // 9-of-16 segment test (strictly brighter than v+t or strictly darker than v-t on 9 contiguous ring pixels).
@@ -611,7 +617,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 8) k_fast_cells(const __grid_
     u8* win = smem + (size_t)warp * WS;
     u8* tile = win + SP * SR;
     unsigned short* list = reinterpret_cast<unsigned short*>(tile + TP * TR);
-    unsigned short* rowq = list + LC;
+    u8* rowq = reinterpret_cast<u8*>(list + LC);
     unsigned long long* bar = &win_bar[warp];
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
@@ -691,33 +697,71 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 8) k_fast_cells(const __grid_
         __syncwarp();
         return __any_sync(0xffffffffu, any);
     };
+    // keep the entries whose tile score is >= tKeep (in place)
+    auto filter_list = [&](int n, int tKeep) {
+        int kept = 0;
+        for (int b0 = 0; b0 < n; b0 += 32) {
+            const int i = b0 + lane;
+            const int e = i < n ? list[i] : 0;
+            const bool cc = i < n && tile[((e >> 6) + 1) * TP + (e & 63) + 1] >= tKeep;
+            const u32 m = __ballot_sync(0xffffffffu, cc);
+            __syncwarp();
+            if (cc) list[kept + __popc(m & lt)] = (unsigned short)e;
+            kept += __popc(m);
+        }
+        __syncwarp();
+        return kept;
+    };
+    // ---- phase 5: ordered emission of the flagged entries of list[0, n), appended at out[count...] ----
+    u32* out = cand + (size_t)cur.slot * P.cand_entries + cur.cand_ofs;
+    const int xrel0 = cur.iniX - ORB_DET_ORIGIN + 3 - xa, yrel0 = cur.iniY - ORB_DET_ORIGIN + 3;
+    auto emit_list = [&](int n, int count) {
+        for (int b0 = 0; b0 < n; b0 += 32) {
+            const int i = b0 + lane;
+            const int e = i < n ? list[i] : 0;
+            const int y = (e >> 6) & 63, x = e & 63;
+            const int sc = tile[(y + 1) * TP + x + 1];
+            const bool keep = (e & 0x8000) != 0;
+            const u32 m = __ballot_sync(0xffffffffu, keep);
+            if (keep) out[count + __popc(m & lt)] = (u32)(xrel0 + x) | ((u32)(yrel0 + y) << 12) | ((u32)sc << 24);
+            count += __popc(m);
+        }
+        return count;
+    };
     // One loop body for the two attempts (a single copy of the expansion / scoring / NMS code: the kernel is sensitive to
     // instruction-cache misses):
     //   pass 0  pixels passing at iniThFAST: score, keep score >= iniThFAST, NMS (ORBextractor.cpp:808-809); done if anything survives
     //   pass 1  vKeysCell.empty() (:811): pixels passing at minThFAST: score, keep score >= minThFAST, NMS (:813-815)
-    int nB = 0;
+    // The list holds LC entries (half the window).  A cell with more passing pixels (noise, dense texture at a low threshold) is
+    // walked in bands of LC / 64 rows: first every band is scored into the tile, then every band is listed again, cut at the
+    // threshold by its tile scores, suppressed and emitted -- bands in row order, so the output order is the same.
+    int nB = 0, count = -1;         // count >= 0: the banded path has emitted already
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-        const int n = fast_expand(rowq, cwa, ch, colmask, pass != 0, list, lane);
-        nB = score_list(n, max(pass == 0 ? iniTh : minTh, 1));
-        if (nms_list(nB) || minTh >= iniTh) break;
+        const int tKeep = max(pass == 0 ? iniTh : minTh, 1);
+        const int n = fast_expand(rowq, cwa, ch, colmask, pass != 0, 0, 64, list, LC, lane);
+        if (n <= LC) {
+            nB = score_list(n, tKeep);
+            if (nms_list(nB) || minTh >= iniTh) break;
+        } else {
+            const int rpb = LC >> 6;
+#pragma unroll 1
+            for (int r0 = 0; r0 < ch; r0 += rpb) score_list(fast_expand(rowq, cwa, ch, colmask, pass != 0, r0, r0 + rpb, list, LC, lane), 256);
+            count = 0;
+#pragma unroll 1
+            for (int r0 = 0; r0 < ch; r0 += rpb) {
+                const int nb = filter_list(fast_expand(rowq, cwa, ch, colmask, pass != 0, r0, r0 + rpb, list, LC, lane), tKeep);
+                nms_list(nb);
+                count = emit_list(nb, count);
+                __syncwarp();
+            }
+            if (count > 0 || minTh >= iniTh) break;
+            count = -1;
+        }
     }
     __syncwarp();
     if (more) stage(nxt);        // nothing reads the window any more: the next cell's copy may start now
-    // ---- phase 5 ----
-    u32* out = cand + (size_t)cur.slot * P.cand_entries + cur.cand_ofs;
-    int count = 0;
-    const int xrel0 = cur.iniX - ORB_DET_ORIGIN + 3 - xa, yrel0 = cur.iniY - ORB_DET_ORIGIN + 3;
-    for (int b0 = 0; b0 < nB; b0 += 32) {
-        const int i = b0 + lane;
-        const int e = i < nB ? list[i] : 0;
-        const int y = (e >> 6) & 63, x = e & 63;
-        const int sc = tile[(y + 1) * TP + x + 1];
-        const bool keep = (e & 0x8000) != 0;
-        const u32 m = __ballot_sync(0xffffffffu, keep);
-        if (keep) out[count + __popc(m & lt)] = (u32)(xrel0 + x) | ((u32)(yrel0 + y) << 12) | ((u32)sc << 24);
-        count += __popc(m);
-    }
+    if (count < 0) count = emit_list(nB, 0);
     if (lane == 0) *cnt_out = count;
     __syncwarp();
     cur = nxt; c = cn;
