@@ -265,7 +265,8 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
     // wCell = ceil(width / floor(width / 30)) <= 59 whenever the level has cells at all
     if (maxwa > 64 || maxh > 63) return fail(B200ORB_E_ARG, "FAST cell larger than 61 x 63 px");
     // work list: half the window's pixels (a cell with more passing pixels is walked in row bands), at least one 64-pixel row
-    static const int lc_env = [] { const char* v = getenv("B200ORB_FAST_LC"); return v ? atoi(v) : 0; }();     // tests: force the banded path
+    const char* lc_str = getenv("B200ORB_FAST_LC");           // tests: a small capacity forces the banded path
+    const int lc_env = lc_str ? atoi(lc_str) : 0;
     hp.fast_LC = round_up(std::max(lc_env > 0 ? lc_env : maxw * maxh / 2, 64), 8);            // 16-byte multiple
     hp.fast_RQ = round_up(std::max(maxh, 1), 4) * (maxwa > 32 ? 16 : 8);   // per warp: rows x quads x (min | ini nibble pair in a byte)
     // cell table (ORBextractor.cpp:783-806): window origin, detection size, level and candidate offset of every cell of an image

@@ -174,3 +174,57 @@ def test_multi_gpu_runner_equals_single_engine():
                 assert torch.equal(got[key][i, :nl], one[key][i, :nl])
         assert int(multi.last_pair_status.sum()) == 0
         multi.close()
+
+
+def test_fast_row_band_path_vs_oracle(monkeypatch):
+    """k_fast_cells keeps a work list of half a cell's pixels; a cell with more passing pixels is walked in bands of rows (all bands
+    scored first, then listed again, cut at the threshold, suppressed and emitted in row order).  B200ORB_FAST_LC (read when an
+    extractor plans its geometry) shrinks the list to 64 entries so that ordinary cells take that path as well: same keypoints and
+    descriptors as the oracle on a textured scene, on noise (every cell dense) and on a low-contrast scene (minThFAST retries)."""
+    from pyorbslam_b200.synthetic import make_kitti_like_pair
+    monkeypatch.setenv("B200ORB_FAST_LC", "64")
+    rng = np.random.default_rng(17)
+    H, W = 230, 410
+    scene = make_kitti_like_pair(5, H, W)[0]
+    imgs = [scene, rng.integers(0, 256, (H, W), dtype=np.uint8), (scene // 4 + 90).astype(np.uint8)]
+    params = (1500, 1.2, 5, 20, 7)
+    for img in imgs:
+        ko, do = O.OracleExtractor(*params).extract_arrays(img)
+        kg, dg = ORBextractor(*params).extract_arrays(img)
+        _same(kg, dg, ko, do)
+    monkeypatch.delenv("B200ORB_FAST_LC")
+    kg, dg = ORBextractor(*params).extract_arrays(imgs[1])          # and the default capacity on the dense image
+    ko, do = O.OracleExtractor(*params).extract_arrays(imgs[1])
+    _same(kg, dg, ko, do)
+
+
+@pytest.mark.parametrize("lanes", ["1", "2"])
+def test_run_host_lanes_and_half_chunks_equal_device_path(monkeypatch, lanes):
+    """run_host alternates chunks between two compute lanes (own stream + workspace) and, for engines of 16 pairs or more, cuts the
+    job into half-capacity chunks with a ramp at both ends; B200ORB_HOST_LANES=1 keeps one lane and full chunks.  Either way every
+    output equals what the device API gives chunk by chunk (70 pairs through a 16-pair engine: ramp 2, 4 | 8 ... | 4, 2)."""
+    import torch
+    from pyorbslam_b200 import StereoFrontend
+    from pyorbslam_b200.synthetic import make_kitti_like_pair
+    monkeypatch.setenv("B200ORB_HOST_LANES", lanes)
+    params = (400, 1.2, 4, 20, 7)
+    H, W, n, P = 120, 320, 70, 16
+    base = [make_kitti_like_pair(80 + i, H, W) for i in range(7)]
+    left = torch.from_numpy(np.stack([np.roll(base[i % 7][0], 5 * (i // 7), axis=1) for i in range(n)])).pin_memory()
+    right = torch.from_numpy(np.stack([np.roll(base[i % 7][1], 5 * (i // 7), axis=1) for i in range(n)])).pin_memory()
+    fe = StereoFrontend(*params, H, W, P)
+    host = fe.run_host(left, right, 90.0, 300.0)
+    ref = StereoFrontend(*params, H, W, P)
+    for c in range(0, n, P):
+        m = min(P, n - c)
+        dev = ref.run(left[c:c + m].cuda(), right[c:c + m].cuda(), 90.0, 300.0)
+        ref.check_status(m)
+        dev = {k: v.cpu() for k, v in dev.items()}
+        assert torch.equal(host["nkp"][:, c:c + m], dev["nkp"][:, :m]), c
+        for i in range(m):
+            nl, nr = int(dev["nkp"][0, i]), int(dev["nkp"][1, i])
+            for side, k in ((0, nl), (1, nr)):
+                assert torch.equal(host["kps"][side, c + i, :k], dev["kps"][side, i, :k]) and torch.equal(host["desc"][side, c + i, :k], dev["desc"][side, i, :k]), (c, i)
+            for key in ("uRight", "depth", "matchIdx"):
+                assert torch.equal(host[key][c + i, :nl], dev[key][i, :nl]), (key, c, i)
+    assert int(host["nkp"].min()) > 50
