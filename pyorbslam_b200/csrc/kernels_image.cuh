@@ -350,11 +350,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
 // ------------------------------------------------------------------------------------------------
 // K2: FAST-9/16 per 30-px cell with the iniThFAST -> minThFAST retry (ORBextractor.cpp:788-828) and
 // cv::FAST's cell-confined strict non-max suppression.
-// Persistent, barrier-free: every WARP is an independent worker that walks the cells c = global warp id, + total warps, ...
-// of the whole launch (all images, all levels).  A cell's raw window (detection area + 3-px rim) is staged in the warp's private
+// Persistent, barrier-free: every WARP is an independent worker that claims cells of the whole launch (all images, all levels) from
+// a global counter; the cell's geometry comes from a host-built table.  A cell's raw window (detection area + 3-px rim) is staged in the warp's private
 // shared-memory buffer by ONE tensor-map TMA copy (cp.async.bulk.tensor.3d of a BW x BH box at the cell's pixel coordinates,
 // completion counted on the warp's own mbarrier); the copy of the NEXT cell is issued as soon as the current cell's last
-// scoring pass is done, so it lands underneath the NMS / emission work and nobody ever waits at a block-wide barrier (the
+// scoring pass and NMS are done, so it lands underneath the emission and the next cell's set-up and nobody ever waits at a
+// block-wide barrier (the
 // strip-per-CTA version lost 22 % of its warp time there; per-row bulk copies issued by 32 lanes cost ~10 instructions each).
 // Per cell: quick reject of every pixel at both thresholds -> row bitmaps -> ordered work list -> exact corner strength ->
 // strict NMS inside the cell's own detection window, at iniThFAST first and at minThFAST only if nothing survived ->
@@ -381,7 +382,7 @@ __device__ __forceinline__ bool fast_quick(const u8* p, int SP, int t) {
     return br | dk;
 }
 
-// The same reject for FOUR consecutive pixels of a row (address o, o & 3 == AL) from aligned 32-bit shared-memory words, for BOTH
+// The same reject for FOUR consecutive pixels of a row (a word-aligned group) from aligned 32-bit shared-memory words, for BOTH
 // thresholds at once (iniThFAST and minThFAST, ORBextractor.cpp:808-815): the five operands (centre, x-3, x+3, y-3, y+3) are cut
 // out of the words with funnel shifts, spread into 16-bit lanes (pixels 0|2 and 1|3) and tested two pixels per instruction with
 // the packed min / max (VIMNMX.U16x2):
