@@ -191,6 +191,12 @@ int b200orb_batch_profile_read(b200orb_batch* b, float* ms_per_stage, int* n_cal
 /* kernel launches per stage of one b200orb_batch_run_device call */
 int b200orb_batch_stage_launches(const b200orb_batch* b, int* launches_per_stage);
 
+/* Host logic, no GPU needed: the chunk sizes b200orb_batch_run_host cuts a job of n_pairs into for an engine of max_pairs with
+ * `lanes` compute lanes (1 or 2; run_host uses 2 unless B200ORB_HOST_LANES=1): half-capacity chunks with two lanes, a ramp
+ * C/4, C/2 at both ends of a job of at least four chunks.  Writes at most `capacity` sizes (sizes may be NULL) and returns the
+ * number of chunks (the reference has no counterpart: Tracking.py:95-112 builds one Frame per call). */
+int b200orb_host_chunk_schedule(int max_pairs, int lanes, int n_pairs, int32_t* sizes, int capacity);
+
 /* ---------------------------------------------------------------------------------------------
  * BoW transform of the descriptors -- the tree descent of
  * TemplatedVocabulary.transform_feature (pyDBoW/TemplatedVocabulary.py:139-163) with FORB.distance

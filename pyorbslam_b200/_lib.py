@@ -63,11 +63,22 @@ def lib():
     l.b200orb_batch_candidate_count.argtypes = [vp, i32, C.POINTER(C.c_longlong)]
     l.b200orb_batch_profile.argtypes = [vp, i32, i32]
     l.b200orb_batch_stage_launches.argtypes = [vp, vp]
+    l.b200orb_host_chunk_schedule.argtypes = [i32, i32, i32, vp, i32]
     l.b200orb_batch_profile_read.argtypes = [vp, vp, C.POINTER(i32), C.POINTER(C.c_longlong)]
     l.b200orb_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     l.b200orb_host_free.argtypes = [vp]
     _lib = l
     return l
+
+
+def chunk_schedule(max_pairs, lanes, n_pairs):
+    """Chunk sizes b200orb_batch_run_host cuts a job into (pure host logic, no GPU needed)."""
+    n = lib().b200orb_host_chunk_schedule(int(max_pairs), int(lanes), int(n_pairs), None, 0)
+    if n < 0:
+        check(n)
+    buf = (C.c_int32 * n)()
+    lib().b200orb_host_chunk_schedule(int(max_pairs), int(lanes), int(n_pairs), buf, n)
+    return list(buf)
 
 
 def check(rc):

@@ -1255,6 +1255,34 @@ int b200orb_batch_profile_read(b200orb_batch* b, float* ms_per_stage, int* n_cal
     return 0;
 }
 
+// Chunk schedule of run_host: full chunks with a short ramp at both ends of a long job (C/4, C/2, C ... C, C/2, C/4) so that the
+// first kernels start after a quarter-chunk upload and only a quarter-chunk download is left when the last kernels finish.
+// With two compute lanes the chunk C is half the engine's capacity: a chunk's kernels then take longer than the next chunk's
+// upload, so consecutive chunks do overlap on the GPU (with full chunks the next upload ends just as the kernels do), and the
+// job ends half as long after its last upload.
+static std::vector<int> host_chunk_schedule(int max_pairs, int lanes, int n_pairs) {
+    std::vector<int> sizes, tail;
+    const int P = (lanes == 2 && max_pairs >= 16) ? max_pairs / 2 : max_pairs;
+    int left = n_pairs;
+    if (n_pairs >= 4 * P && P >= 8) {
+        static const int min_tail = [] { const char* v = getenv("B200ORB_HOST_MIN_TAIL"); return v ? std::max(1, atoi(v)) : 0; }();
+        sizes.push_back(P / 4); sizes.push_back(P / 2);
+        left -= P / 4 + P / 2;
+        // the job ends one chunk latency after its last upload: taper the last chunks down to min_tail pairs (default C/4)
+        for (int c = P / 2; c >= std::max(min_tail ? min_tail : P / 4, 1) && c >= 4; c /= 2) { tail.push_back(c); left -= c; }
+    }
+    while (left > 0) { const int c = std::min(P, left); sizes.push_back(c); left -= c; }
+    sizes.insert(sizes.end(), tail.begin(), tail.end());
+    return sizes;
+}
+
+int b200orb_host_chunk_schedule(int max_pairs, int lanes, int n_pairs, int32_t* sizes, int capacity) {
+    if (max_pairs < 1 || n_pairs < 1 || lanes < 1 || lanes > 2) return fail(B200ORB_E_ARG, "bad schedule arguments");
+    const std::vector<int> v = host_chunk_schedule(max_pairs, lanes, n_pairs);
+    if (sizes) for (int i = 0; i < (int)v.size() && i < capacity; ++i) sizes[i] = v[i];
+    return (int)v.size();
+}
+
 static int batch_host_setup(b200orb_batch* b) {
     if (b->host_ready) return 0;
     const Plan& P = b->eng.hp.P;
@@ -1313,26 +1341,7 @@ int b200orb_batch_run_host_shard(b200orb_batch* b, const uint8_t* h_left, const 
         b->h_status_cap = n_pairs;
     }
     b->h_status_n = n_pairs;
-    // chunk schedule: full chunks of max_pairs, with a short ramp at both ends of a long job (P/4, P/2, P ... P, P/2, P/4) so that the
-    // first kernels start after a quarter-chunk upload and only a quarter-chunk download is left when the last kernels finish
-    // With two compute lanes the chunks are half the engine's capacity: a chunk's kernels then take longer than the next chunk's
-    // upload, so consecutive chunks do overlap on the GPU (with full chunks the next upload ends just as the kernels do), and the
-    // job ends half as long after its last upload.
-    std::vector<int> sizes;
-    {
-        const int P = (b->lanes == 2 && b->P >= 16) ? b->P / 2 : b->P;
-        int left = n_pairs;
-        std::vector<int> tail;
-        if (n_pairs >= 4 * P && P >= 8) {
-            static const int min_tail = [] { const char* v = getenv("B200ORB_HOST_MIN_TAIL"); return v ? std::max(1, atoi(v)) : 0; }();
-            sizes.push_back(P / 4); sizes.push_back(P / 2);
-            left -= P / 4 + P / 2;
-            // the job ends one chunk latency after its last upload: taper the last chunks down to min_tail pairs (default P/4)
-            for (int c = P / 2; c >= std::max(min_tail ? min_tail : P / 4, 1) && c >= 4; c /= 2) { tail.push_back(c); left -= c; }
-        }
-        while (left > 0) { const int c = std::min(P, left); sizes.push_back(c); left -= c; }
-        sizes.insert(sizes.end(), tail.begin(), tail.end());
-    }
+    const std::vector<int> sizes = host_chunk_schedule(b->P, b->lanes, n_pairs);
     // B200ORB_HOST_TRACE=1: per-chunk completion times of upload / kernels / download on stderr (diagnostic; extra timing events)
     static const bool trace = [] { const char* v = getenv("B200ORB_HOST_TRACE"); return v && atoi(v) != 0; }();
     std::vector<cudaEvent_t> tev;

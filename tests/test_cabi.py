@@ -82,3 +82,25 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "liborb_oracle" not in txt and "oracle/_ref" not in txt, f
+
+
+def test_run_host_chunk_schedule_host_logic():
+    """b200orb_host_chunk_schedule (pure host logic behind b200orb_batch_run_host): every pair lands in exactly one chunk, no chunk
+    exceeds the engine, half-capacity chunks on two lanes, a C/4, C/2 ramp at both ends of jobs of at least four chunks."""
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        P = int(rng.integers(1, 300)); n = int(rng.integers(1, 5000)); lanes = int(rng.integers(1, 3))
+        s = _lib.chunk_schedule(P, lanes, n)
+        C = P // 2 if (lanes == 2 and P >= 16) else P
+        assert sum(s) == n and min(s) >= 1 and max(s) <= C
+        if n >= 4 * C and C >= 8:
+            assert s[:2] == [C // 4, C // 2] and s[-1] <= C // 2 and s[-2] >= s[-1]          # ramp up, taper down
+            assert s[2:-3].count(C) >= len(s[2:-3]) - 1              # full chunks in between, at most one remainder chunk
+        else:
+            assert s[:-1] == [C] * (len(s) - 1)
+    # the bench's end-to-end job: 2048 pairs through a 128-pair engine
+    assert _lib.chunk_schedule(128, 2, 2048) == [16, 32] + [64] * 30 + [32, 32, 16]
+    assert _lib.chunk_schedule(128, 1, 2048) == [32, 64] + [128] * 14 + [64, 64, 32]
+    assert _lib.chunk_schedule(2, 2, 3) == [2, 1]
+    with pytest.raises(ValueError):
+        _lib.chunk_schedule(0, 1, 5)
