@@ -316,6 +316,7 @@ int build_plan(const Params& prm, int H, int W, HostPlan& hp) {
 // Engine: workspace for S image slots + the kernel sequence
 // ------------------------------------------------------------------------------------------------
 constexpr int kStatusBanks = 4;      // = b200orb_batch::NBUF
+constexpr int kMaxDynSmem = 200 * 1024;   // upper bound of the dynamic shared memory any launch of k_fast_cells / k_octree asks for
 struct Engine {
     Params prm;
     HostPlan hp;
@@ -441,9 +442,12 @@ struct Engine {
         }
         if (!hp.ytab.empty()) CU_TRY(cudaMemcpy(d_ytab, hp.ytab.data(), hp.ytab.size() * sizeof(YTab), cudaMemcpyHostToDevice));
         TRY(make_level_maps());
-        CU_TRY(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.fast_smem));
+        // the attribute is per kernel and device, not per engine: every engine sets the same upper bound (the most any geometry may ask
+        // for), or an engine planned later with a smaller need would make the launches of an earlier one fail
+        CU_TRY(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
         CU_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
-        CU_TRY(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.oct_smem));
+        if ((int)hp.oct_smem > kMaxDynSmem || (int)hp.fast_smem > kMaxDynSmem) return fail(B200ORB_E_ARG, "kernel shared memory beyond the per-CTA limit");
+        CU_TRY(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
         planned = true;
         return 0;
     }

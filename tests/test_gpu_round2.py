@@ -228,3 +228,19 @@ def test_run_host_lanes_and_half_chunks_equal_device_path(monkeypatch, lanes):
             for key in ("uRight", "depth", "matchIdx"):
                 assert torch.equal(host[key][c + i, :nl], dev[key][i, :nl]), (key, c, i)
     assert int(host["nkp"].min()) > 50
+
+
+def test_extractors_of_different_geometry_interleave():
+    """The dynamic shared-memory ceiling of a kernel is a per-device attribute, not a per-object one: an extractor with a small
+    octree / FAST footprint planned AFTER a large one must not break the large one's next launch (the attribute used to be set to
+    each plan's own need).  Also: objects keep their own tensor maps, tables and workspaces when used alternately."""
+    big_p, small_p = (30000, 1.2, 4, 20, 7), (300, 1.5, 3, 20, 7)
+    rng = np.random.default_rng(23)
+    noise = rng.integers(0, 256, (300, 620), dtype=np.uint8)
+    scene = make_stereo_pair(12, 150, 260)[0]
+    big, small = ORBextractor(*big_p), ORBextractor(*small_p)
+    for rnd in range(2):
+        a = np.roll(noise, 3 * rnd, axis=1)
+        b = np.roll(scene, 2 * rnd, axis=0)
+        _same(*big.extract_arrays(a), *O.OracleExtractor(*big_p).extract_arrays(a))
+        _same(*small.extract_arrays(b), *O.OracleExtractor(*small_p).extract_arrays(b))
