@@ -1300,7 +1300,13 @@ static int batch_host_setup(b200orb_batch* b) {
         CU_TRY(cudaStreamCreateWithFlags(&b->s_comp2, cudaStreamNonBlocking));
         b->eng2 = new Engine;
         b->eng2->prm = b->eng.prm; b->eng2->device = b->eng.device;
-        TRY(b->eng2->plan(b->H, b->W, 2 * b->P));
+        if (b->eng2->plan(b->H, b->W, 2 * b->P) != 0) {      // no room for a second workspace: one lane, full chunks
+            b->eng2->release();
+            delete b->eng2;
+            b->eng2 = nullptr; b->lanes = 1;
+            cudaGetLastError();
+            cudaStreamDestroy(b->s_comp2); b->s_comp2 = nullptr;
+        }
     }
     for (int i = 0; i < b200orb_batch::NBUF; ++i) {
         CU_TRY(cudaEventCreateWithFlags(&b->ev_in[i], cudaEventDisableTiming));
