@@ -95,10 +95,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_co
     const int slot = blockIdx.y, lane = threadIdx.x & 31;
     // the moment table goes to shared memory once per CTA, the float pattern into registers once per warp; every warp then
     // walks DESC_KPW consecutive keypoints
-    __shared__ uint2 s_mtab[4 * MOM_STEPS * 32];
     __shared__ __align__(128) u8 s_patch[DESC_WARPS * DESC_WIN];   // per warp: 37 rows x DESC_PP bytes of the blurred level (one TMA box)
     __shared__ unsigned long long s_bar[DESC_WARPS];
-    for (int k = threadIdx.x; k < 4 * MOM_STEPS * 32; k += DESC_WARPS * 32) s_mtab[k] = __ldg(mtab + k);
     __shared__ float4 s_fpat[256];
     for (int k = threadIdx.x; k < 256; k += DESC_WARPS * 32) s_fpat[k] = __ldg(fpat + k);
     // level of keypoint i: lanes hold the running ends of the per-level counts
@@ -146,12 +144,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(const __grid_co
         const int rsub = (lane * 57) >> 9, k = lane - 9 * rsub;   // lane / 9, lane % 9
         const int wpr = G.pitch >> 2;
         const u32* p = reinterpret_cast<const u32*>(c0 - al) + (ptrdiff_t)((rsub - 15) * wpr + k);
-        const uint2* tb = s_mtab + al * (MOM_STEPS * 32) + lane;
+        const uint2* tb = mtab + al * (MOM_STEPS * 32) + lane;          // 11 KB table, read through L1 (in shared memory it cost a CTA per SM)
         const ptrdiff_t step = 3 * wpr;
 #pragma unroll
         for (int s = 0; s < MOM_STEPS; ++s, p += step) {
             const u32 w = *p;
-            const uint2 cf = tb[s * 32];
+            const uint2 cf = __ldg(tb + s * 32);
             m10 = dp4a_us(w, cf.x, m10);
             m01 = dp4a_us(w, cf.y, m01);
         }
