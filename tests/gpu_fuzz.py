@@ -2,7 +2,9 @@
 noise, low-contrast scenes that send most cells through the minThFAST retry) and extractor parameters (1-8 levels, scale factors
 1.1-2.0, quotas 50-4000, several threshold pairs); extractor outputs bit-exact, then stereo (uRight, depth, match index) bit-exact
 or both sides raising IndexError.  `python tests/gpu_fuzz.py [seed] [cases]` on a GPU box; tests/test_gpu_parity.py runs a small
-batch.  1110 single-image cases (seeds 1, 7, 11, 21) and 85 batch-engine cases (seeds 3, 22) passed with 0 mismatches at the end of round 1."""
+batch.  1110 single-image cases (seeds 1, 7, 11, 21) and 85 batch-engine cases (seeds 3, 22) passed with 0 mismatches at the end of round 1;
+round 2: 1680 single-image and 100 batch-engine cases, 0 mismatches (the last 460 on the final FAST kernel, 60 of them with
+B200ORB_FAST_LC=128, i.e. through the row-band path)."""
 import os
 import sys
 import time
