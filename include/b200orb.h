@@ -197,6 +197,13 @@ int b200orb_batch_stage_launches(const b200orb_batch* b, int* launches_per_stage
  * number of chunks (the reference has no counterpart: Tracking.py:95-112 builds one Frame per call). */
 int b200orb_host_chunk_schedule(int max_pairs, int lanes, int n_pairs, int32_t* sizes, int capacity);
 
+/* Host logic, no GPU needed: the FAST cell grid the engine plans for an H x W image -- the cells of ComputeKeyPointsOctTree's loops
+ * (ORBextractor.cpp:770-806) in loop order, all levels.  Six ints per cell: level, iniX, iniY (window origin in level coordinates,
+ * 3-px rim included), detection width and height (window minus the rim; 0 x 0 = a cell the reference skips or FAST cannot fill),
+ * offset of the cell's candidate segment.  Writes at most `capacity` cells (cells may be NULL), returns the number of cells. */
+int b200orb_plan_cells(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int H, int W, int32_t* cells,
+                       int capacity);
+
 /* ---------------------------------------------------------------------------------------------
  * BoW transform of the descriptors -- the tree descent of
  * TemplatedVocabulary.transform_feature (pyDBoW/TemplatedVocabulary.py:139-163) with FORB.distance

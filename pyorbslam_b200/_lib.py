@@ -64,11 +64,24 @@ def lib():
     l.b200orb_batch_profile.argtypes = [vp, i32, i32]
     l.b200orb_batch_stage_launches.argtypes = [vp, vp]
     l.b200orb_host_chunk_schedule.argtypes = [i32, i32, i32, vp, i32]
+    l.b200orb_plan_cells.argtypes = [i32, f32, i32, i32, i32, i32, i32, vp, i32]
     l.b200orb_batch_profile_read.argtypes = [vp, vp, C.POINTER(i32), C.POINTER(C.c_longlong)]
     l.b200orb_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     l.b200orb_host_free.argtypes = [vp]
     _lib = l
     return l
+
+
+def plan_cells(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, H, W):
+    """FAST cell grid the engine plans for an H x W image: int32 array [cells][level, iniX, iniY, cw, ch, cand_ofs] (host logic)."""
+    import numpy as np
+    args = (int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST), int(H), int(W))
+    n = lib().b200orb_plan_cells(*args, None, 0)
+    if n < 0:
+        check(n)
+    out = np.zeros((n, 6), np.int32)
+    lib().b200orb_plan_cells(*args, out.ctypes.data_as(C.c_void_p), n)
+    return out
 
 
 def chunk_schedule(max_pairs, lanes, n_pairs):

@@ -1280,6 +1280,24 @@ static std::vector<int> host_chunk_schedule(int max_pairs, int lanes, int n_pair
     return sizes;
 }
 
+int b200orb_plan_cells(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int H, int W, int32_t* cells,
+                       int capacity) {
+    Params prm;
+    TRY(make_params(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, prm));
+    HostPlan* hp = new HostPlan;
+    const int r = build_plan(prm, H, W, *hp);
+    if (r) { delete hp; return r; }
+    const int n = hp->fast_cells;
+    for (int i = 0; cells && i < n && i < capacity; ++i) {
+        const uint4 t = hp->celltab[i];
+        int32_t* o = cells + 6 * (size_t)i;
+        o[0] = (int)(t.y >> 16); o[1] = (int)(t.x & 0xffffu); o[2] = (int)(t.x >> 16);
+        o[3] = (int)(t.y & 0xffu); o[4] = (int)((t.y >> 8) & 0xffu); o[5] = (int)t.z;
+    }
+    delete hp;
+    return n;
+}
+
 int b200orb_host_chunk_schedule(int max_pairs, int lanes, int n_pairs, int32_t* sizes, int capacity) {
     if (max_pairs < 1 || n_pairs < 1 || lanes < 1 || lanes > 2) return fail(B200ORB_E_ARG, "bad schedule arguments");
     const std::vector<int> v = host_chunk_schedule(max_pairs, lanes, n_pairs);

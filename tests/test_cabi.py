@@ -104,3 +104,62 @@ def test_run_host_chunk_schedule_host_logic():
     assert _lib.chunk_schedule(2, 2, 3) == [2, 1]
     with pytest.raises(ValueError):
         _lib.chunk_schedule(0, 1, 5)
+
+
+def _reference_cells(w, h):
+    """The cell loops of ComputeKeyPointsOctTree (ORBextractor.cpp:770-806) restated: (iniX, iniY, cw, ch) per (row, column) with
+    cw = ch = 0 for the cells the loops `continue` over; detection area = FAST window minus its 3-px rim."""
+    f32 = np.float32
+    min_b, max_bx, max_by = 16, w - 19 + 3, h - 19 + 3                      # EDGE_THRESHOLD - 3, cols/rows - EDGE_THRESHOLD + 3
+    width, height = f32(max_bx - min_b), f32(max_by - min_b)
+    n_cols, n_rows = int(width / f32(30)), int(height / f32(30))
+    if n_cols <= 0 or n_rows <= 0:
+        return []
+    w_cell, h_cell = int(np.ceil(width / f32(n_cols))), int(np.ceil(height / f32(n_rows)))
+    cells = []
+    for i in range(n_rows):
+        ini_y = min_b + i * h_cell
+        max_y = min(ini_y + h_cell + 6, max_by)
+        for j in range(n_cols):
+            ini_x = min_b + j * w_cell
+            max_x = min(ini_x + w_cell + 6, max_bx)
+            skipped = ini_y >= max_by - 3 or ini_x >= max_bx - 6 or max_x - ini_x < 7 or max_y - ini_y < 7      # :793, :801, FAST needs 7 px
+            cells.append((ini_x, ini_y, 0, 0) if skipped else (ini_x, ini_y, max_x - ini_x - 6, max_y - ini_y - 6))
+    return cells
+
+
+@pytest.mark.parametrize("H,W,params", [(376, 1241, (2000, 1.2, 8, 20, 7)), (200, 480, (800, 1.2, 5, 20, 7)), (131, 257, (300, 1.5, 4, 20, 7)),
+                                        (90, 300, (500, 2.0, 3, 20, 7))])
+def test_planned_fast_cells_are_the_reference_loops_cells(H, W, params):
+    """b200orb_plan_cells (host logic: the table k_fast_cells walks) against the restated loops on the oracle's level sizes, and
+    against what the reference itself found: every FAST candidate of the compiled reference lies in the detection area of exactly
+    one planned cell, and no cell holds more candidates than its segment has room for."""
+    from pyorbslam_b200.synthetic import make_kitti_like_pair
+    img = make_kitti_like_pair(3, H, W)[0]
+    o = O.OracleExtractor(*params)
+    o.extract_arrays(img)
+    cells = _lib.plan_cells(*params, H, W)
+    k = 0
+    for l in range(params[2]):
+        w, h = o.level_size(l)
+        ref = _reference_cells(w, h)
+        mine = cells[k:k + len(ref)]
+        assert len(mine) == len(ref) and (mine[:, 0] == l).all()
+        for (x, y, cw, ch), m in zip(ref, mine):
+            assert (int(m[3]), int(m[4])) == (cw, ch)
+            if cw:
+                assert (int(m[1]), int(m[2])) == (x, y)
+        cand = o.level_candidates(l)                                        # x, y relative to (16, 16), score
+        hits = np.zeros(len(cand), np.int32)
+        caps = np.append(cells[k + 1:k + len(ref), 5], 0) - mine[:, 5] if len(ref) else []
+        for n_c, m in enumerate(mine):
+            if m[3] == 0:
+                continue
+            x0, y0 = m[1] + 3 - 16, m[2] + 3 - 16
+            inside = (cand[:, 0] >= x0) & (cand[:, 0] < x0 + m[3]) & (cand[:, 1] >= y0) & (cand[:, 1] < y0 + m[4])
+            hits += inside
+            if n_c + 1 < len(mine):
+                assert inside.sum() <= caps[n_c]
+        assert (hits == 1).all()
+        k += len(ref)
+    assert k == len(cells)
